@@ -1,0 +1,52 @@
+// common.cuh -- error plumbing and small helpers shared by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define RCOT_OK 0
+#define RCOT_ERR_ARG (-1)
+#define RCOT_ERR_CUDA (-2)
+#define RCOT_ERR_ARCH (-3)
+
+namespace rcot {
+
+void set_error(const char* fmt, ...);  // api.cu
+int check_launch(const char* what);    // api.cu: cudaPeekAtLastError -> error code
+
+#define RCOT_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      rcot::set_error(__VA_ARGS__);    \
+      return RCOT_ERR_ARG;             \
+    }                                  \
+  } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return ((a + b - 1) / b) * b; }
+
+// Tiling of the N (output-channel) dimension of a pixel-as-M GEMM.
+// One CTA owns up to NSUB accumulators of BN columns each (NSUB*BN <= 512 TMEM columns);
+// `passes` CTAs along grid.y cover all of N.
+struct NPlan {
+  int N, BN, nsub_total, NSUB, passes;
+};
+static inline NPlan make_nplan(int N) {
+  NPlan p;
+  p.N = N;
+  if (N <= 256) {
+    p.nsub_total = 1;
+    p.BN = round_up(N, 16);
+    p.NSUB = 1;
+    p.passes = 1;
+  } else {
+    p.nsub_total = cdiv(N, 256);
+    p.BN = round_up(cdiv(N, p.nsub_total), 16);
+    p.NSUB = 2;
+    p.passes = cdiv(p.nsub_total, 2);
+  }
+  return p;
+}
+
+}  // namespace rcot

@@ -1,0 +1,211 @@
+// tc.cuh -- sm_100a primitives: mbarrier, 1-D bulk TMA copy, TMEM allocation,
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) and tcgen05.ld, plus the
+// no-swizzle K-major operand layout every GEMM-shaped kernel in this library uses.
+//
+// Operand layout (shared memory, "core matrix" = 8 rows x 16 bytes, stored as 128
+// contiguous bytes): element (row r, k) of a [rows x KC] bf16 tile lives at
+//     (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2        bytes
+// with LBO = 128 (core matrices adjacent in K are contiguous) and SBO = (KC/8)*128.
+// Threads produce the operands (fp32 -> bf16 hi [+ lo]), so no TMA swizzle mode has
+// to be matched; weights are pre-packed in this layout in HBM and brought in with
+// cp.async.bulk (UBLKCP).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace rcot {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a barrier that never completes traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 3000000000LL) {
+      printf("rcot: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completes on `bar`.
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// Make generic-proxy shared-memory writes visible to the async proxy (tensor core / TMA).
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ TMEM
+// One full warp calls alloc/dealloc. ncols: power of two in [32, 512].
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__host__ __device__ inline uint32_t tmem_cols_pow2(uint32_t n) {
+  uint32_t c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+// ------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor, SWIZZLE_NONE, K-major (bit layout as documented for
+// sm_100 UMMA: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48)).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, M x N tile.
+__host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on `bar` when all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------ TMEM -> registers
+// 32x32b: thread t of warp w reads lane 32*(w%4)+t, consecutive columns.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t tmem_lane_base(uint32_t tmem_base) {
+  // lane field is bits [31:16]; each warp may only touch its own 32-lane quarter.
+  return tmem_base + ((((threadIdx.x >> 5) & 3u) * 32u) << 16);
+}
+
+// ------------------------------------------------------------------ operand packing
+constexpr int KC = 32;                 // K elements per pipeline stage
+constexpr uint32_t OP_LBO = 128;       // bytes between core matrices adjacent in K
+constexpr uint32_t OP_SBO = (KC / 8) * 128;  // bytes between 8-row groups
+
+__device__ __host__ inline uint32_t op_offset(int row, int k) {  // k in [0,KC)
+  return (uint32_t)(row >> 3) * OP_SBO + (uint32_t)(k >> 3) * OP_LBO + (uint32_t)(row & 7) * 16u +
+         (uint32_t)(k & 7) * 2u;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// Split 8 fp32 values into bf16 hi and lo (x ~= hi + lo, |err| <= 2^-17 |x|).
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2bfloat16_rn(v[i]);
+    l[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h[i]));
+  }
+  hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+  lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+// Store 8 consecutive-k values of one operand row (k8 = k/8 within the stage).
+template <int TERMS>
+__device__ __forceinline__ void op_store8(uint8_t* hi_tile, uint8_t* lo_tile, int row, int k8, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  uint32_t off = (uint32_t)(row >> 3) * OP_SBO + (uint32_t)k8 * OP_LBO + (uint32_t)(row & 7) * 16u;
+  *reinterpret_cast<uint4*>(hi_tile + off) = hi;
+  if (TERMS > 1) *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+}
+
+// Issue the MMAs of one K stage (KC = 2 k16 steps) for one [128 x BN] accumulator.
+// TERMS==3: hi*hi + lo*hi + hi*lo (fp32-class accuracy); TERMS==1: hi*hi (bf16 compute).
+template <int TERMS>
+__device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                            uint32_t b_lo, uint32_t idesc, bool first_stage) {
+#pragma unroll
+  for (int s = 0; s < KC / 16; ++s) {
+    uint32_t ko = s * 2 * OP_LBO;
+    uint64_t dah = make_sdesc(a_hi + ko, OP_LBO, OP_SBO);
+    uint64_t dbh = make_sdesc(b_hi + ko, OP_LBO, OP_SBO);
+    tc_mma_bf16(tmem_d, dah, dbh, idesc, (first_stage && s == 0) ? 0u : 1u);
+    if (TERMS > 1) {
+      uint64_t dal = make_sdesc(a_lo + ko, OP_LBO, OP_SBO);
+      uint64_t dbl = make_sdesc(b_lo + ko, OP_LBO, OP_SBO);
+      tc_mma_bf16(tmem_d, dal, dbh, idesc, 1u);
+      tc_mma_bf16(tmem_d, dah, dbl, idesc, 1u);
+    }
+  }
+}
+
+}  // namespace rcot
