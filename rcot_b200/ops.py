@@ -1,0 +1,180 @@
+"""Thin ctypes bindings: torch tensors -> raw pointers -> ``librcot_b200.so`` (include/rcot_b200.h).
+
+Every function launches asynchronously on ``torch.cuda.current_stream()`` and allocates outputs
+with torch's caching allocator (the library never allocates).  No op has a PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+TERMS = 3  # default GEMM precision: 3 = bf16x3 split (fp32-class), 1 = single bf16 product
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int32), ("K", C.c_int32),
+                ("R", C.c_int32), ("s_kouter", C.c_int32), ("s_n", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PMParams(C.Structure):
+    _fields_ = [
+        ("in_", C.c_void_p), ("in2", C.c_void_p), ("in_bs", C.c_int64), ("in2_bs", C.c_int64),
+        ("C1", C.c_int32), ("C2", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32),
+        ("Hr", C.c_int32), ("Wr", C.c_int32), ("B", C.c_int32),
+        ("ks", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("mode", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
+        ("wpack", C.c_void_p), ("wpack_bs", C.c_int64), ("N", C.c_int32), ("terms", C.c_int32),
+        ("out", C.c_void_p), ("out_bs", C.c_int64), ("out_coff", C.c_int32), ("act", C.c_int32),
+        ("slope", C.c_float), ("accumulate", C.c_int32), ("bias", C.c_void_p),
+        ("mask_y", C.c_void_p), ("mask_bs", C.c_int64), ("residual", C.c_void_p), ("res_bs", C.c_int64),
+    ]
+
+
+class PKParams(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("a_bs", C.c_int64), ("CA", C.c_int32),
+        ("b", C.c_void_p), ("b2", C.c_void_p), ("b_bs", C.c_int64), ("b2_bs", C.c_int64),
+        ("CB1", C.c_int32), ("CB2", C.c_int32),
+        ("Ha", C.c_int32), ("Wa", C.c_int32), ("Hb", C.c_int32), ("Wb", C.c_int32), ("B", C.c_int32),
+        ("ks", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
+        ("per_image", C.c_int32), ("terms", C.c_int32),
+        ("out", C.c_void_p), ("out_bs", C.c_int64), ("ldo", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+_configured = False
+
+
+def L():
+    global _configured
+    lib = _lib.lib()
+    if not _configured:
+        lib.rcot_packed_bytes.restype = C.c_size_t
+        lib.rcot_packed_bytes.argtypes = [C.c_int, C.c_int]
+        _lib.check(lib.rcot_check_device(), "check_device")
+        _configured = True
+    return lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32(t, name="tensor"):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+def _img_view(t, name="tensor"):
+    """NCHW tensor whose per-image block [C,H,W] is contiguous; returns batch stride in elements."""
+    _f32(t, name)
+    B, Cc, H, W = t.shape
+    if t.stride(3) != 1 or t.stride(2) != W or t.stride(1) != H * W:
+        raise ValueError(f"{name}: per-image block must be contiguous, strides={t.stride()}")
+    return t.stride(0) if B > 1 else Cc * H * W
+
+
+# ------------------------------------------------------------------ weight packing
+def packed_bytes(N: int, K: int) -> int:
+    return int(L().rcot_packed_bytes(N, K))
+
+
+def pack_layout(kind: str, w: torch.Tensor):
+    """(N, K, R, s_kouter, s_n) of the [N x K] view of conv weight ``w`` [Cout, Cin, kh, kw]."""
+    Cout, Cin, kh, kw = w.shape
+    if kind == "fwd":      # B[n=co][k=(ci,ky,kx)]
+        return Cout, Cin * kh * kw, Cin * kh * kw + 1, 0, Cin * kh * kw
+    if kind == "dgrad":    # B[n=ci][k=(co,ky,kx)]
+        return Cin, Cout * kh * kw, kh * kw, Cin * kh * kw, kh * kw
+    raise ValueError(kind)
+
+
+class PackTable:
+    """A set of weight tensors packed by ONE kernel launch into one flat device buffer."""
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = []   # (src tensor, N, K, R, s_kouter, s_n, offset)
+        self.total = 0
+        self.buf = None
+        self.table = None
+        self.max_elems = 0
+
+    def add(self, w: torch.Tensor, kind: str) -> int:
+        N, K, R, sk, sn = pack_layout(kind, w)
+        off = self.total
+        nb = packed_bytes(N, K)
+        self.entries.append((w, N, K, R, sk, sn, off))
+        self.total += (nb + 255) // 256 * 256
+        self.max_elems = max(self.max_elems, nb // 4)
+        return len(self.entries) - 1
+
+    def finalize(self):
+        self.buf = torch.empty(max(self.total, 256), dtype=torch.uint8, device=self.device)
+        arr = (PackDesc * len(self.entries))()
+        for i, (w, N, K, R, sk, sn, off) in enumerate(self.entries):
+            arr[i] = PackDesc(w.data_ptr(), self.buf.data_ptr() + off, N, K, R, sk, sn, 0)
+        raw = bytes(arr)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        return self
+
+    def ptr(self, idx: int) -> int:
+        return self.buf.data_ptr() + self.entries[idx][6]
+
+    def repack(self):
+        """Re-pack every tensor from its current values (call after each optimizer step)."""
+        _lib.check(L().rcot_pack_weights(_ptr(self.table), len(self.entries), C.c_size_t(self.max_elems), _stream()),
+                   "pack_weights")
+
+
+def pack_single(w: torch.Tensor, kind: str):
+    t = PackTable(w.device)
+    t.add(w, kind)
+    t.finalize().repack()
+    return t
+
+
+# ------------------------------------------------------------------ pixel-as-M GEMM
+def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None, out_hw=None, out_coff=0,
+            ln=None, bias=None, act=False, slope=0.2, mask_y=None, residual=None, accumulate=False,
+            wpack_bs=0, terms=None):
+    """out[b, coff+n, p] = epi(sum_k A(b,p,k) W[n,k]).  ``ln`` = (stats[B,HW,2], gamma, beta)."""
+    B, C1, Hs, Ws = x.shape
+    in_bs = _img_view(x, "x")
+    C2 = 0 if x2 is None else x2.shape[1]
+    in2_bs = 0 if x2 is None else _img_view(x2, "x2")
+    if out_hw is None:
+        if mode == 0:
+            out_hw = ((Hs + 2 * pad - ks) // stride + 1, (Ws + 2 * pad - ks) // stride + 1)
+        else:
+            raise ValueError("dgrad needs out_hw")
+    Hr, Wr = out_hw
+    if out is None:
+        out = torch.empty(B, N, Hr, Wr, device=x.device, dtype=torch.float32)
+    out_bs = _img_view(out, "out")
+    p = PMParams()
+    p.in_, p.in2, p.in_bs, p.in2_bs = x.data_ptr(), (None if x2 is None else x2.data_ptr()), in_bs, in2_bs
+    p.C1, p.C2, p.Hs, p.Ws, p.Hr, p.Wr, p.B = C1, C2, Hs, Ws, Hr, Wr, B
+    p.ks, p.stride, p.pad, p.mode = ks, stride, pad, mode
+    if ln is not None:
+        stats, gamma, beta = ln
+        p.ln_stats, p.ln_gamma, p.ln_beta = _f32(stats).data_ptr(), _f32(gamma).data_ptr(), _f32(beta).data_ptr()
+    p.wpack, p.wpack_bs, p.N, p.terms = wpack_ptr, wpack_bs, N, (TERMS if terms is None else terms)
+    p.out, p.out_bs, p.out_coff = out.data_ptr(), out_bs, out_coff
+    p.act, p.slope, p.accumulate = int(act), slope, int(accumulate)
+    p.bias = None if bias is None else _f32(bias).data_ptr()
+    if mask_y is not None:
+        p.mask_y, p.mask_bs = mask_y.data_ptr(), _img_view(mask_y, "mask_y")
+    if residual is not None:
+        p.residual, p.res_bs = residual.data_ptr(), _img_view(residual, "residual")
+    _lib.check(L().rcot_pm_gemm(C.byref(p), _stream()), "pm_gemm")
+    return out
