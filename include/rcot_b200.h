@@ -110,12 +110,82 @@ typedef struct {
   int32_t per_image;    /* 1: out is [B, CA, N] (Gram); 0: reduce over the batch */
   int32_t terms;
   float* out;           /* accumulated with atomics: caller zeroes or accumulates into .grad */
-  int64_t out_bs;
+  int64_t out_bs;       /* per-image stride of out (per_image=1) */
   int32_t ldo;
-  int32_t reserved;
+  int32_t groups;       /* >1: a channels g*CA.., b channels g*CB1.., out + g*out_gs (MDTA heads) */
+  int64_t out_gs;
 } rcot_pk_params;
 
 int rcot_pk_gemm(const rcot_pk_params* p, rcot_stream_t stream);
+
+/* ---------------------------------------------------------------- LayerNorm over channels
+ * Net_Restormer.py:173-200 (WithBias_LayerNorm on the 'b (h w) c' view): stats[b, p] = (mean, rstd)
+ * with biased variance and eps 1e-5; the normalisation itself is applied as a GEMM prologue. */
+int rcot_ln_stats(const float* x, int64_t x_bs, int B, int C, int HW, float* stats, rcot_stream_t stream);
+/* dx = [dy +] LN'(dz); dgamma += sum dz*xhat; dbeta += sum dz  (dy may be NULL; dx may alias dy or dz) */
+int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64_t x_bs, const float* stats,
+                const float* gamma, const float* dy, int64_t dy_bs, float* dx, int64_t dx_bs, float* dgamma,
+                float* dbeta, int B, int C, int HW, rcot_stream_t stream);
+
+/* ---------------------------------------------------------------- depthwise 3x3 (pad 1, no bias)
+ * Net_Restormer.py:26 (qkv_dwconv), :75 + :81-83 (GDFN dwconv, chunk, gelu(x1)*x2).
+ * mode 0: out[ch] = dw(in[ch]); flip=1 gives the data gradient; sumsq[b*nsq+ch] += sum_p out^2 (ch<nsq)
+ * mode 1: out[j] = gelu_erf(dw(in[j])) * dw(in[j+hid])                      (Cn = 2*hid, out has hid)
+ * mode 2: gate backward: out[j] = dg*b*gelu'(a), out[j+hid] = dg*gelu(a); g_out[j] = gelu(a)*b (optional) */
+typedef struct {
+  const float* in;
+  int64_t in_bs;
+  const float* w;       /* [Cn, 1, 3, 3] */
+  float* out;
+  int64_t out_bs;
+  int32_t B, Cn, H, W;
+  int32_t mode, flip, hid, nsq;
+  const float* dg;
+  int64_t dg_bs;
+  float* g_out;
+  int64_t g_bs;
+  float* sumsq;
+} rcot_dw_params;
+int rcot_dwconv3x3(const rcot_dw_params* p, rcot_stream_t stream);
+/* dw[ch, k] += sum_{b,p} dout[b,ch,p] * in[b,ch,p+off_k] */
+int rcot_dwconv3x3_wgrad(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, float* dw, int B,
+                         int Cn, int H, int W, rcot_stream_t stream);
+
+/* ---------------------------------------------------------------- MDTA small-matrix steps
+ * Net_Restormer.py:39-49: normalize(q), normalize(k), softmax(q k^T * temperature), attn @ v,
+ * project_out -- folded into the per-image matrix M = W_out * blockdiag(A). */
+typedef struct {
+  int32_t B, C, heads, reserved;
+  const float* G;            /* [B, heads, c, c] raw q k^T                       (fwd in)  */
+  const float* sumsq;        /* [B, 2C] sum over pixels of q^2 then k^2                    */
+  const float* temperature;  /* [heads]                                                    */
+  const float* w_out;        /* [C, C] project_out.weight                                  */
+  float* A;                  /* [B, heads, c, c] softmax probabilities   (fwd out, bwd in) */
+  float* Gt;                 /* [B, heads, c, c] normalised Gram         (fwd out, bwd in) */
+  void* Mpack;               /* per-image packed M   (N=C, K=C)           (fwd out)        */
+  void* MTpack;              /* per-image packed M^T, may be NULL         (fwd out)        */
+  int64_t pack_bs;           /* bytes between images = rcot_packed_bytes(C, C)             */
+  const float* P;            /* [B, C, C] dy v^T                          (bwd in)         */
+  float* dw_out;             /* [C, C] +=                                  (bwd out)       */
+  float* dtemperature;       /* [heads] +=                                 (bwd out)       */
+  void* W12pack;             /* per-image packed [2C x 2C], zero-initialised by the caller */
+  int64_t pack12_bs;         /* = rcot_packed_bytes(2C, 2C)                                */
+} rcot_attn_params;
+int rcot_attn_fwd(const rcot_attn_params* p, rcot_stream_t stream);
+int rcot_attn_bwd(const rcot_attn_params* p, rcot_stream_t stream);
+
+/* ---------------------------------------------------------------- data movement / small reductions */
+/* PixelShuffle(2) (inverse=0) / PixelUnshuffle(2) (inverse=1), Net_Restormer.py:91,108.
+ * C,H,W describe the [4C,H,W] side; the other side is [C,2H,2W]. */
+int rcot_pixel_shuffle(const float* in, int64_t in_bs, float* out, int64_t out_bs, int B, int C, int H, int W,
+                       int inverse, rcot_stream_t stream);
+/* out = a*x + b*y (y may be NULL); with a_vec: out = a_vec[b]*x + (1-a_vec[b])*y (trainer.py:286) */
+int rcot_axpby(float* out, int64_t out_bs, const float* x, int64_t x_bs, const float* y, int64_t y_bs, float a,
+               float b, const float* a_vec, int B, int64_t n, rcot_stream_t stream);
+/* out[c] += sum_{b,p} x[b,c,p] (bias gradients) */
+int rcot_channel_sum(const float* x, int64_t x_bs, float* out, int B, int C, int HW, rcot_stream_t stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream (graph-capturable) */
+int rcot_zero(void* ptr, size_t bytes, rcot_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -48,4 +48,18 @@ int rcot_check_device(void) {
   return RCOT_OK;
 }
 
+int rcot_zero(void* ptr, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return RCOT_OK;
+  if (ptr == nullptr) {
+    rcot::set_error("rcot_zero: null pointer");
+    return RCOT_ERR_ARG;
+  }
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, stream);
+  if (e != cudaSuccess) {
+    rcot::set_error("rcot_zero: %s", cudaGetErrorString(e));
+    return RCOT_ERR_CUDA;
+  }
+  return RCOT_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,218 @@
+// attn.cu -- the small-matrix steps of MDTA channel attention (Net_Restormer.py:39-49), one CTA per
+// (head, image), everything c x c (c = C/heads in {24,48,96}) in shared memory:
+//   forward : Gt = G / (|q| |k|^T), A = softmax_rows(Gt * temperature), M = W_out * blockdiag(A)
+//             -> M (and M^T) written as per-image packed tcgen05 B operands, so that
+//             project_out(attn @ v) becomes ONE pixel-as-M GEMM  y = x + M v.
+//   backward: from P = dy v^T  ->  dW_out, dtemperature, and the per-image packed matrix
+//             W12 = [[diag(c_q), B_q], [B_q^T, diag(c_k)]] with  [dq; dk] = W12 [q; k]
+//             (softmax backward, L2-normalisation backward folded into c_q, c_k).
+#include "../../include/rcot_b200.h"
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace rcot {
+
+__device__ __forceinline__ float warp_sum_a(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_a(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void store_split(uint8_t* base, int N, int K, int n, int k, float w) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  *reinterpret_cast<__nv_bfloat16*>(base + packed_offset(N, K, n, k, 0)) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(base + packed_offset(N, K, n, k, 1)) = lo;
+}
+
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p) {
+  extern __shared__ float sm[];
+  const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
+  float* sA = sm;            // [c*c]
+  float* snq = sm + c * c;   // [c]
+  float* snk = snq + c;      // [c]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const float* Gb = p.G + ((size_t)b * p.heads + h) * c * c;
+  const float* ss = p.sumsq + (size_t)b * 2 * C;
+  for (int i = tid; i < c; i += blockDim.x) {
+    snq[i] = fmaxf(sqrtf(ss[h * c + i]), 1e-12f);
+    snk[i] = fmaxf(sqrtf(ss[C + h * c + i]), 1e-12f);
+  }
+  __syncthreads();
+  const float tau = __ldg(p.temperature + h);
+  float* Ab = p.A + ((size_t)b * p.heads + h) * c * c;
+  float* Gtb = p.Gt + ((size_t)b * p.heads + h) * c * c;
+  for (int i = warp; i < c; i += nwarp) {  // one warp per row
+    float mx = -INFINITY;
+    for (int j = lane; j < c; j += 32) {
+      const float gt = Gb[i * c + j] / (snq[i] * snk[j]);
+      Gtb[i * c + j] = gt;
+      const float l = gt * tau;
+      sA[i * c + j] = l;
+      mx = fmaxf(mx, l);
+    }
+    mx = warp_max_a(mx);
+    float sum = 0.f;
+    for (int j = lane; j < c; j += 32) {
+      const float e = expf(sA[i * c + j] - mx);
+      sA[i * c + j] = e;
+      sum += e;
+    }
+    sum = warp_sum_a(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < c; j += 32) {
+      const float a = sA[i * c + j] * inv;
+      sA[i * c + j] = a;
+      Ab[i * c + j] = a;
+    }
+  }
+  __syncthreads();
+  // M[co, (h,j)] = sum_i W_out[co, (h,i)] * A[i,j]
+  uint8_t* Mp = reinterpret_cast<uint8_t*>(p.Mpack) + (size_t)b * p.pack_bs;
+  uint8_t* MTp = p.MTpack ? reinterpret_cast<uint8_t*>(p.MTpack) + (size_t)b * p.pack_bs : nullptr;
+  for (int e = tid; e < C * c; e += blockDim.x) {
+    const int co = e / c, j = e - co * c;
+    const float* wrow = p.w_out + (size_t)co * C + h * c;
+    float acc = 0.f;
+    for (int i = 0; i < c; ++i) acc = fmaf(__ldg(wrow + i), sA[i * c + j], acc);
+    store_split(Mp, C, C, co, h * c + j, acc);
+    if (MTp) store_split(MTp, C, C, h * c + j, co, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p) {
+  extern __shared__ float sm[];
+  const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
+  float* sA = sm;             // [c*c] softmax probabilities
+  float* sG = sA + c * c;     // [c*c] normalised Gram
+  float* sD = sG + c * c;     // [c*c] dA -> dGt
+  float* snq = sD + c * c;    // [c]
+  float* snk = snq + c;
+  float* srq = snk + c;
+  float* srk = srq + c;
+  __shared__ float s_dtau;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const size_t hb = ((size_t)b * p.heads + h) * c * c;
+  const float* ss = p.sumsq + (size_t)b * 2 * C;
+  const float* Pm = p.P + (size_t)b * C * C;  // [co, ci]
+  for (int i = tid; i < c * c; i += blockDim.x) {
+    sA[i] = p.A[hb + i];
+    sG[i] = p.Gt[hb + i];
+  }
+  for (int i = tid; i < c; i += blockDim.x) {
+    snq[i] = sqrtf(ss[h * c + i]);
+    snk[i] = sqrtf(ss[C + h * c + i]);
+    srk[i] = 0.f;
+  }
+  if (tid == 0) s_dtau = 0.f;
+  __syncthreads();
+  // dA[i,j] = sum_co W_out[co,(h,i)] * P[co,(h,j)]
+  for (int e = tid; e < c * c; e += blockDim.x) {
+    const int i = e / c, j = e - i * c;
+    float acc = 0.f;
+    for (int co = 0; co < C; ++co)
+      acc = fmaf(__ldg(p.w_out + (size_t)co * C + h * c + i), __ldg(Pm + (size_t)co * C + h * c + j), acc);
+    sD[e] = acc;
+  }
+  __syncthreads();
+  const float tau = __ldg(p.temperature + h);
+  float dtau = 0.f;
+  for (int i = warp; i < c; i += nwarp) {
+    float rd = 0.f;
+    for (int j = lane; j < c; j += 32) rd = fmaf(sD[i * c + j], sA[i * c + j], rd);
+    rd = warp_sum_a(rd);
+    float rq = 0.f;
+    for (int j = lane; j < c; j += 32) {
+      const float dS = sA[i * c + j] * (sD[i * c + j] - rd);
+      dtau = fmaf(dS, sG[i * c + j], dtau);
+      const float dG = dS * tau;
+      sD[i * c + j] = dG;
+      const float t = dG * sG[i * c + j];
+      rq += t;
+      atomicAdd(&srk[j], t);
+    }
+    rq = warp_sum_a(rq);
+    if (lane == 0) srq[i] = rq;
+  }
+  dtau = warp_sum_a(dtau);
+  if (lane == 0) atomicAdd(&s_dtau, dtau);
+  __syncthreads();
+  if (tid == 0) atomicAdd(p.dtemperature + h, s_dtau);
+  // packed W12: rows [0,C) produce dq, rows [C,2C) produce dk; K runs over [q channels ; k channels].
+  // Only the head-diagonal blocks are ever written: the caller keeps one zero-initialised pack
+  // buffer per (C, heads) configuration, so every other entry stays zero.
+  uint8_t* Wp = reinterpret_cast<uint8_t*>(p.W12pack) + (size_t)b * p.pack12_bs;
+  const int N2 = 2 * C;
+  for (int e = tid; e < c * c; e += blockDim.x) {
+    const int i = e / c, j = e - i * c;
+    const float nq = fmaxf(snq[i], 1e-12f), nk = fmaxf(snk[j], 1e-12f);
+    const float bq = sD[e] / (nq * nk);
+    store_split(Wp, N2, N2, h * c + i, C + h * c + j, bq);
+    store_split(Wp, N2, N2, C + h * c + j, h * c + i, bq);
+  }
+  for (int i = tid; i < c; i += blockDim.x) {
+    // d/dq of q/max(|q|,eps): the projection term vanishes when the clamp is active
+    const float cq = snq[i] >= 1e-12f ? -srq[i] / (snq[i] * snq[i]) : 0.f;
+    const float ck = snk[i] >= 1e-12f ? -srk[i] / (snk[i] * snk[i]) : 0.f;
+    store_split(Wp, N2, N2, h * c + i, h * c + i, cq);
+    store_split(Wp, N2, N2, C + h * c + i, C + h * c + i, ck);
+  }
+  // dW_out[co,(h,i)] += sum_j P[co,(h,j)] * A[i,j]
+  for (int e = tid; e < C * c; e += blockDim.x) {
+    const int co = e / c, i = e - co * c;
+    const float* prow = Pm + (size_t)co * C + h * c;
+    float acc = 0.f;
+    for (int j = 0; j < c; ++j) acc = fmaf(__ldg(prow + j), sA[i * c + j], acc);
+    atomicAdd(p.dw_out + (size_t)co * C + h * c + i, acc);
+  }
+}
+
+}  // namespace rcot
+
+using namespace rcot;
+
+static int attn_check(const rcot_attn_params& p) {
+  RCOT_REQUIRE(p.B > 0 && p.B <= 65535 && p.C > 0 && p.heads > 0 && p.C % p.heads == 0, "attn: bad sizes");
+  RCOT_REQUIRE(p.C / p.heads <= 96, "attn: per-head channels must be <= 96 (got %d)", p.C / p.heads);
+  RCOT_REQUIRE(p.sumsq && p.temperature && p.w_out && p.A && p.Gt, "attn: null pointer");
+  return RCOT_OK;
+}
+
+extern "C" int rcot_attn_fwd(const rcot_attn_params* pp, rcot_stream_t st) {
+  RCOT_REQUIRE(pp != nullptr, "attn_fwd: null params");
+  const rcot_attn_params& p = *pp;
+  int rc = attn_check(p);
+  if (rc) return rc;
+  RCOT_REQUIRE(p.G && p.Mpack, "attn_fwd: null pointer");
+  const int c = p.C / p.heads;
+  const size_t smem = ((size_t)c * c + 2 * c) * sizeof(float);
+  dim3 grid(p.heads, p.B);
+  attn_fwd_kernel<<<grid, 256, smem, (cudaStream_t)st>>>(p);
+  return check_launch("attn_fwd");
+}
+
+extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
+  RCOT_REQUIRE(pp != nullptr, "attn_bwd: null params");
+  const rcot_attn_params& p = *pp;
+  int rc = attn_check(p);
+  if (rc) return rc;
+  RCOT_REQUIRE(p.P && p.dw_out && p.dtemperature && p.W12pack, "attn_bwd: null pointer");
+  const int c = p.C / p.heads;
+  const size_t smem = ((size_t)3 * c * c + 4 * c) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    if (e != cudaSuccess) {
+      set_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return RCOT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(p.heads, p.B);
+  attn_bwd_kernel<<<grid, 256, smem, (cudaStream_t)st>>>(p);
+  return check_launch("attn_bwd");
+}

@@ -1,0 +1,357 @@
+// elem.cu -- CUDA-core (HBM-bound) pieces of the Restormer block and its backward:
+//   per-pixel LayerNorm statistics and LayerNorm backward   (Net_Restormer.py:173-200)
+//   depthwise 3x3 stencil: plain / transposed / GELU-gated / gate backward / weight gradient
+//                                                           (Net_Restormer.py:26,75,81-83)
+//   pixel (un)shuffle, axpby, per-channel sums (bias gradients)
+// Layout everywhere: fp32 NCHW, per-image block contiguous, `*_bs` = batch stride in elements.
+#include "../../include/rcot_b200.h"
+#include "common.cuh"
+
+namespace rcot {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ LayerNorm statistics
+// One thread per pixel, loop over channels (coalesced across the warp). Shifted single pass:
+// var = E[(x-s)^2] - (E[x-s])^2 with s = x[0], which is as accurate as two passes here.
+__global__ void __launch_bounds__(256)
+    ln_stats_kernel(const float* __restrict__ x, int64_t x_bs, int C, int HW, float2* __restrict__ stats) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (p >= HW) return;
+  const float* xp = x + (size_t)b * x_bs + p;
+  const float s = __ldg(xp);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {
+    const float d = __ldg(xp + (size_t)c * HW) - s;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+  }
+  const float inv = 1.f / (float)C;
+  const float m = s1 * inv;
+  const float var = fmaxf(s2 * inv - m * m, 0.f);
+  stats[(size_t)b * HW + p] = make_float2(s + m, 1.0f / sqrtf(var + 1e-5f));
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// g = dz*gamma ; dx = [dy +] rstd*(g - mean_c(g) - xhat*mean_c(g*xhat)) ; dgamma += sum dz*xhat ;
+// dbeta += sum dz.  One thread per pixel, two sweeps over the channels (the second one hits L1/L2).
+// Channel sums: warp shuffle over 32 pixels -> shared accumulators -> one atomicAdd per channel per CTA.
+__global__ void __launch_bounds__(256)
+    ln_bwd_kernel(const float* __restrict__ dz, int64_t dz_bs, const float* __restrict__ x, int64_t x_bs,
+                  const float2* __restrict__ stats, const float* __restrict__ gamma, const float* dy, int64_t dy_bs,
+                  float* dx, int64_t dx_bs, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int HW) {
+  extern __shared__ float sacc[];  // [2*C]
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  const bool valid = p < HW;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const float* xp = x + (size_t)b * x_bs + p;
+  const float* dzp = dz + (size_t)b * dz_bs + p;
+  float mu = 0.f, rstd = 0.f;
+  if (valid) {
+    const float2 st = stats[(size_t)b * HW + p];
+    mu = st.x;
+    rstd = st.y;
+  }
+  float sg = 0.f, sgx = 0.f;
+  const int lane = threadIdx.x & 31;
+  for (int c = 0; c < C; ++c) {
+    float d = 0.f, xh = 0.f;
+    if (valid) {
+      d = __ldg(dzp + (size_t)c * HW);
+      xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+    }
+    const float g = d * __ldg(gamma + c);
+    sg += g;
+    sgx = fmaf(g, xh, sgx);
+    const float wg = warp_sum(d * xh);
+    const float wb = warp_sum(d);
+    if (lane == 0) {
+      atomicAdd(&sacc[c], wg);
+      atomicAdd(&sacc[C + c], wb);
+    }
+  }
+  if (valid) {
+    const float inv = 1.f / (float)C;
+    const float mg = sg * inv, mgx = sgx * inv;
+    const float* dyp = dy ? dy + (size_t)b * dy_bs + p : nullptr;
+    float* dxp = dx + (size_t)b * dx_bs + p;
+    for (int c = 0; c < C; ++c) {
+      const float d = __ldg(dzp + (size_t)c * HW);
+      const float xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+      float r = rstd * (d * __ldg(gamma + c) - mg - xh * mgx);
+      if (dyp) r += dyp[(size_t)c * HW];
+      dxp[(size_t)c * HW] = r;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, sacc[i]);
+    atomicAdd(dbeta + i, sacc[C + i]);
+  }
+}
+
+// ------------------------------------------------------------------ depthwise 3x3
+__device__ __forceinline__ float gelu_erf(float a) { return 0.5f * a * (1.f + erff(a * 0.70710678118654752f)); }
+// d/da gelu(a) = Phi(a) + a*phi(a)
+__device__ __forceinline__ float gelu_erf_grad(float a) {
+  return 0.5f * (1.f + erff(a * 0.70710678118654752f)) + a * 0.39894228040143268f * __expf(-0.5f * a * a);
+}
+
+// 3x3 stencil at (y,x) of one plane with zero padding; w[9] already flipped by the caller if needed.
+__device__ __forceinline__ float stencil9(const float* __restrict__ plane, const float* w, int y, int x, int H, int W) {
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if ((unsigned)yy >= (unsigned)H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if ((unsigned)xx >= (unsigned)W) continue;
+      acc = fmaf(__ldg(plane + yy * W + xx), w[ky * 3 + kx], acc);
+    }
+  }
+  return acc;
+}
+
+// mode 0: out[ch] = dw(in[ch])                (flip=1: transposed = data gradient)
+//         optional sumsq[b*nsq + ch] += sum_p out^2 for ch < nsq   (MDTA row norms of q and k)
+// mode 1: out[j] = gelu(dw(in[j])) * dw(in[j+hid]),  j < hid            (GDFN gate)
+// mode 2: a = dw(in[j]), b = dw(in[j+hid]); out[j] = dg*b*gelu'(a); out[j+hid] = dg*gelu(a);
+//         optional g_out[j] = gelu(a)*b                                 (GDFN gate backward)
+__global__ void __launch_bounds__(256) dwconv_kernel(const rcot_dw_params p) {
+  const int HW = p.H * p.W;
+  const int ch = blockIdx.y, b = blockIdx.z;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = pix < HW;
+  const int y = valid ? pix / p.W : 0, x = valid ? pix - (pix / p.W) * p.W : 0;
+  const float* inb = p.in + (size_t)b * p.in_bs;
+  float w0[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) w0[i] = __ldg(p.w + ch * 9 + (p.flip ? 8 - i : i));
+  if (p.mode == 0) {
+    float o = 0.f;
+    if (valid) {
+      o = stencil9(inb + (size_t)ch * HW, w0, y, x, p.H, p.W);
+      p.out[(size_t)b * p.out_bs + (size_t)ch * HW + pix] = o;
+    }
+    if (p.sumsq && ch < p.nsq) {
+      __shared__ float red[8];
+      float s = warp_sum(o * o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) atomicAdd(p.sumsq + (size_t)b * p.nsq + ch, s);
+      }
+    }
+    return;
+  }
+  if (!valid) return;
+  float w1[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) w1[i] = __ldg(p.w + (ch + p.hid) * 9 + i);
+  const float a = stencil9(inb + (size_t)ch * HW, w0, y, x, p.H, p.W);
+  const float g = stencil9(inb + (size_t)(ch + p.hid) * HW, w1, y, x, p.H, p.W);
+  if (p.mode == 1) {
+    p.out[(size_t)b * p.out_bs + (size_t)ch * HW + pix] = gelu_erf(a) * g;
+  } else {
+    const float d = __ldg(p.dg + (size_t)b * p.dg_bs + (size_t)ch * HW + pix);
+    const float ga = gelu_erf(a);
+    float* ob = p.out + (size_t)b * p.out_bs;
+    ob[(size_t)ch * HW + pix] = d * g * gelu_erf_grad(a);
+    ob[(size_t)(ch + p.hid) * HW + pix] = d * ga;
+    if (p.g_out) p.g_out[(size_t)b * p.g_bs + (size_t)ch * HW + pix] = ga * g;
+  }
+}
+
+// dW[ch, k] += sum_{b,p} dout[b,ch,p] * in[b,ch,p+off_k].  grid = (chunks, Cn); each CTA strides over
+// (image, pixel) pairs, keeps 9 partial sums per thread, reduces and issues 9 atomics.
+__global__ void __launch_bounds__(256)
+    dw_wgrad_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
+                    float* __restrict__ dw, int B, int H, int W) {
+  const int HW = H * W, ch = blockIdx.y;
+  const long total = (long)B * HW;
+  float acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / HW), pix = (int)(e - (long)b * HW);
+    const int y = pix / W, x = pix - y * W;
+    const float d = __ldg(dout + (size_t)b * dout_bs + (size_t)ch * HW + pix);
+    const float* plane = in + (size_t)b * in_bs + (size_t)ch * HW;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if ((unsigned)yy >= (unsigned)H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if ((unsigned)xx >= (unsigned)W) continue;
+        acc[ky * 3 + kx] = fmaf(d, __ldg(plane + yy * W + xx), acc[ky * 3 + kx]);
+      }
+    }
+  }
+  __shared__ float red[9][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) red[i][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    atomicAdd(dw + ch * 9 + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------ pixel (un)shuffle, r = 2
+// inverse=0 (PixelShuffle):   out[b, c, 2y+i, 2x+j] = in[b, 4c+2i+j, y, x]     in: [4C,H,W]  out: [C,2H,2W]
+// inverse=1 (PixelUnshuffle): out[b, 4c+2i+j, y, x] = in[b, c, 2y+i, 2x+j]     in: [C,2H,2W] out: [4C,H,W]
+// C,H,W always describe the (4C,H,W) side. One thread per element of the (C,2H,2W) side.
+__global__ void __launch_bounds__(256)
+    pixel_shuffle_kernel(const float* __restrict__ in, int64_t in_bs, float* __restrict__ out, int64_t out_bs, int C,
+                         int H, int W, int inverse) {
+  const int W2 = 2 * W, H2 = 2 * H;
+  const long n = (long)C * H2 * W2;
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (e >= n) return;
+  const int c = (int)(e / ((long)H2 * W2));
+  const int r = (int)(e - (long)c * H2 * W2);
+  const int yy = r / W2, xx = r - yy * W2;
+  const size_t small = ((size_t)(4 * c + 2 * (yy & 1) + (xx & 1)) * H + (yy >> 1)) * W + (xx >> 1);
+  if (inverse) out[(size_t)b * out_bs + small] = __ldg(in + (size_t)b * in_bs + e);
+  else out[(size_t)b * out_bs + e] = __ldg(in + (size_t)b * in_bs + small);
+}
+
+// ------------------------------------------------------------------ out = a*x + b*y (per-sample a optional)
+__global__ void __launch_bounds__(256)
+    axpby_kernel(float* out, int64_t out_bs, const float* x, int64_t x_bs, const float* y, int64_t y_bs, float a,
+                 float bcoef, const float* __restrict__ a_vec, int mode, long n) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (e >= n) return;
+  float av = a, bv = bcoef;
+  if (mode == 1) {  // interpolation: a_vec[b]*x + (1-a_vec[b])*y
+    av = __ldg(a_vec + b);
+    bv = 1.f - av;
+  }
+  const float xv = x[(size_t)b * x_bs + e];
+  const float yv = y ? y[(size_t)b * y_bs + e] : 0.f;
+  out[(size_t)b * out_bs + e] = av * xv + bv * yv;
+}
+
+// out[c] += sum_{b,p} x[b,c,p]   (bias gradients).  grid = (chunks, C)
+__global__ void __launch_bounds__(256)
+    channel_sum_kernel(const float* __restrict__ x, int64_t x_bs, float* __restrict__ out, int B, int HW) {
+  const int c = blockIdx.y;
+  const long total = (long)B * HW;
+  float s = 0.f;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / HW), pix = (int)(e - (long)b * HW);
+    s += __ldg(x + (size_t)b * x_bs + (size_t)c * HW + pix);
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out + c, t);
+  }
+}
+
+}  // namespace rcot
+
+using namespace rcot;
+
+extern "C" int rcot_ln_stats(const float* x, int64_t x_bs, int B, int C, int HW, float* stats, rcot_stream_t st) {
+  RCOT_REQUIRE(x && stats && B > 0 && C > 0 && HW > 0, "ln_stats: bad arguments");
+  RCOT_REQUIRE(B <= 65535, "ln_stats: batch too large");
+  dim3 grid(cdiv(HW, 256), B);
+  ln_stats_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(x, x_bs, C, HW, reinterpret_cast<float2*>(stats));
+  return check_launch("ln_stats");
+}
+
+extern "C" int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64_t x_bs, const float* stats,
+                           const float* gamma, const float* dy, int64_t dy_bs, float* dx, int64_t dx_bs,
+                           float* dgamma, float* dbeta, int B, int C, int HW, rcot_stream_t st) {
+  RCOT_REQUIRE(dz && x && stats && gamma && dx && dgamma && dbeta, "ln_bwd: null pointer");
+  RCOT_REQUIRE(B > 0 && B <= 65535 && C > 0 && HW > 0, "ln_bwd: bad sizes");
+  dim3 grid(cdiv(HW, 256), B);
+  ln_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)st>>>(
+      dz, dz_bs, x, x_bs, reinterpret_cast<const float2*>(stats), gamma, dy, dy_bs, dx, dx_bs, dgamma, dbeta, C, HW);
+  return check_launch("ln_bwd");
+}
+
+extern "C" int rcot_dwconv3x3(const rcot_dw_params* pp, rcot_stream_t st) {
+  RCOT_REQUIRE(pp != nullptr, "dwconv3x3: null params");
+  const rcot_dw_params& p = *pp;
+  RCOT_REQUIRE(p.in && p.w && p.out, "dwconv3x3: null pointer");
+  RCOT_REQUIRE(p.B > 0 && p.B <= 65535 && p.Cn > 0 && p.H > 0 && p.W > 0, "dwconv3x3: bad sizes");
+  RCOT_REQUIRE(p.mode >= 0 && p.mode <= 2, "dwconv3x3: bad mode %d", p.mode);
+  int planes = p.Cn;
+  if (p.mode != 0) {
+    RCOT_REQUIRE(p.hid > 0 && 2 * p.hid == p.Cn, "dwconv3x3: gate modes need Cn == 2*hid");
+    RCOT_REQUIRE(p.flip == 0, "dwconv3x3: gate modes cannot flip");
+    if (p.mode == 2) RCOT_REQUIRE(p.dg != nullptr, "dwconv3x3: gate backward needs dg");
+    planes = p.hid;
+  }
+  RCOT_REQUIRE(planes <= 65535, "dwconv3x3: too many channels");
+  dim3 grid(cdiv((long)p.H * p.W, 256), planes, p.B);
+  dwconv_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(p);
+  return check_launch("dwconv3x3");
+}
+
+extern "C" int rcot_dwconv3x3_wgrad(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, float* dw,
+                                    int B, int Cn, int H, int W, rcot_stream_t st) {
+  RCOT_REQUIRE(in && dout && dw && B > 0 && Cn > 0 && Cn <= 65535 && H > 0 && W > 0, "dwconv3x3_wgrad: bad arguments");
+  long total = (long)B * H * W;
+  int chunks = (int)((total + 256 * 16 - 1) / (256 * 16));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 64) chunks = 64;
+  dim3 grid(chunks, Cn);
+  dw_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(in, in_bs, dout, dout_bs, dw, B, H, W);
+  return check_launch("dwconv3x3_wgrad");
+}
+
+extern "C" int rcot_pixel_shuffle(const float* in, int64_t in_bs, float* out, int64_t out_bs, int B, int C, int H,
+                                  int W, int inverse, rcot_stream_t st) {
+  RCOT_REQUIRE(in && out && B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "pixel_shuffle: bad arguments");
+  const long n = (long)C * 4 * H * W;
+  dim3 grid(cdiv(n, 256), B);
+  pixel_shuffle_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(in, in_bs, out, out_bs, C, H, W, inverse);
+  return check_launch("pixel_shuffle");
+}
+
+extern "C" int rcot_axpby(float* out, int64_t out_bs, const float* x, int64_t x_bs, const float* y, int64_t y_bs,
+                          float a, float b, const float* a_vec, int B, int64_t n, rcot_stream_t st) {
+  RCOT_REQUIRE(out && x && B > 0 && B <= 65535 && n > 0, "axpby: bad arguments");
+  dim3 grid(cdiv(n, 256), B);
+  axpby_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(out, out_bs, x, x_bs, y, y_bs, a, b, a_vec, a_vec ? 1 : 0, n);
+  return check_launch("axpby");
+}
+
+extern "C" int rcot_channel_sum(const float* x, int64_t x_bs, float* out, int B, int C, int HW, rcot_stream_t st) {
+  RCOT_REQUIRE(x && out && B > 0 && C > 0 && C <= 65535 && HW > 0, "channel_sum: bad arguments");
+  long total = (long)B * HW;
+  int chunks = (int)((total + 256 * 8 - 1) / (256 * 8));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 32) chunks = 32;
+  dim3 grid(chunks, C);
+  channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(x, x_bs, out, B, HW);
+  return check_launch("channel_sum");
+}

@@ -164,6 +164,26 @@ __device__ __host__ inline uint32_t op_offset(int row, int k) {  // k in [0,KC)
          (uint32_t)(k & 7) * 2u;
 }
 
+// Byte offset of element (n, k), term (0 = hi, 1 = lo), inside the packed B-operand image of an
+// [N x K] matrix: tiles ordered [pass][k-chunk][term][sub-tile][BN x 32] (see pack.cu / make_nplan).
+__device__ __host__ inline size_t packed_offset(int N, int K, int n, int k, int term) {
+  int BN, NSUB;
+  if (N <= 256) {
+    BN = (N + 15) / 16 * 16;
+    NSUB = 1;
+  } else {
+    const int nst = (N + 255) / 256;
+    BN = ((N + nst - 1) / nst + 15) / 16 * 16;
+    NSUB = 2;
+  }
+  const int nk = (K + KC - 1) / KC;
+  const int si = n / BN, np = n - si * BN;
+  const int pass = si / NSUB, sub = si - pass * NSUB;
+  const int kc = k / KC, kp = k - kc * KC;
+  const size_t tile = (size_t)BN * KC * 2;
+  return ((((size_t)pass * nk + kc) * 2 + term) * NSUB + sub) * tile + op_offset(np, kp);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

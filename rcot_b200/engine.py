@@ -1,0 +1,319 @@
+"""Host-side execution engine for the transport map: hand-derived forward and backward of the
+Restormer blocks and glue convolutions, expressed as sequences of ``librcot_b200`` kernel launches.
+
+Nothing here differentiates with autograd: every op records its own backward closure on a small
+tape (``Tape``), the closures call the backward kernels, and weight gradients are accumulated
+straight into the parameter set's flat gradient buffer (so modules that are invoked twice per
+forward -- reference Net_Restormer.py:343-432 -- sum their gradients like autograd would).
+
+Reference behaviour followed:  TransformerBlock Net_Restormer.py:201-214, Attention :19-50,
+FeedForward :67-85, LayerNorm :173-200, Downsample/Upsample/OverlapPatchEmbed :86-122,
+T_net.forward :328-434.  Algebra: SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+# ---------------------------------------------------------------------------------- parameters
+class ParamSet:
+    """Parameters of one network as views into ONE flat fp32 buffer, a matching flat gradient
+    buffer, and the packed bf16 hi/lo tcgen05 operand images of every GEMM weight."""
+
+    def __init__(self, named_params, device, used=None):
+        """named_params: ordered {name: tensor}. ``used``: names that receive gradients (the rest
+        is placed at the tail of the flat buffers so optimizer kernels can skip it)."""
+        names = list(named_params)
+        if used is not None:
+            names = [n for n in names if n in used] + [n for n in names if n not in used]
+        self.names = names
+        self.offsets = {}
+        off = 0
+        for n in names:
+            self.offsets[n] = off
+            off += named_params[n].numel()
+        self.numel = off
+        self.n_used = off if used is None else sum(named_params[n].numel() for n in names if n in used)
+        self.flat = torch.empty(off, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(off, device=device, dtype=torch.float32)
+        self.p, self.g = {}, {}
+        for n in names:
+            src = named_params[n]
+            o = self.offsets[n]
+            view = self.flat[o:o + src.numel()].view(src.shape)
+            view.copy_(src.detach())
+            self.p[n] = view
+            self.g[n] = self.grad[o:o + src.numel()].view(src.shape)
+        self.table = ops.PackTable(device)
+        self.pack_idx = {}
+
+    def add_pack(self, name, kind):
+        key = (name, kind)
+        if key not in self.pack_idx:
+            self.pack_idx[key] = self.table.add(self.p[name], kind)
+        return key
+
+    def finalize(self):
+        self.table.finalize()
+        self.repack()
+        return self
+
+    def repack(self):
+        if self.table.entries:
+            self.table.repack()
+
+    def pack(self, name, kind):
+        return self.table.ptr(self.pack_idx[(name, kind)])
+
+    def zero_grad(self):
+        ops.zero_(self.grad)
+
+
+# ---------------------------------------------------------------------------------- tape
+class Tape:
+    """Reverse-mode tape over engine ops. Gradients are keyed by tensor identity."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.ops = []
+        self.grads = {}
+
+    def record(self, out, bwd):
+        if self.enabled:
+            self.ops.append((out, bwd))
+
+    def add_grad(self, t, g):
+        k = id(t)
+        cur = self.grads.get(k)
+        if cur is None:
+            self.grads[k] = (t, g)
+        else:
+            ops.axpby(cur[1], g, 1.0, 1.0, out=cur[1])
+
+    def backward(self, out, dout):
+        """dout must be a tensor the tape may overwrite."""
+        self.add_grad(out, dout)
+        while self.ops:
+            t, bwd = self.ops.pop()
+            ent = self.grads.pop(id(t), None)
+            if ent is not None:
+                bwd(ent[1])
+        leaves = {k: v for k, v in self.grads.items()}
+        self.grads = {}
+        return leaves
+
+    def grad_of(self, leaves, t):
+        ent = leaves.get(id(t))
+        return None if ent is None else ent[1]
+
+
+# ---------------------------------------------------------------------------------- scratch for MDTA small matrices
+class AttnScratch:
+    """Per (B, C, heads) buffers: Gram, row norms, softmax, packed per-image matrices.
+    The packed buffers are zero-initialised once; the kernels only ever write the same
+    head-diagonal entries, so the padding / off-diagonal zeros persist."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, B, C, heads, device):
+        key = (B, C, heads, str(device))
+        s = cls._cache.get(key)
+        if s is None:
+            s = cls(B, C, heads, device)
+            cls._cache[key] = s
+        return s
+
+    def __init__(self, B, C, heads, device):
+        c = C // heads
+        self.pb = ops.packed_bytes(C, C)
+        self.pb12 = ops.packed_bytes(2 * C, 2 * C)
+        # one allocation for everything that must be zeroed per call: [sumsq | G | P]
+        self.zbuf = torch.zeros(B * (2 * C + heads * c * c + C * C), device=device)
+        self.sumsq = self.zbuf[:B * 2 * C].view(B, 2 * C)
+        self.G = self.zbuf[B * 2 * C:B * (2 * C + heads * c * c)].view(B, heads, c, c)
+        self.P = self.zbuf[B * (2 * C + heads * c * c):].view(B, C, C)
+        self.A = torch.empty(B, heads, c, c, device=device)
+        self.Gt = torch.empty(B, heads, c, c, device=device)
+        self.Mpack = torch.zeros(B * self.pb, dtype=torch.uint8, device=device)
+        self.MTpack = torch.zeros(B * self.pb, dtype=torch.uint8, device=device)
+        self.W12pack = None
+        self.device = device
+        self.B = B
+
+    def w12(self):
+        if self.W12pack is None:
+            self.W12pack = torch.zeros(self.B * self.pb12, dtype=torch.uint8, device=self.device)
+        return self.W12pack
+
+
+# ---------------------------------------------------------------------------------- Restormer block
+class BlockSpec:
+    """Names and sizes of one TransformerBlock inside a ParamSet."""
+
+    def __init__(self, ps: ParamSet, prefix: str, C: int, heads: int, has_norm=True, has_attn=True, has_ffn=True):
+        self.ps, self.pre, self.C, self.heads = ps, prefix, C, heads
+        self.has_norm, self.has_attn, self.has_ffn = has_norm, has_attn, has_ffn
+        if has_attn:
+            a = prefix + "attn."
+            ps.add_pack(a + "qkv.weight", "fwd")
+            ps.add_pack(a + "qkv.weight", "dgrad")
+        if has_ffn:
+            f = prefix + "ffn."
+            self.hid = ps.p[f + "project_out.weight"].shape[1]
+            for n in ("project_in.weight", "project_out.weight"):
+                ps.add_pack(f + n, "fwd")
+                ps.add_pack(f + n, "dgrad")
+
+
+def _ln_args(ps, name, stats):
+    return (stats, ps.p[name + ".body.weight"], ps.p[name + ".body.bias"])
+
+
+def mdta_fwd(bs: BlockSpec, x, norm_name, residual, need_bwd):
+    """y = [x +] project_out(attn(dwconv(qkv(LN(x))))).  Returns (y, ctx)."""
+    ps, C, h = bs.ps, bs.C, bs.heads
+    a = bs.pre + "attn."
+    B, _, H, W = x.shape
+    sc = AttnScratch.get(B, C, h, x.device)
+    stats = ops.ln_stats(x) if norm_name else None
+    ln = _ln_args(ps, norm_name, stats) if norm_name else None
+    pre = ops.pm_gemm(x, ps.pack(a + "qkv.weight", "fwd"), 3 * C, ln=ln)
+    ops.zero_(sc.zbuf)
+    qkv = ops.dwconv(pre, ps.p[a + "qkv_dwconv.weight"], sumsq=sc.sumsq, nsq=2 * C)
+    c = C // h
+    ops.pk_gemm(qkv[:, :C], qkv[:, C:2 * C], sc.G, ldo=c, per_image=True, groups=h, out_gs=c * c)
+    ops.attn_fwd(sc.G, sc.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], sc.A, sc.Gt, sc.Mpack,
+                 sc.MTpack if need_bwd else None, B, C, h)
+    y = ops.pm_gemm(qkv[:, 2 * C:], sc.Mpack.data_ptr(), C, wpack_bs=sc.pb, residual=x if residual else None)
+    return y, (stats, pre, qkv, sc)
+
+
+def mdta_bwd(bs: BlockSpec, x, dy, norm_name, residual, ctx):
+    """Backward of mdta_fwd given the recomputed ctx. Returns dx (fresh tensor)."""
+    ps, C, h = bs.ps, bs.C, bs.heads
+    a = bs.pre + "attn."
+    B, _, H, W = x.shape
+    stats, pre, qkv, sc = ctx
+    ops.pk_gemm(dy, qkv[:, 2 * C:], sc.P, ldo=C, per_image=True)
+    ops.attn_bwd(sc.P, sc.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], sc.A, sc.Gt,
+                 ps.g[a + "project_out.weight"], ps.g[a + "temperature"], sc.w12(), B, C, h)
+    dqkv = torch.empty_like(qkv)
+    ops.pm_gemm(qkv[:, :2 * C], sc.w12().data_ptr(), 2 * C, wpack_bs=sc.pb12, out=dqkv, out_coff=0)
+    ops.pm_gemm(dy, sc.MTpack.data_ptr(), C, wpack_bs=sc.pb, out=dqkv, out_coff=2 * C)
+    dw = ps.p[a + "qkv_dwconv.weight"]
+    dpre = ops.dwconv(dqkv, dw, flip=True)
+    ops.dwconv_wgrad(pre, dqkv, ps.g[a + "qkv_dwconv.weight"])
+    ln = _ln_args(ps, norm_name, stats) if norm_name else None
+    ops.pk_gemm(dpre, x, ps.g[a + "qkv.weight"], ldo=C, ln=ln)
+    dz = ops.pm_gemm(dpre, ps.pack(a + "qkv.weight", "dgrad"), C, residual=None if norm_name or not residual else dy)
+    if not norm_name:
+        return dz
+    return ops.ln_bwd(dz, x, stats, ps.p[norm_name + ".body.weight"], ps.g[norm_name + ".body.weight"],
+                      ps.g[norm_name + ".body.bias"], dy=dy if residual else None, dx=dz)
+
+
+def gdfn_fwd(bs: BlockSpec, x, norm_name, residual):
+    ps, C = bs.ps, bs.C
+    f = bs.pre + "ffn."
+    hid = bs.hid
+    stats = ops.ln_stats(x) if norm_name else None
+    ln = _ln_args(ps, norm_name, stats) if norm_name else None
+    u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
+    g = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=1)
+    y = ops.pm_gemm(g, ps.pack(f + "project_out.weight", "fwd"), C, residual=x if residual else None)
+    return y
+
+
+def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual):
+    """Recomputes the hidden tensors from x, returns dx (fresh tensor)."""
+    ps, C = bs.ps, bs.C
+    f = bs.pre + "ffn."
+    hid = bs.hid
+    stats = ops.ln_stats(x) if norm_name else None
+    ln = _ln_args(ps, norm_name, stats) if norm_name else None
+    u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
+    dg = ops.pm_gemm(dy, ps.pack(f + "project_out.weight", "dgrad"), hid)
+    g = torch.empty_like(dg)
+    dab = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=2, dg=dg, g_out=g, out=torch.empty_like(u))
+    ops.pk_gemm(dy, g, ps.g[f + "project_out.weight"], ldo=hid)
+    del g, dg
+    du = ops.dwconv(dab, ps.p[f + "dwconv.weight"], flip=True)
+    ops.dwconv_wgrad(u, dab, ps.g[f + "dwconv.weight"])
+    del dab, u
+    ops.pk_gemm(du, x, ps.g[f + "project_in.weight"], ldo=C, ln=ln)
+    dz = ops.pm_gemm(du, ps.pack(f + "project_in.weight", "dgrad"), C,
+                     residual=None if norm_name or not residual else dy)
+    if not norm_name:
+        return dz
+    return ops.ln_bwd(dz, x, stats, ps.p[norm_name + ".body.weight"], ps.g[norm_name + ".body.weight"],
+                      ps.g[norm_name + ".body.bias"], dy=dy if residual else None, dx=dz)
+
+
+def block_fwd(bs: BlockSpec, x, tape: Tape | None):
+    """TransformerBlock: x + MDTA(LN1(x)), then + GDFN(LN2(.)). Saves only the block input."""
+    xm, _ = mdta_fwd(bs, x, bs.pre + "norm1", True, False)
+    y = gdfn_fwd(bs, xm, bs.pre + "norm2", True)
+    if tape is not None and tape.enabled:
+        def bwd(dy, x=x):
+            xm, ctx = mdta_fwd(bs, x, bs.pre + "norm1", True, True)
+            dxm = gdfn_bwd(bs, xm, dy, bs.pre + "norm2", True)
+            dx = mdta_bwd(bs, x, dxm, bs.pre + "norm1", True, ctx)
+            tape.add_grad(x, dx)
+        tape.record(y, bwd)
+    return y
+
+
+# ---------------------------------------------------------------------------------- glue convolutions
+class ConvSpec:
+    def __init__(self, ps: ParamSet, name: str, ks: int, pad: int, need_dgrad=True):
+        self.ps, self.name, self.ks, self.pad = ps, name, ks, pad
+        w = ps.p[name]
+        self.Cout, self.Cin = w.shape[0], w.shape[1]
+        ps.add_pack(name, "fwd")
+        if need_dgrad:
+            ps.add_pack(name, "dgrad")
+
+
+def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True):
+    """Dense conv (stride 1, no bias), optional concat input [x, x2] and residual epilogue."""
+    ps = cs.ps
+    y = ops.pm_gemm(x, ps.pack(cs.name, "fwd"), cs.Cout, ks=cs.ks, pad=cs.pad, x2=x2, residual=residual)
+    if tape is not None and tape.enabled:
+        def bwd(dy):
+            Cin = cs.Cin
+            ops.pk_gemm(dy, x, ps.g[cs.name].view(cs.Cout, -1), ldo=Cin * cs.ks * cs.ks, ks=cs.ks, pad=cs.pad, b2=x2)
+            if need_dx:
+                dx = ops.pm_gemm(dy, ps.pack(cs.name, "dgrad"), Cin, ks=cs.ks, pad=cs.pad, mode=1,
+                                 out_hw=(x.shape[2], x.shape[3]))
+                if x2 is None:
+                    tape.add_grad(x, dx)
+                else:
+                    tape.add_grad(x, dx[:, :x.shape[1]])
+                    tape.add_grad(x2, dx[:, x.shape[1]:])
+            if residual is not None:
+                tape.add_grad(residual, dy)
+        tape.record(y, bwd)
+    return y
+
+
+def shuffle_fwd(x, inverse, tape, out=None):
+    y = ops.pixel_shuffle(x, inverse=inverse, out=out)
+    if tape is not None and tape.enabled:
+        def bwd(dy):
+            tape.add_grad(x, ops.pixel_shuffle(dy, inverse=not inverse))
+        tape.record(y, bwd)
+    return y
+
+
+def axpby_fwd(x, y, a, b, tape):
+    """z = a*x + b*y with gradients to both."""
+    z = ops.axpby(x, y, a, b)
+    if tape is not None and tape.enabled:
+        def bwd(dz):
+            tape.add_grad(x, ops.axpby(dz, None, a, 0.0))
+            tape.add_grad(y, ops.axpby(dz, None, b, 0.0))
+        tape.record(z, bwd)
+    return z

@@ -42,7 +42,28 @@ class PKParams(C.Structure):
         ("ks", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
         ("per_image", C.c_int32), ("terms", C.c_int32),
-        ("out", C.c_void_p), ("out_bs", C.c_int64), ("ldo", C.c_int32), ("reserved", C.c_int32),
+        ("out", C.c_void_p), ("out_bs", C.c_int64), ("ldo", C.c_int32), ("groups", C.c_int32),
+        ("out_gs", C.c_int64),
+    ]
+
+
+class DWParams(C.Structure):
+    _fields_ = [
+        ("in_", C.c_void_p), ("in_bs", C.c_int64), ("w", C.c_void_p), ("out", C.c_void_p), ("out_bs", C.c_int64),
+        ("B", C.c_int32), ("Cn", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("mode", C.c_int32), ("flip", C.c_int32), ("hid", C.c_int32), ("nsq", C.c_int32),
+        ("dg", C.c_void_p), ("dg_bs", C.c_int64), ("g_out", C.c_void_p), ("g_bs", C.c_int64),
+        ("sumsq", C.c_void_p),
+    ]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("reserved", C.c_int32),
+        ("G", C.c_void_p), ("sumsq", C.c_void_p), ("temperature", C.c_void_p), ("w_out", C.c_void_p),
+        ("A", C.c_void_p), ("Gt", C.c_void_p), ("Mpack", C.c_void_p), ("MTpack", C.c_void_p),
+        ("pack_bs", C.c_int64), ("P", C.c_void_p), ("dw_out", C.c_void_p), ("dtemperature", C.c_void_p),
+        ("W12pack", C.c_void_p), ("pack12_bs", C.c_int64),
     ]
 
 
@@ -178,3 +199,136 @@ def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None
         p.residual, p.res_bs = residual.data_ptr(), _img_view(residual, "residual")
     _lib.check(L().rcot_pm_gemm(C.byref(p), _stream()), "pm_gemm")
     return out
+
+
+# ------------------------------------------------------------------ pixel-as-K GEMM
+def pk_gemm(a, b, out, *, ldo, ks=1, stride=1, pad=0, b2=None, ln=None, per_image=False, groups=1, out_gs=0,
+            CA=None, CB=None, terms=None):
+    """out[(b,g,) m, n] += sum_q a[b, g*CA+m, q] * Bg(b, g, n, q); ``out`` is accumulated (atomics)."""
+    B, CAf, Ha, Wa = a.shape
+    _, CBf, Hb, Wb = b.shape
+    p = PKParams()
+    p.a, p.a_bs, p.CA = a.data_ptr(), _img_view(a, "a"), (CAf // groups if CA is None else CA)
+    p.b, p.b_bs, p.CB1 = b.data_ptr(), _img_view(b, "b"), (CBf // groups if CB is None else CB)
+    if b2 is not None:
+        p.b2, p.b2_bs, p.CB2 = b2.data_ptr(), _img_view(b2, "b2"), b2.shape[1]
+    p.Ha, p.Wa, p.Hb, p.Wb, p.B = Ha, Wa, Hb, Wb, B
+    p.ks, p.stride, p.pad = ks, stride, pad
+    if ln is not None:
+        stats, gamma, beta = ln
+        p.ln_stats, p.ln_gamma, p.ln_beta = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    p.per_image, p.terms = int(per_image), (TERMS if terms is None else terms)
+    _f32(out, "out")
+    p.out, p.ldo, p.groups, p.out_gs = out.data_ptr(), ldo, groups, out_gs
+    p.out_bs = out.stride(0) if per_image else 0
+    _lib.check(L().rcot_pk_gemm(C.byref(p), _stream()), "pk_gemm")
+    return out
+
+
+# ------------------------------------------------------------------ LayerNorm
+def ln_stats(x, out=None):
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty(B, H * W, 2, device=x.device, dtype=torch.float32)
+    _lib.check(L().rcot_ln_stats(_ptr(x), C.c_int64(_img_view(x, "x")), B, Cc, H * W, _ptr(out), _stream()), "ln_stats")
+    return out
+
+
+def ln_bwd(dz, x, stats, gamma, dgamma, dbeta, dy=None, dx=None):
+    B, Cc, H, W = x.shape
+    if dx is None:
+        dx = torch.empty_like(x)
+    _lib.check(L().rcot_ln_bwd(_ptr(dz), C.c_int64(_img_view(dz, "dz")), _ptr(x), C.c_int64(_img_view(x, "x")),
+                               _ptr(stats), _ptr(gamma), _ptr(dy), C.c_int64(0 if dy is None else _img_view(dy, "dy")),
+                               _ptr(dx), C.c_int64(_img_view(dx, "dx")), _ptr(dgamma), _ptr(dbeta), B, Cc, H * W,
+                               _stream()), "ln_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------ depthwise 3x3
+def dwconv(x, w, *, out=None, mode=0, flip=False, dg=None, g_out=None, sumsq=None, nsq=0):
+    B, Cn, H, W = x.shape
+    hid = Cn // 2 if mode != 0 else 0
+    if out is None:
+        out = torch.empty(B, hid if mode == 1 else Cn, H, W, device=x.device, dtype=torch.float32)
+    p = DWParams()
+    p.in_, p.in_bs, p.w, p.out, p.out_bs = x.data_ptr(), _img_view(x, "x"), _f32(w).data_ptr(), out.data_ptr(), _img_view(out, "out")
+    p.B, p.Cn, p.H, p.W = B, Cn, H, W
+    p.mode, p.flip, p.hid, p.nsq = mode, int(flip), hid, nsq
+    if dg is not None:
+        p.dg, p.dg_bs = dg.data_ptr(), _img_view(dg, "dg")
+    if g_out is not None:
+        p.g_out, p.g_bs = g_out.data_ptr(), _img_view(g_out, "g_out")
+    if sumsq is not None:
+        p.sumsq = sumsq.data_ptr()
+    _lib.check(L().rcot_dwconv3x3(C.byref(p), _stream()), "dwconv3x3")
+    return out
+
+
+def dwconv_wgrad(x, dout, dw):
+    B, Cn, H, W = x.shape
+    _lib.check(L().rcot_dwconv3x3_wgrad(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(dout),
+                                        C.c_int64(_img_view(dout, "dout")), _ptr(_f32(dw)), B, Cn, H, W, _stream()),
+               "dwconv3x3_wgrad")
+    return dw
+
+
+# ------------------------------------------------------------------ MDTA small-matrix steps
+def attn_fwd(G, sumsq, temperature, w_out, A, Gt, Mpack, MTpack, B, Cc, heads):
+    p = AttnParams()
+    p.B, p.C, p.heads = B, Cc, heads
+    p.G, p.sumsq, p.temperature, p.w_out = G.data_ptr(), sumsq.data_ptr(), temperature.data_ptr(), w_out.data_ptr()
+    p.A, p.Gt, p.Mpack = A.data_ptr(), Gt.data_ptr(), Mpack.data_ptr()
+    p.MTpack = None if MTpack is None else MTpack.data_ptr()
+    p.pack_bs = packed_bytes(Cc, Cc)
+    _lib.check(L().rcot_attn_fwd(C.byref(p), _stream()), "attn_fwd")
+
+
+def attn_bwd(P, sumsq, temperature, w_out, A, Gt, dw_out, dtemp, W12pack, B, Cc, heads):
+    p = AttnParams()
+    p.B, p.C, p.heads = B, Cc, heads
+    p.sumsq, p.temperature, p.w_out = sumsq.data_ptr(), temperature.data_ptr(), w_out.data_ptr()
+    p.A, p.Gt, p.P = A.data_ptr(), Gt.data_ptr(), P.data_ptr()
+    p.dw_out, p.dtemperature, p.W12pack = dw_out.data_ptr(), dtemp.data_ptr(), W12pack.data_ptr()
+    p.pack12_bs = packed_bytes(2 * Cc, 2 * Cc)
+    _lib.check(L().rcot_attn_bwd(C.byref(p), _stream()), "attn_bwd")
+
+
+# ------------------------------------------------------------------ data movement
+def pixel_shuffle(x, inverse=False, out=None):
+    B, Cc, H, W = x.shape
+    if inverse:   # [C,2H,2W] -> [4C,H,W]
+        Cs, Hs, Ws = Cc, H // 2, W // 2
+        shape = (B, 4 * Cc, Hs, Ws)
+    else:         # [4C,H,W] -> [C,2H,2W]
+        Cs, Hs, Ws = Cc // 4, H, W
+        shape = (B, Cs, 2 * H, 2 * W)
+    if out is None:
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    _lib.check(L().rcot_pixel_shuffle(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(out), C.c_int64(_img_view(out, "out")),
+                                      B, Cs, Hs, Ws, int(inverse), _stream()), "pixel_shuffle")
+    return out
+
+
+def axpby(x, y=None, a=1.0, b=1.0, a_vec=None, out=None):
+    """out = a*x + b*y per image block; with a_vec[B]: out = a_vec*x + (1-a_vec)*y."""
+    B = x.shape[0]
+    n = x[0].numel()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _lib.check(L().rcot_axpby(_ptr(out), C.c_int64(_img_view(out, "out")), _ptr(x), C.c_int64(_img_view(x, "x")),
+                              _ptr(y), C.c_int64(0 if y is None else _img_view(y, "y")), C.c_float(a), C.c_float(b),
+                              _ptr(a_vec), B, C.c_int64(n), _stream()), "axpby")
+    return out
+
+
+def channel_sum(x, out):
+    B, Cc, H, W = x.shape
+    _lib.check(L().rcot_channel_sum(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(out), B, Cc, H * W, _stream()),
+               "channel_sum")
+    return out
+
+
+def zero_(t):
+    _lib.check(L().rcot_zero(_ptr(t), C.c_size_t(t.numel() * t.element_size()), _stream()), "zero")
+    return t

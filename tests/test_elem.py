@@ -1,0 +1,147 @@
+"""Unit parity of the building-block kernels against fp64 PyTorch: pixel-as-K GEMM (weight
+gradients, per-image Grams), LayerNorm stats/backward, depthwise 3x3 variants, pixel shuffle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(name, got, ref, rtol=1e-3, atol=1e-4):
+    got = got.detach().cpu().double().reshape(ref.shape)
+    scale = max(1.0, ref.abs().max().item())
+    err = (got - ref).abs()
+    bad = (err > atol * scale + rtol * ref.abs()).sum().item()
+    print(f"{name:24s} max_err={err.max().item():.3e} scale={scale:.3e} bad={bad}/{err.numel()}")
+    assert bad == 0, name
+
+
+@pytest.mark.parametrize("Cin,Cout,k,s,p,H,W", [(48, 24, 3, 1, 1, 16, 16), (3, 64, 5, 1, 2, 16, 16),
+                                                (64, 64, 4, 2, 1, 16, 16), (256, 512, 3, 1, 1, 8, 8),
+                                                (512, 512, 4, 2, 1, 4, 4), (512, 512, 4, 2, 1, 2, 2),
+                                                (96, 3, 3, 1, 1, 10, 14), (96, 300, 1, 1, 0, 8, 8)])
+def test_conv_wgrad(cuda_lib, Cin, Cout, k, s, p, H, W):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(Cin + Cout + k)
+    B = 3
+    x = torch.randn(B, Cin, H, W, generator=g)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    dy = torch.randn(B, Cout, Ho, Wo, generator=g)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, k, k), dy.double(), stride=s, padding=p)
+    prev = torch.randn(Cout, Cin, k, k, generator=g)
+    out = prev.cuda().clone()
+    ops.pk_gemm(dy.cuda(), x.cuda(), out, ldo=Cin * k * k, ks=k, stride=s, pad=p)
+    _close("dW", out, prev.double() + ref)
+
+
+def test_wgrad_ln_and_concat(cuda_lib):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W, N = 2, 96, 8, 16, 510
+    x = torch.randn(B, C, H, W, generator=g)
+    du = torch.randn(B, N, H, W, generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    xd = x.double()
+    mu = xd.mean(1, keepdim=True)
+    rstd = 1 / torch.sqrt(((xd - mu) ** 2).mean(1, keepdim=True) + 1e-5)
+    z = (xd - mu) * rstd * gamma.double().view(1, -1, 1, 1) + beta.double().view(1, -1, 1, 1)
+    ref = torch.einsum("bnhw,bchw->nc", du.double(), z)
+    stats = ops.ln_stats(x.cuda())
+    _close("stats", stats, torch.stack([mu.flatten(1), rstd.flatten(1)], -1))
+    out = torch.zeros(N, C, device="cuda")
+    ops.pk_gemm(du.cuda(), x.cuda(), out, ldo=C, ln=(stats, gamma.cuda(), beta.cuda()))
+    _close("dW_ln", out, ref)
+    x2 = torch.randn(B, 48, H, W, generator=g)
+    ref2 = torch.einsum("bnhw,bchw->nc", du.double(), torch.cat([x, x2], 1).double())
+    out2 = torch.zeros(N, C + 48, device="cuda")
+    ops.pk_gemm(du.cuda(), x.cuda(), out2, ldo=C + 48, b2=x2.cuda())
+    _close("dW_cat", out2, ref2)
+
+
+@pytest.mark.parametrize("C,heads,HW", [(48, 1, (16, 16)), (96, 4, (8, 8)), (384, 8, (4, 4)), (384, 4, (4, 8))])
+def test_gram_per_image(cuda_lib, C, heads, HW):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    B = 2
+    qkv = torch.randn(B, 3 * C, *HW, generator=g)
+    c = C // heads
+    q = qkv[:, :C].reshape(B, heads, c, -1).double()
+    k = qkv[:, C:2 * C].reshape(B, heads, c, -1).double()
+    ref = q @ k.transpose(-1, -2)
+    d = qkv.cuda()
+    G = torch.zeros(B, heads, c, c, device="cuda")
+    ops.pk_gemm(d[:, :C], d[:, C:2 * C], G, ldo=c, per_image=True, groups=heads, out_gs=c * c)
+    _close("gram", G, ref)
+    v = qkv[:, 2 * C:].flatten(2).double()
+    dy = torch.randn(B, C, *HW, generator=g)
+    P = torch.zeros(B, C, C, device="cuda")
+    ops.pk_gemm(dy.cuda(), d[:, 2 * C:], P, ldo=C, per_image=True)
+    _close("P", P, dy.flatten(2).double() @ v.transpose(1, 2))
+
+
+def test_layernorm_bwd(cuda_lib):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, C, H, W = 2, 96, 8, 12
+    x = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
+    dz = torch.randn(B, C, H, W, generator=g)
+    dy = torch.randn(B, C, H, W, generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    x64 = x.double().requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    from oracle import restormer_ref as R
+    z = R.layer_norm_c(x64, g64, b64)
+    z.backward(dz.double())
+    stats = ops.ln_stats(x.cuda())
+    dgam, dbet = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = ops.ln_bwd(dz.cuda(), x.cuda(), stats, gamma.cuda(), dgam, dbet, dy=dy.cuda())
+    _close("dx", dx, x64.grad + dy.double())
+    _close("dgamma", dgam, g64.grad)
+    _close("dbeta", dbet, b64.grad)
+
+
+def test_dwconv_variants(cuda_lib):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    B, hid, H, W = 2, 127, 9, 12
+    Cn = 2 * hid
+    u = torch.randn(B, Cn, H, W, generator=g)
+    w = torch.randn(Cn, 1, 3, 3, generator=g) / 3
+    u64 = u.double().requires_grad_(True)
+    w64 = w.double().requires_grad_(True)
+    full = F.conv2d(u64, w64, padding=1, groups=Cn)
+    a, b = full.chunk(2, 1)
+    gate = F.gelu(a) * b
+    dgate = torch.randn(B, hid, H, W, generator=g)
+    gate.backward(dgate.double())
+    ud, wd = u.cuda(), w.cuda()
+    sumsq = torch.zeros(B, 100, device="cuda")
+    out = ops.dwconv(ud, wd, sumsq=sumsq, nsq=100)
+    _close("dw plain", out, full.detach())
+    _close("sumsq", sumsq, (full.detach()[:, :100] ** 2).sum((2, 3)))
+    _close("gate", ops.dwconv(ud, wd, mode=1), gate.detach())
+    gout = torch.empty(B, hid, H, W, device="cuda")
+    dab = ops.dwconv(ud, wd, mode=2, dg=dgate.cuda(), g_out=gout, out=torch.empty_like(ud))
+    _close("g_out", gout, gate.detach())
+    du = ops.dwconv(dab, wd, flip=True)
+    _close("du", du, u64.grad)
+    dw = torch.zeros_like(wd)
+    ops.dwconv_wgrad(ud, dab, dw)
+    _close("dw_w", dw, w64.grad)
+
+
+def test_pixel_shuffle_axpby(cuda_lib):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 24, 6, 10, generator=g)
+    xd = x.cuda()
+    assert torch.equal(ops.pixel_shuffle(xd).cpu(), F.pixel_shuffle(x, 2))
+    assert torch.equal(ops.pixel_shuffle(xd, inverse=True).cpu(), F.pixel_unshuffle(x, 2))
+    wide = torch.zeros(2, 10, 12, 20, device="cuda")
+    ops.pixel_shuffle(xd, out=wide[:, 2:8])
+    assert torch.equal(wide[:, 2:8].cpu(), F.pixel_shuffle(x, 2)) and wide[:, :2].abs().max() == 0
+    y = torch.randn(2, 24, 6, 10, generator=g)
+    torch.testing.assert_close(ops.axpby(xd, y.cuda(), 1.0, 0.8).cpu(), x + 0.8 * y)
+    al = torch.rand(2, generator=g)
+    torch.testing.assert_close(ops.axpby(xd, y.cuda(), a_vec=al.cuda()).cpu(),
+                               al.view(2, 1, 1, 1) * x + (1 - al.view(2, 1, 1, 1)) * y)
