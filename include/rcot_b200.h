@@ -187,6 +187,44 @@ int rcot_channel_sum(const float* x, int64_t x_bs, float* out, int B, int C, int
 /* cudaMemsetAsync(ptr, 0, bytes) on the stream (graph-capturable) */
 int rcot_zero(void* ptr, size_t bytes, rcot_stream_t stream);
 
+/* ---------------------------------------------------------------- F_net fully connected tail
+ * Net_Restormer.py:496-498,512-520 (fc, fc1, LeakyReLU, fc2) -- fp32 CUDA-core, row-major [B,K] x [O,K]^T.
+ * mask (same shape as the result) multiplies by (mask > 0 ? 1 : slope): LeakyReLU derivative taken
+ * from the saved post-activation. */
+int rcot_linear_fwd(const float* x, const float* W, const float* bias, const float* mask, float* y, int B, int K,
+                    int O, int act, float slope, rcot_stream_t stream);
+int rcot_linear_dgrad(const float* dy, const float* W, const float* mask, float* dx, int B, int K, int O, float slope,
+                      rcot_stream_t stream);
+/* dW += dy^T x ; db += sum_b dy (db may be NULL) */
+int rcot_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int B, int K, int O,
+                      rcot_stream_t stream);
+
+/* ---------------------------------------------------------------- transport cost (trainer.py:320-343)
+ * stage 1, per (image, channel): acc[0] += sum res^2, acc[1] += Fourier penalty (sum over the batch),
+ * acc[2] += sum |out - target| (target may be NULL = unpaired); gfou = d(Fourier)/d(res).
+ * de_id: int64 [B] on the device (de_id < 3 selects the mean|F|^2/2 branch).  P: power of two <= 128.
+ * stage 2: dout = dF - sigma*(res/(N*rmse) + gfou) + Sigma*sign(out-target)/N, rmse = sqrt(acc[0]/N),
+ * N = n_global (elements of the GLOBAL batch; acc[0] must be all-reduced first when data parallel). */
+int rcot_cost_stage1(const float* out, const float* degraded, const float* target, const int64_t* de_id, float* gfou,
+                     float* acc, int B, int P, rcot_stream_t stream);
+int rcot_cost_stage2(const float* out, const float* degraded, const float* target, const float* gfou, const float* dF,
+                     const float* acc, float* dout, float sigma, float Sigma, double n_global, int64_t n,
+                     rcot_stream_t stream);
+
+/* ---------------------------------------------------------------- gradient penalty helpers (trainer.py:300-305) */
+int rcot_sample_sumsq(const float* x, float* out, int B, int64_t n, rcot_stream_t stream); /* out[b] += sum x[b,:]^2 */
+/* coef[b] = 20/B_global * (|g_b|-1)/|g_b| ; loss[0] += 10/B_global * sum_b (|g_b|-1)^2 */
+int rcot_gp_coef(const float* sumsq, float* coef, float* loss, int B, int B_global, rcot_stream_t stream);
+/* out[0] += scale * (sum_{i>=n_neg} x[i] - sum_{i<n_neg} x[i]) */
+int rcot_signed_sum(const float* x, float* out, int n, int n_neg, float scale, rcot_stream_t stream);
+
+/* ---------------------------------------------------------------- optimizers on flat buffers
+ * torch.optim.RMSprop / Adam defaults as used at trainer.py:121-126; g is multiplied by gscale first. */
+int rcot_rmsprop(float* p, const float* g, float* sq, int64_t n, float lr, float alpha, float eps, float gscale,
+                 rcot_stream_t stream);
+int rcot_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+              int step, float gscale, rcot_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -277,7 +277,7 @@ class ConvSpec:
             ps.add_pack(name, "dgrad")
 
 
-def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True):
+def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True, need_res_grad=True):
     """Dense conv (stride 1, no bias), optional concat input [x, x2] and residual epilogue."""
     ps = cs.ps
     y = ops.pm_gemm(x, ps.pack(cs.name, "fwd"), cs.Cout, ks=cs.ks, pad=cs.pad, x2=x2, residual=residual)
@@ -293,7 +293,7 @@ def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True):
                 else:
                     tape.add_grad(x, dx[:, :x.shape[1]])
                     tape.add_grad(x2, dx[:, x.shape[1]:])
-            if residual is not None:
+            if residual is not None and need_res_grad:
                 tape.add_grad(residual, dy)
         tape.record(y, bwd)
     return y
@@ -308,12 +308,82 @@ def shuffle_fwd(x, inverse, tape, out=None):
     return y
 
 
-def axpby_fwd(x, y, a, b, tape):
-    """z = a*x + b*y with gradients to both."""
+def axpby_fwd(x, y, a, b, tape, need_dx=True):
+    """z = a*x + b*y with gradients to both (x only if need_dx)."""
     z = ops.axpby(x, y, a, b)
     if tape is not None and tape.enabled:
         def bwd(dz):
-            tape.add_grad(x, ops.axpby(dz, None, a, 0.0))
+            if need_dx:
+                tape.add_grad(x, ops.axpby(dz, None, a, 0.0))
             tape.add_grad(y, ops.axpby(dz, None, b, 0.0))
         tape.record(z, bwd)
     return z
+
+
+def shuffle_cat_fwd(t, skip, tape):
+    """cat([PixelShuffle(2)(t), skip], dim=1) written into one buffer (Net_Restormer.py:368-369)."""
+    B, C4, H, W = t.shape
+    Cs = C4 // 4
+    out = torch.empty(B, Cs + skip.shape[1], 2 * H, 2 * W, device=t.device, dtype=torch.float32)
+    ops.pixel_shuffle(t, out=out[:, :Cs])
+    ops.axpby(skip, None, 1.0, 0.0, out=out[:, Cs:])
+    if tape is not None and tape.enabled:
+        def bwd(dcat):
+            tape.add_grad(t, ops.pixel_shuffle(dcat[:, :Cs], inverse=True))
+            tape.add_grad(skip, dcat[:, Cs:])
+        tape.record(out, bwd)
+    return out
+
+
+# ---------------------------------------------------------------------------------- standalone modules
+class LeafProgram:
+    """Program behind a stand-alone Attention / FeedForward / TransformerBlock / Downsample /
+    Upsample / OverlapPatchEmbed module (the reference's classes are usable on their own)."""
+
+    def __init__(self, named, device, kind, C, heads, strip=""):
+        self.kind, self.strip = kind, strip
+        self.ps = ParamSet(named, device)
+        self.grad_names = {k[len(strip):] for k in named}
+        if kind == "block":
+            self.bs = BlockSpec(self.ps, "", C, heads)
+        elif kind == "attn":
+            self.bs = BlockSpec(self.ps, "", C, heads, has_ffn=False)
+        elif kind == "ffn":
+            self.bs = BlockSpec(self.ps, "", C, 1, has_attn=False)
+        elif kind in ("down", "up", "embed"):
+            self.cs = ConvSpec(self.ps, next(iter(named)), 3, 1)
+        else:
+            raise ValueError(kind)
+        self.ps.finalize()
+
+    def pview(self, name):
+        return self.ps.p[self.strip + name]
+
+    def gview(self, name):
+        return self.ps.g[self.strip + name]
+
+    def run(self, x, tape):
+        kind = self.kind
+        if kind == "block":
+            return block_fwd(self.bs, x, tape)
+        if kind == "attn":
+            bs = self.bs
+            y, _ = mdta_fwd(bs, x, None, False, False)
+            if tape.enabled:
+                def bwd(dy):
+                    _, ctx = mdta_fwd(bs, x, None, False, True)
+                    tape.add_grad(x, mdta_bwd(bs, x, dy, None, False, ctx))
+                tape.record(y, bwd)
+            return y
+        if kind == "ffn":
+            bs = self.bs
+            y = gdfn_fwd(bs, x, None, False)
+            if tape.enabled:
+                tape.record(y, lambda dy: tape.add_grad(x, gdfn_bwd(bs, x, dy, None, False)))
+            return y
+        y = conv_fwd(self.cs, x, tape)
+        if kind == "down":
+            y = shuffle_fwd(y, True, tape)
+        elif kind == "up":
+            y = shuffle_fwd(y, False, tape)
+        return y

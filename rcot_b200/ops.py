@@ -332,3 +332,64 @@ def channel_sum(x, out):
 def zero_(t):
     _lib.check(L().rcot_zero(_ptr(t), C.c_size_t(t.numel() * t.element_size()), _stream()), "zero")
     return t
+
+
+# ------------------------------------------------------------------ F_net fully connected tail
+def linear_fwd(x, W, bias=None, act=False, mask=None, slope=0.2):
+    B, K = x.shape
+    O = W.shape[0]
+    y = torch.empty(B, O, device=x.device, dtype=torch.float32)
+    _lib.check(L().rcot_linear_fwd(_ptr(x), _ptr(W), _ptr(bias), _ptr(mask), _ptr(y), B, K, O, int(act),
+                                   C.c_float(slope), _stream()), "linear_fwd")
+    return y
+
+
+def linear_dgrad(dy, W, mask=None, slope=0.2):
+    B, O = dy.shape
+    K = W.shape[1]
+    dx = torch.empty(B, K, device=dy.device, dtype=torch.float32)
+    _lib.check(L().rcot_linear_dgrad(_ptr(dy), _ptr(W), _ptr(mask), _ptr(dx), B, K, O, C.c_float(slope), _stream()),
+               "linear_dgrad")
+    return dx
+
+
+def linear_wgrad(dy, x, dW, db=None):
+    B, O = dy.shape
+    K = x.shape[1]
+    _lib.check(L().rcot_linear_wgrad(_ptr(dy), _ptr(x), _ptr(dW), _ptr(db), B, K, O, _stream()), "linear_wgrad")
+
+
+# ------------------------------------------------------------------ objective
+def cost_stage1(out, degraded, target, de_id, gfou, acc):
+    B, _, P, _ = out.shape
+    _lib.check(L().rcot_cost_stage1(_ptr(out), _ptr(degraded), _ptr(target), _ptr(de_id), _ptr(gfou), _ptr(acc), B, P,
+                                    _stream()), "cost_stage1")
+
+
+def cost_stage2(out, degraded, target, gfou, dF, acc, dout, sigma, Sigma, n_global):
+    _lib.check(L().rcot_cost_stage2(_ptr(out), _ptr(degraded), _ptr(target), _ptr(gfou), _ptr(dF), _ptr(acc), _ptr(dout),
+                                    C.c_float(sigma), C.c_float(Sigma), C.c_double(n_global), C.c_int64(out.numel()),
+                                    _stream()), "cost_stage2")
+
+
+def sample_sumsq(x, out):
+    B = x.shape[0]
+    _lib.check(L().rcot_sample_sumsq(_ptr(x), _ptr(out), B, C.c_int64(x[0].numel()), _stream()), "sample_sumsq")
+
+
+def gp_coef(sumsq, coef, loss, B_global):
+    _lib.check(L().rcot_gp_coef(_ptr(sumsq), _ptr(coef), _ptr(loss), sumsq.numel(), B_global, _stream()), "gp_coef")
+
+
+def signed_sum(x, out, n_neg, scale):
+    _lib.check(L().rcot_signed_sum(_ptr(x), _ptr(out), x.numel(), n_neg, C.c_float(scale), _stream()), "signed_sum")
+
+
+def rmsprop(p, g, sq, n, lr, alpha=0.99, eps=1e-8, gscale=1.0):
+    _lib.check(L().rcot_rmsprop(_ptr(p), _ptr(g), _ptr(sq), C.c_int64(n), C.c_float(lr), C.c_float(alpha),
+                                C.c_float(eps), C.c_float(gscale), _stream()), "rmsprop")
+
+
+def adam(p, g, m, v, n, lr, step, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
+    _lib.check(L().rcot_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(n), C.c_float(lr), C.c_float(b1),
+                             C.c_float(b2), C.c_float(eps), step, C.c_float(gscale), _stream()), "adam")
