@@ -71,9 +71,8 @@ class _ProgramFn(torch.autograd.Function):
     """One autograd node for a whole module call; backward = hand-derived kernels via the tape."""
 
     @staticmethod
-    def forward(ctx, prog, run, x, *params):
+    def forward(ctx, prog, run, need, x, *params):
         from rcot_b200.engine import Tape
-        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         tape = Tape(enabled=need)
         xin = x.detach().contiguous()
         out = run(prog, xin, tape)
@@ -88,15 +87,17 @@ class _ProgramFn(torch.autograd.Function):
         leaves = tape.backward(ctx.out, dout.contiguous().clone())
         dx = tape.grad_of(leaves, ctx.xin) if ctx.x_needs else None
         grads = []
-        for name, need in zip(prog.param_order, ctx.needs_input_grad[3:]):
+        for name, need in zip(prog.param_order, ctx.needs_input_grad[4:]):
             grads.append(prog.gview(name).clone() if need and name in prog.grad_names else None)
-        return (None, None, dx, *grads)
+        return (None, None, None, dx, *grads)
 
 
 def _run_program(module, prog, run, x):
     named = module._named()
     prog.param_order = list(named)
-    return _ProgramFn.apply(prog, run, x, *named.values())
+    # grad mode is off inside Function.forward, so decide here whether a tape is needed
+    need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in named.values()))
+    return _ProgramFn.apply(prog, run, need, x, *named.values())
 
 
 # ---------------------------------------------------------------------------------- leaf modules

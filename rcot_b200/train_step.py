@@ -1,0 +1,105 @@
+"""One adversarial iteration of the reference's training loop (trainer.py:247-346) on the engine:
+
+    F-sub   critic step        L_F  = -mean f(target) + mean f(T(x))            RMSprop(lr)   :262-280
+    GP      gradient penalty   L_GP = 10 mean_b (|grad f(x~_b)| - 1)^2           RMSprop(lr)   :283-308
+    T-sub   transport step     L_T  = -mean f(T(x)) + sigma (rmse + fourier) [+ Sigma L1]      :311-346
+                                                                               RMSprop(lr/2)
+
+Value-neutral deviation from the reference: T(x) is evaluated ONCE per iteration (the reference
+evaluates it at :271 without a graph and again at :318 with one; T's weights do not change in
+between, so both evaluations are identical).
+
+Data parallel: every rank holds a batch shard and the full weights; the three gradient buffers are
+all-reduced (sum) before their optimizer steps, and the global-batch RMSE gets its sum of squares
+all-reduced between the two cost stages -- with batch-mean terms scaled by 1/B_global and the
+Fourier term left as a batch SUM this reproduces the single-process global-batch gradients
+(SURVEY section 8e).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .engine import Tape
+
+
+class FlatOptimizer:
+    """torch.optim.RMSprop / Adam (defaults) over a ParamSet's flat buffers."""
+
+    def __init__(self, ps, kind="RMSprop"):
+        if kind not in ("RMSprop", "Adam"):
+            raise ValueError(f"unsupported optimizer {kind!r} (reference supports RMSprop and Adam)")
+        self.ps, self.kind = ps, kind
+        self.sq = torch.zeros_like(ps.flat)
+        self.m = torch.zeros_like(ps.flat) if kind == "Adam" else None
+        self.steps = 0
+
+    def step(self, lr, n=None):
+        ps = self.ps
+        n = ps.numel if n is None else n
+        self.steps += 1
+        if self.kind == "RMSprop":
+            ops.rmsprop(ps.flat, ps.grad, self.sq, n, lr)
+        else:
+            ops.adam(ps.flat, ps.grad, self.m, self.sq, n, lr, self.steps)
+        ps.repack()
+
+
+class OTTrainStep:
+    def __init__(self, Tprog, Fprog, optimizer="RMSprop", sigma=1.0, Sigma=10000.0, group=None):
+        self.T, self.F = Tprog, Fprog
+        self.sigma, self.Sigma = float(sigma), float(Sigma)
+        self.T_opt = FlatOptimizer(Tprog.ps, optimizer)
+        self.F_opt = FlatOptimizer(Fprog.ps, optimizer)
+        self.group = group
+        self.world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.group)
+
+    def iteration(self, degraded, target, de_id, alpha, paired, lr):
+        """degraded/target: [B,3,P,P] local shard; de_id: int64 [B]; alpha: [B] gradient-penalty
+        interpolation draws (trainer.py:284, CPU RNG in the reference).  Returns device tensors
+        {loss_F, loss_gp, loss_T, loss_mse} (global-batch values), no host sync."""
+        T, F = self.T, self.F
+        B, _, P, _ = degraded.shape
+        Bg = B * self.world
+        tape = Tape()
+        out = T.forward(degraded, tape)
+        # ---------------- F-sub
+        F.ps.zero_grad()
+        loss_F = F.critic_step(target, out, Bg)
+        self._allreduce(F.ps.grad)
+        self.F_opt.step(lr)
+        # ---------------- gradient penalty (on the updated potential)
+        F.ps.zero_grad()
+        interp = ops.axpby(target, out, a_vec=alpha)
+        loss_gp = F.penalty_step(interp, Bg)
+        self._allreduce(F.ps.grad)
+        self.F_opt.step(lr, n=F.n_without_fc2_bias)      # fc2.bias has no gradient here -> skipped
+        # ---------------- T-sub
+        T.ps.zero_grad()
+        f, dF = F.input_grad(out, -1.0 / Bg)
+        acc = torch.zeros(4, device=out.device)          # [sum res^2, fourier, sum |out-target|, sum f]
+        gfou = torch.empty_like(out)
+        tgt = target if paired else None
+        ops.cost_stage1(out, degraded, tgt, de_id, gfou, acc)
+        ops.signed_sum(f, acc[3:], 0, 1.0)
+        self._allreduce(acc)
+        n_global = float(Bg * 3 * P * P)
+        dout = torch.empty_like(out)
+        ops.cost_stage2(out, degraded, tgt, gfou, dF, acc, dout, self.sigma, self.Sigma, n_global)
+        tape.backward(out, dout)
+        self._allreduce(T.ps.grad[:T.ps.n_used])
+        self.T_opt.step(lr / 2, n=T.ps.n_used)           # never-used modules have grad None -> skipped
+        rmse = torch.sqrt(acc[0] / n_global)
+        loss_T = -acc[3] / Bg + self.sigma * (rmse + acc[1])
+        if paired:
+            loss_T = loss_T + self.Sigma * acc[2] / n_global
+        if self.world > 1:
+            self._allreduce(loss_F)
+            self._allreduce(loss_gp)
+        return {"loss_F": loss_F[0], "loss_gp": loss_gp[0], "loss_T": loss_T, "loss_mse": rmse, "out": out}
