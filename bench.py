@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the RCOT training hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (sm_100a kernels)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU arm: the reference algorithm
+                                                                        (oracle port) on the host cores
+
+A "step" is one full adversarial iteration (F-sub critic step, gradient penalty step, T-sub transport
+step with the Fourier-residual cost, three optimizer steps) on one synthetic batch of 128x128 patches,
+per-GPU batch 32 (weak scaling: global batch = 32 * N; gradients all-reduced with NCCL).
+`value`  = images/s with the batches already resident in HBM.
+`e2e`    = images/s through trainer.train_one() from pinned HOST batches (H2D inside the timed region,
+           losses read back to the host every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "training images/sec at 128x128 bs=32"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--patch", type=int, default=128)
+    ap.add_argument("--terms", type=int, default=3, help="3: bf16x3 split products (fp32-class), 1: bf16 products")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def synth_host_batches(n, B, P, seed=0):
+    """n pinned host batches shaped like the reference DataLoader's: ([names, de_id], degraded, target).
+    Half of each batch is denoise sigma=25 (de_id 1, |F|^2 branch), half derain-like (de_id 3, |F| branch)."""
+    out = []
+    for i in range(n):
+        g = torch.Generator().manual_seed(seed * 7919 + i)
+        tgt = torch.floor(torch.rand(B, 3, P, P, generator=g) * 255) / 255
+        deg = torch.floor(torch.clamp(tgt * 255 + 25 * torch.randn(B, 3, P, P, generator=g), 0, 255)) / 255
+        streak = (torch.rand(B, 1, P, P, generator=g) > 0.97).float() * 0.6
+        rain = torch.clamp(tgt + streak, 0, 1)
+        de_id = torch.tensor([1 if j % 2 == 0 else 3 for j in range(B)])
+        deg = torch.where((de_id == 1).view(B, 1, 1, 1), deg, rain)
+        pin = torch.cuda.is_available()
+        out.append(([[f"s{i}_{j}" for j in range(B)], de_id],
+                    deg.pin_memory() if pin else deg, tgt.pin_memory() if pin else tgt))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake": 0x80}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.1)
+        except Exception as e:  # NVML unavailable: report it instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def block_algorithmic_bytes(B, P):
+    """per TransformerBlock call fwd 5*B*C*H*W*4 + W, bwd 8*B*C*H*W*4 + 2W; sum over the 102
+    calls of one T_net forward: sum C*N = 49.35 M elements per 128^2 image, block weights 0.2567 GB."""
+    elems = 49.35e6 * (P / 128.0) ** 2
+    wbytes = 0.2567e9
+    return 13 * B * elems * 4 + 3 * wbytes
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+def cpu_reference_rate(P, B, steps, warmup, budget_s=200.0):
+    """The reference algorithm on the host cores: oracle/train_ref.py (a restatement of trainer.py:247-346 +
+    Net_Restormer.py validated against the unmodified reference; the reference itself is Python and is not
+    on the GPU box).  Returns (images/s, cores, steps actually timed)."""
+    import Net_Restormer as N
+    from oracle import train_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    T = N.T_net(decoder=True)
+    F = N.F_net(patch_size=P)
+    T_sd = {k: v.detach().clone() for k, v in T.state_dict().items()}
+    F_sd = {k: v.detach().clone() for k, v in F.state_dict().items()}
+    Ts, Fs = {}, {}
+    batches = synth_host_batches(max(1, warmup + steps), B, P, seed=1)
+    t_used, done, t0 = 0.0, 0, time.perf_counter()
+    for i in range(warmup + steps):
+        ([_, de_id], deg, tgt) = batches[i % len(batches)]
+        alpha = torch.rand(B)
+        s = time.perf_counter()
+        with torch.enable_grad():
+            train_ref.train_iteration(T_sd, F_sd, Ts, Fs, deg, tgt, de_id, alpha, 1e-4, 1.0, 10000.0, True)
+        e = time.perf_counter()
+        if i >= warmup:
+            t_used += e - s
+            done += 1
+        if e - t0 > budget_s and done >= 1:
+            break
+    return B * done / t_used, cores, done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bs = 2
+    rate, cores, done = cpu_reference_rate(args.patch, Bs, args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * Bs / rate, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"one full adversarial iteration (F-sub + GP + T-sub), {args.patch}x{args.patch} patches",
+                       "patch": args.patch, "per_gpu_batch": args.batch, "paired": True},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{done} iteration(s) of the same step at batch {Bs} (bounded sample), PyTorch CPU fp32, "
+                                       f"{cores} threads; oracle/train_ref.py"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import Net_Restormer as N
+    import trainer
+    from rcot_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl")
+    ops.TERMS = args.terms
+    B, P, K, W = args.batch, args.patch, args.steps, max(args.warmup, 3)
+    trainer.opt = trainer.parser.parse_args(["--batchSize", str(B * world), "--patch_size", str(P), "--pairnum", "1000000000",
+                                             "--no_dump"])
+    torch.manual_seed(0)
+    Tnet = N.T_net(decoder=True).cuda()
+    Fnet = N.F_net(patch_size=P).cuda()
+    step = trainer._train_step(Tnet, Fnet, "RMSprop")
+    lr = 1e-4
+    host = synth_host_batches(4, B, P, seed=rank)
+    dev = [(b[1].cuda(), b[2].cuda(), b[0][1].cuda()) for b in host]
+    alphas = [torch.rand(B).cuda() for _ in range(4)]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step(i):
+        d, t, ids = dev[i % 4]
+        return step.iteration(d, t, ids, alphas[i % 4], True, lr)
+
+    for i in range(W):
+        resident_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        r = resident_step(i)
+    e1.record()
+    barrier()
+    launches = ops.LAUNCHES - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = ms.item()
+    value = B * world * K / (ms / 1000.0)
+
+    # ---- end to end: pinned host batches -> trainer.train_one -> losses read back every step
+    h2d = sum(t.numel() * t.element_size() for t in (host[0][1], host[0][2], host[0][0][1])) + 4 * B
+    torch.manual_seed(1)
+    for i in range(2):
+        trainer.train_one(step, host[i % 4], i, lr)
+    barrier()
+    e0.record()
+    for i in range(K):
+        r, _, _ = trainer.train_one(step, host[i % 4], i, lr)
+        losses = torch.stack([r["loss_F"], r["loss_T"], r["loss_mse"]]).tolist()      # D2H + sync each step
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
+    e2e = B * world * K / (ms2.item() / 1000.0)
+
+    # ---- per-kernel CUDA-event timing of the same step (one extra step, outside the timed regions)
+    roof, kernels = None, None
+    peak, peak_src = peaks()
+    if not args.no_profile:
+        ops.PROF = ops.Profiler()
+        resident_step(0)
+        summ = ops.PROF.summary()
+        ops.PROF = None
+        tot = sum(v["ms"] for v in summ.values())
+        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4),
+                       "GBps": round(v["bytes"] / 1e9 / (v["ms"] / 1e3), 1) if v["ms"] > 0 else None}
+                   for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+        top, tv = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        achieved = tv["bytes"] / 1e9 / (tv["ms"] / 1e3)
+        roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "launches": tv["launches"], "avg_launch_ms": tv["ms"] / tv["launches"],
+                "note": "achieved = algorithmic bytes of all launches of this kernel in one step / their summed "
+                        "CUDA-event time, taken on one extra step right after the timed region"}
+    barrier()
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 storage, bf16x3 split products on tcgen05 (fp32-class)" if args.terms == 3 else "bf16 products, fp32 storage/accumulate",
+            "data": "synthetic",
+            "config": {"workload": f"one full adversarial iteration (F-sub + GP + T-sub, 3 optimizer steps), {P}x{P} patches, "
+                                   f"per-GPU batch {B}, paired, de_id mix [1,3]",
+                       "patch": P, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "working set per step (tens of GB) >> 126 MB L2; no explicit flush"},
+            "clocks": sampler.result(), "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                    "ms_per_step": ms2.item() / K},
+            "losses_last_step": losses}
+    if roof:
+        line["roofline"] = roof
+        line["kernels"] = kernels
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            rate, cores, done = cpu_reference_rate(P, 2, 1, 1, budget_s=60.0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{done} iteration of the same step at batch 2 after 1 warm-up, PyTorch CPU "
+                                              f"fp32 on {cores} threads (oracle/train_ref.py)"}
+        except Exception as e:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {type(e).__name__}: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,8 +153,17 @@ class PackTable:
 
     def repack(self):
         """Re-pack every tensor from its current values (call after each optimizer step)."""
+        global LAUNCHES
+        LAUNCHES += 1
+        e0 = e1 = None
+        if PROF is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(L().rcot_pack_weights(_ptr(self.table), len(self.entries), C.c_size_t(self.max_elems), _stream()),
                    "pack_weights")
+        if PROF is not None:
+            e1.record()
+            PROF.records.append(("pack_weights", e0, e1, self.total + sum(e[0].numel() * 4 for e in self.entries)))
 
 
 def pack_single(w: torch.Tensor, kind: str):
@@ -393,3 +402,80 @@ def rmsprop(p, g, sq, n, lr, alpha=0.99, eps=1e-8, gscale=1.0):
 def adam(p, g, m, v, n, lr, step, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
     _lib.check(L().rcot_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(n), C.c_float(lr), C.c_float(b1),
                              C.c_float(b2), C.c_float(eps), step, C.c_float(gscale), _stream()), "adam")
+
+
+# ------------------------------------------------------------------ launch accounting / per-kernel timing
+class Profiler:
+    """Per-op CUDA-event timing on the launching stream plus the op's ALGORITHMIC bytes (every
+    operand counted once: what an ideal kernel must move), for bench.py's roofline block."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, nbytes in self.records:
+            a = agg.setdefault(name, [0, 0.0, 0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += nbytes
+        return {k: {"launches": v[0], "ms": v[1], "bytes": v[2]} for k, v in agg.items()}
+
+
+PROF: Profiler | None = None
+LAUNCHES = 0
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
+def _instrument(name, bytes_fn):
+    def deco(fn):
+        def wrapped(*a, **k):
+            global LAUNCHES
+            LAUNCHES += 1
+            if PROF is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            PROF.records.append((name, e0, e1, int(bytes_fn(a, k, r))))
+            return r
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
+def _pm_bytes(a, k, r):
+    x, N = a[0], a[2]
+    ks = k.get("ks", 1)
+    Kdim = (x.shape[1] + (k["x2"].shape[1] if k.get("x2") is not None else 0)) * ks * ks
+    return (_nb(x, k.get("x2"), k.get("residual"), k.get("mask_y")) + r.shape[0] * N * r.shape[2] * r.shape[3] * 4 +
+            N * Kdim * 4 * (r.shape[0] if k.get("wpack_bs", 0) else 1))
+
+
+pm_gemm = _instrument("pm_gemm", _pm_bytes)(pm_gemm)
+pk_gemm = _instrument("pk_gemm", lambda a, k, r: _nb(a[0], a[1], k.get("b2"), a[2]))(pk_gemm)
+ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
+ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)
+dwconv = _instrument("dwconv", lambda a, k, r: _nb(a[0], r, k.get("dg"), k.get("g_out")))(dwconv)
+dwconv_wgrad = _instrument("dwconv_wgrad", lambda a, k, r: _nb(a[0], a[1]))(dwconv_wgrad)
+attn_fwd = _instrument("attn_fwd", lambda a, k, r: _nb(a[0], a[3]) * 2)(attn_fwd)
+attn_bwd = _instrument("attn_bwd", lambda a, k, r: _nb(a[0], a[3]) * 3)(attn_bwd)
+pixel_shuffle = _instrument("pixel_shuffle", lambda a, k, r: _nb(a[0], a[0]))(pixel_shuffle)
+axpby = _instrument("axpby", lambda a, k, r: _nb(a[0], a[1] if len(a) > 1 else k.get("y"), r))(axpby)
+channel_sum = _instrument("channel_sum", lambda a, k, r: _nb(a[0]))(channel_sum)
+zero_ = _instrument("zero", lambda a, k, r: _nb(a[0]))(zero_)
+linear_fwd = _instrument("linear_fwd", lambda a, k, r: _nb(a[0], a[1], r))(linear_fwd)
+linear_dgrad = _instrument("linear_dgrad", lambda a, k, r: _nb(a[0], a[1], r))(linear_dgrad)
+linear_wgrad = _instrument("linear_wgrad", lambda a, k, r: _nb(a[0], a[1], a[2]) + _nb(a[2]))(linear_wgrad)
+cost_stage1 = _instrument("cost_stage1", lambda a, k, r: _nb(a[0], a[1], a[2], a[4]))(cost_stage1)
+cost_stage2 = _instrument("cost_stage2", lambda a, k, r: _nb(a[0], a[1], a[2], a[3], a[4], a[6]))(cost_stage2)
+sample_sumsq = _instrument("sample_sumsq", lambda a, k, r: _nb(a[0]))(sample_sumsq)
+gp_coef = _instrument("gp_coef", lambda a, k, r: 0)(gp_coef)
+signed_sum = _instrument("signed_sum", lambda a, k, r: 0)(signed_sum)
+rmsprop = _instrument("rmsprop", lambda a, k, r: a[3] * 4 * 5)(rmsprop)
+adam = _instrument("adam", lambda a, k, r: a[4] * 4 * 7)(adam)
