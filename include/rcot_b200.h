@@ -85,6 +85,8 @@ typedef struct {
   int64_t mask_bs;
   const float* residual; /* same indexing as out (without coff): result += residual */
   int64_t res_bs;
+  int32_t debug;        /* bring-up only: 1 skip gather loads, 2 skip epilogue stores, 4 skip MMA issue */
+  int32_t reserved;
 } rcot_pm_params;
 
 int rcot_pm_gemm(const rcot_pm_params* p, rcot_stream_t stream);

@@ -84,13 +84,18 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p)
   }
 }
 
+constexpr int AB_CH = 16;  // rows of W_out / P staged per step in attn_bwd
+
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p) {
   extern __shared__ float sm[];
   const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
-  float* sA = sm;             // [c*c] softmax probabilities
-  float* sG = sA + c * c;     // [c*c] normalised Gram
-  float* sD = sG + c * c;     // [c*c] dA -> dGt
-  float* snq = sD + c * c;    // [c]
+  const int ca = c + 1;         // padded row stride of sA: conflict-free when threads differ in the row
+  float* sA = sm;               // [c*ca] softmax probabilities
+  float* sG = sA + c * ca;      // [c*c] normalised Gram
+  float* sD = sG + c * c;       // [c*c] dA -> dGt
+  float* sW = sD + c * c;       // [AB_CH*c] rows of W_out[:, head block]
+  float* sP = sW + AB_CH * c;   // [AB_CH*c] rows of P[:, head block]
+  float* snq = sP + AB_CH * c;  // [c]
   float* snk = snq + c;
   float* srq = snk + c;
   float* srk = srq + c;
@@ -99,9 +104,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
   const size_t hb = ((size_t)b * p.heads + h) * c * c;
   const float* ss = p.sumsq + (size_t)b * 2 * C;
   const float* Pm = p.P + (size_t)b * C * C;  // [co, ci]
-  for (int i = tid; i < c * c; i += blockDim.x) {
-    sA[i] = p.A[hb + i];
-    sG[i] = p.Gt[hb + i];
+  for (int e = tid; e < c * c; e += blockDim.x) {
+    const int i = e / c, j = e - i * c;
+    sA[i * ca + j] = p.A[hb + e];
+    sG[e] = p.Gt[hb + e];
   }
   for (int i = tid; i < c; i += blockDim.x) {
     snq[i] = sqrtf(ss[h * c + i]);
@@ -109,25 +115,58 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
     srk[i] = 0.f;
   }
   if (tid == 0) s_dtau = 0.f;
-  __syncthreads();
-  // dA[i,j] = sum_co W_out[co,(h,i)] * P[co,(h,j)]
-  for (int e = tid; e < c * c; e += blockDim.x) {
-    const int i = e / c, j = e - i * c;
-    float acc = 0.f;
-    for (int co = 0; co < C; ++co)
-      acc = fmaf(__ldg(p.w_out + (size_t)co * C + h * c + i), __ldg(Pm + (size_t)co * C + h * c + j), acc);
-    sD[e] = acc;
+  // dA[i,j] = sum_co W_out[co,(h,i)] * P[co,(h,j)]   and   dW_out[co,(h,i)] += sum_j P[co,(h,j)] * A[i,j],
+  // streaming W_out / P through shared memory AB_CH rows at a time (coalesced along the head block).
+  constexpr int MAXO = 36;  // ceil(96*96/256)
+  float acc[MAXO];
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) acc[o] = 0.f;
+  const int nout = (c * c + 255) / 256;
+  for (int co0 = 0; co0 < C; co0 += AB_CH) {
+    __syncthreads();
+    for (int e = tid; e < AB_CH * c; e += blockDim.x) {
+      const int r = e / c, i = e - r * c;
+      sW[e] = __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i);
+      sP[e] = __ldg(Pm + (size_t)(co0 + r) * C + h * c + i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < nout) {
+        const int e = tid + o * 256;
+        if (e < c * c) {
+          const int i = e / c, j = e - i * c;
+          float a = acc[o];
+#pragma unroll 8
+          for (int r = 0; r < AB_CH; ++r) a = fmaf(sW[r * c + i], sP[r * c + j], a);
+          acc[o] = a;
+        }
+      }
+    }
+    for (int e = tid; e < AB_CH * c; e += blockDim.x) {
+      const int r = e / c, i = e - r * c;
+      const float* prow = sP + r * c;
+      const float* arow = sA + i * ca;
+      float a = 0.f;
+      for (int j = 0; j < c; ++j) a = fmaf(prow[j], arow[j], a);
+      atomicAdd(p.dw_out + (size_t)(co0 + r) * C + h * c + i, a);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) {
+    const int e = tid + o * 256;
+    if (o < nout && e < c * c) sD[e] = acc[o];
   }
   __syncthreads();
   const float tau = __ldg(p.temperature + h);
   float dtau = 0.f;
   for (int i = warp; i < c; i += nwarp) {
     float rd = 0.f;
-    for (int j = lane; j < c; j += 32) rd = fmaf(sD[i * c + j], sA[i * c + j], rd);
+    for (int j = lane; j < c; j += 32) rd = fmaf(sD[i * c + j], sA[i * ca + j], rd);
     rd = warp_sum_a(rd);
     float rq = 0.f;
     for (int j = lane; j < c; j += 32) {
-      const float dS = sA[i * c + j] * (sD[i * c + j] - rd);
+      const float dS = sA[i * ca + j] * (sD[i * c + j] - rd);
       dtau = fmaf(dS, sG[i * c + j], dtau);
       const float dG = dS * tau;
       sD[i * c + j] = dG;
@@ -160,14 +199,6 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
     const float ck = snk[i] >= 1e-12f ? -srk[i] / (snk[i] * snk[i]) : 0.f;
     store_split(Wp, N2, N2, h * c + i, h * c + i, cq);
     store_split(Wp, N2, N2, C + h * c + i, C + h * c + i, ck);
-  }
-  // dW_out[co,(h,i)] += sum_j P[co,(h,j)] * A[i,j]
-  for (int e = tid; e < C * c; e += blockDim.x) {
-    const int co = e / c, i = e - co * c;
-    const float* prow = Pm + (size_t)co * C + h * c;
-    float acc = 0.f;
-    for (int j = 0; j < c; ++j) acc = fmaf(__ldg(prow + j), sA[i * c + j], acc);
-    atomicAdd(p.dw_out + (size_t)co * C + h * c + i, acc);
   }
 }
 
@@ -202,10 +233,11 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
   if (rc) return rc;
   RCOT_REQUIRE(p.P && p.dw_out && p.dtemperature && p.W12pack, "attn_bwd: null pointer");
   const int c = p.C / p.heads;
-  const size_t smem = ((size_t)3 * c * c + 4 * c) * sizeof(float);
+  RCOT_REQUIRE(p.C % AB_CH == 0, "attn_bwd: C must be a multiple of %d", AB_CH);
+  const size_t smem = ((size_t)c * (c + 1) + 2 * c * c + 2 * AB_CH * c + 4 * c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) {
       set_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return RCOT_ERR_CUDA;

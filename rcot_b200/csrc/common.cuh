@@ -26,26 +26,19 @@ int check_launch(const char* what);    // api.cu: cudaPeekAtLastError -> error c
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 static inline int round_up(int a, int b) { return ((a + b - 1) / b) * b; }
 
-// Tiling of the N (output-channel) dimension of a pixel-as-M GEMM.
-// One CTA owns up to NSUB accumulators of BN columns each (NSUB*BN <= 512 TMEM columns);
-// `passes` CTAs along grid.y cover all of N.
+// Tiling of the N (output-channel) dimension of a pixel-as-M GEMM: `passes` tiles of BN <= 256
+// columns each (two TMEM accumulator buffers of BN columns per CTA); tiles along N are separate
+// work items of the persistent kernel. NSUB is kept (= 1) so the packed layout formula stays generic.
 struct NPlan {
   int N, BN, nsub_total, NSUB, passes;
 };
 static inline NPlan make_nplan(int N) {
   NPlan p;
   p.N = N;
-  if (N <= 256) {
-    p.nsub_total = 1;
-    p.BN = round_up(N, 16);
-    p.NSUB = 1;
-    p.passes = 1;
-  } else {
-    p.nsub_total = cdiv(N, 256);
-    p.BN = round_up(cdiv(N, p.nsub_total), 16);
-    p.NSUB = 2;
-    p.passes = cdiv(p.nsub_total, 2);
-  }
+  p.nsub_total = cdiv(N, 256);
+  p.BN = round_up(cdiv(N, p.nsub_total), 16);
+  p.NSUB = 1;
+  p.passes = p.nsub_total;
   return p;
 }
 

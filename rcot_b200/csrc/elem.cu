@@ -40,58 +40,74 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------ LayerNorm backward
 // g = dz*gamma ; dx = [dy +] rstd*(g - mean_c(g) - xhat*mean_c(g*xhat)) ; dgamma += sum dz*xhat ;
-// dbeta += sum dz.  One thread per pixel, two sweeps over the channels (the second one hits L1/L2).
-// Channel sums: warp shuffle over 32 pixels -> shared accumulators -> one atomicAdd per channel per CTA.
+// dbeta += sum dz.  CTA = 32 pixels (lanes) x 8 channel groups (warps); warp w owns channels w, w+8, ...
+// so the per-channel sums over pixels are warp shuffles into shared slots no other warp touches; the
+// per-pixel sums over channels are combined across the 8 warps through shared memory.  A CTA walks
+// `groups` consecutive 32-pixel groups before it flushes its channel sums with one atomicAdd each.
 __global__ void __launch_bounds__(256)
     ln_bwd_kernel(const float* __restrict__ dz, int64_t dz_bs, const float* __restrict__ x, int64_t x_bs,
                   const float2* __restrict__ stats, const float* __restrict__ gamma, const float* dy, int64_t dy_bs,
-                  float* dx, int64_t dx_bs, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int HW) {
-  extern __shared__ float sacc[];  // [2*C]
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+                  float* dx, int64_t dx_bs, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int HW,
+                  int groups) {
+  extern __shared__ float sacc[];  // [2*C] channel sums, then [2][8][32] pixel partials
+  float* spix = sacc + 2 * C;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const bool valid = p < HW;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  const float* xp = x + (size_t)b * x_bs + p;
-  const float* dzp = dz + (size_t)b * dz_bs + p;
-  float mu = 0.f, rstd = 0.f;
-  if (valid) {
-    const float2 st = stats[(size_t)b * HW + p];
-    mu = st.x;
-    rstd = st.y;
-  }
-  float sg = 0.f, sgx = 0.f;
-  const int lane = threadIdx.x & 31;
-  for (int c = 0; c < C; ++c) {
-    float d = 0.f, xh = 0.f;
+  for (int gi = 0; gi < groups; ++gi) {
+    const int p = (blockIdx.x * groups + gi) * 32 + lane;
+    const bool valid = p < HW;
+    const float* xp = x + (size_t)b * x_bs + p;
+    const float* dzp = dz + (size_t)b * dz_bs + p;
+    float mu = 0.f, rstd = 0.f;
     if (valid) {
-      d = __ldg(dzp + (size_t)c * HW);
-      xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+      const float2 st = stats[(size_t)b * HW + p];
+      mu = st.x;
+      rstd = st.y;
     }
-    const float g = d * __ldg(gamma + c);
-    sg += g;
-    sgx = fmaf(g, xh, sgx);
-    const float wg = warp_sum(d * xh);
-    const float wb = warp_sum(d);
-    if (lane == 0) {
-      atomicAdd(&sacc[c], wg);
-      atomicAdd(&sacc[C + c], wb);
+    float sg = 0.f, sgx = 0.f;
+    for (int c = wy; c < C; c += 8) {
+      float d = 0.f, xh = 0.f;
+      if (valid) {
+        d = __ldg(dzp + (size_t)c * HW);
+        xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+      }
+      const float g = d * __ldg(gamma + c);
+      sg += g;
+      sgx = fmaf(g, xh, sgx);
+      const float wg = warp_sum(d * xh);
+      const float wb = warp_sum(d);
+      if (lane == 0) {
+        sacc[c] += wg;
+        sacc[C + c] += wb;
+      }
     }
-  }
-  if (valid) {
+    spix[wy * 32 + lane] = sg;
+    spix[256 + wy * 32 + lane] = sgx;
+    __syncthreads();
+    float mg = 0.f, mgx = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      mg += spix[w * 32 + lane];
+      mgx += spix[256 + w * 32 + lane];
+    }
     const float inv = 1.f / (float)C;
-    const float mg = sg * inv, mgx = sgx * inv;
-    const float* dyp = dy ? dy + (size_t)b * dy_bs + p : nullptr;
-    float* dxp = dx + (size_t)b * dx_bs + p;
-    for (int c = 0; c < C; ++c) {
-      const float d = __ldg(dzp + (size_t)c * HW);
-      const float xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
-      float r = rstd * (d * __ldg(gamma + c) - mg - xh * mgx);
-      if (dyp) r += dyp[(size_t)c * HW];
-      dxp[(size_t)c * HW] = r;
+    mg *= inv;
+    mgx *= inv;
+    if (valid) {
+      const float* dyp = dy ? dy + (size_t)b * dy_bs + p : nullptr;
+      float* dxp = dx + (size_t)b * dx_bs + p;
+      for (int c = wy; c < C; c += 8) {
+        const float d = __ldg(dzp + (size_t)c * HW);
+        const float xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+        float r = rstd * (d * __ldg(gamma + c) - mg - xh * mgx);
+        if (dyp) r += dyp[(size_t)c * HW];
+        dxp[(size_t)c * HW] = r;
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     atomicAdd(dgamma + i, sacc[i]);
     atomicAdd(dbeta + i, sacc[C + i]);
@@ -105,21 +121,42 @@ __device__ __forceinline__ float gelu_erf_grad(float a) {
   return 0.5f * (1.f + erff(a * 0.70710678118654752f)) + a * 0.39894228040143268f * __expf(-0.5f * a * a);
 }
 
-// 3x3 stencil at (y,x) of one plane with zero padding; w[9] already flipped by the caller if needed.
-__device__ __forceinline__ float stencil9(const float* __restrict__ plane, const float* w, int y, int x, int H, int W) {
-  float acc = 0.f;
+// Each thread produces 4 horizontally adjacent outputs of one (image, channel) plane: three rows of
+// 4+2 inputs are fetched once (one aligned float4 + two edge scalars per row) and reused by the 9 taps.
+// W % 4 == 0 is required by the launcher (all feature maps here have W in {4,8,...,256}).
+struct Row6 {
+  float v[6];  // x0-1 .. x0+4
+};
+__device__ __forceinline__ Row6 load_row6(const float* __restrict__ plane, int y, int x0, int H, int W) {
+  Row6 r;
+  if ((unsigned)y >= (unsigned)H) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = 0.f;
+    return r;
+  }
+  const float* p = plane + (size_t)y * W + x0;
+  const float4 m = __ldg(reinterpret_cast<const float4*>(p));
+  r.v[0] = x0 > 0 ? __ldg(p - 1) : 0.f;
+  r.v[1] = m.x;
+  r.v[2] = m.y;
+  r.v[3] = m.z;
+  r.v[4] = m.w;
+  r.v[5] = x0 + 4 < W ? __ldg(p + 4) : 0.f;
+  return r;
+}
+// out[j] = sum_{ky,kx} w[ky*3+kx] * in(y+ky-1, x0+j+kx-1), j = 0..3
+__device__ __forceinline__ void stencil4(const float* __restrict__ plane, const float* w, int y, int x0, int H, int W,
+                                         float* out) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = 0.f;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
-    const int yy = y + ky - 1;
-    if ((unsigned)yy >= (unsigned)H) continue;
+    const Row6 r = load_row6(plane, y + ky - 1, x0, H, W);
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xx = x + kx - 1;
-      if ((unsigned)xx >= (unsigned)W) continue;
-      acc = fmaf(__ldg(plane + yy * W + xx), w[ky * 3 + kx], acc);
-    }
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[j] = fmaf(r.v[j + kx], w[ky * 3 + kx], out[j]);
   }
-  return acc;
 }
 
 // mode 0: out[ch] = dw(in[ch])                (flip=1: transposed = data gradient)
@@ -127,78 +164,93 @@ __device__ __forceinline__ float stencil9(const float* __restrict__ plane, const
 // mode 1: out[j] = gelu(dw(in[j])) * dw(in[j+hid]),  j < hid            (GDFN gate)
 // mode 2: a = dw(in[j]), b = dw(in[j+hid]); out[j] = dg*b*gelu'(a); out[j+hid] = dg*gelu(a);
 //         optional g_out[j] = gelu(a)*b                                 (GDFN gate backward)
-__global__ void __launch_bounds__(256) dwconv_kernel(const rcot_dw_params p) {
+// Work is flattened over (image, plane, quad) so small feature maps still fill the machine.
+__global__ void __launch_bounds__(256) dwconv_kernel(const rcot_dw_params p, const int planes, const int qpp,
+                                                     const long total) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < total;
+  const long pl = active ? idx / qpp : 0;
+  const int quad = active ? (int)(idx - pl * qpp) : 0;
+  const int b = (int)(pl / planes), ch = (int)(pl - (long)b * planes);
   const int HW = p.H * p.W;
-  const int ch = blockIdx.y, b = blockIdx.z;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = pix < HW;
-  const int y = valid ? pix / p.W : 0, x = valid ? pix - (pix / p.W) * p.W : 0;
+  const int pix = quad * 4;
+  const int y = pix / p.W, x0 = pix - y * p.W;
   const float* inb = p.in + (size_t)b * p.in_bs;
   float w0[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) w0[i] = __ldg(p.w + ch * 9 + (p.flip ? 8 - i : i));
   if (p.mode == 0) {
-    float o = 0.f;
-    if (valid) {
-      o = stencil9(inb + (size_t)ch * HW, w0, y, x, p.H, p.W);
-      p.out[(size_t)b * p.out_bs + (size_t)ch * HW + pix] = o;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      stencil4(inb + (size_t)ch * HW, w0, y, x0, p.H, p.W, o);
+      *reinterpret_cast<float4*>(p.out + (size_t)b * p.out_bs + (size_t)ch * HW + pix) =
+          make_float4(o[0], o[1], o[2], o[3]);
     }
-    if (p.sumsq && ch < p.nsq) {
-      __shared__ float red[8];
-      float s = warp_sum(o * o);
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        s = warp_sum(s);
-        if (threadIdx.x == 0) atomicAdd(p.sumsq + (size_t)b * p.nsq + ch, s);
+    if (p.sumsq) {  // uniform branch
+      float sq = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3];
+      const bool mine = active && ch < p.nsq;
+      if (qpp % 32 == 0) {  // a warp never straddles two planes
+        sq = warp_sum(mine ? sq : 0.f);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(p.sumsq + (size_t)b * p.nsq + ch, sq);
+      } else if (mine) {
+        atomicAdd(p.sumsq + (size_t)b * p.nsq + ch, sq);
       }
     }
     return;
   }
-  if (!valid) return;
+  if (!active) return;
   float w1[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) w1[i] = __ldg(p.w + (ch + p.hid) * 9 + i);
-  const float a = stencil9(inb + (size_t)ch * HW, w0, y, x, p.H, p.W);
-  const float g = stencil9(inb + (size_t)(ch + p.hid) * HW, w1, y, x, p.H, p.W);
+  float a[4], g[4];
+  stencil4(inb + (size_t)ch * HW, w0, y, x0, p.H, p.W, a);
+  stencil4(inb + (size_t)(ch + p.hid) * HW, w1, y, x0, p.H, p.W, g);
   if (p.mode == 1) {
-    p.out[(size_t)b * p.out_bs + (size_t)ch * HW + pix] = gelu_erf(a) * g;
+    *reinterpret_cast<float4*>(p.out + (size_t)b * p.out_bs + (size_t)ch * HW + pix) =
+        make_float4(gelu_erf(a[0]) * g[0], gelu_erf(a[1]) * g[1], gelu_erf(a[2]) * g[2], gelu_erf(a[3]) * g[3]);
   } else {
-    const float d = __ldg(p.dg + (size_t)b * p.dg_bs + (size_t)ch * HW + pix);
-    const float ga = gelu_erf(a);
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.dg + (size_t)b * p.dg_bs + (size_t)ch * HW + pix));
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    float da[4], db[4], gg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float ga = gelu_erf(a[j]);
+      da[j] = d[j] * g[j] * gelu_erf_grad(a[j]);
+      db[j] = d[j] * ga;
+      gg[j] = ga * g[j];
+    }
     float* ob = p.out + (size_t)b * p.out_bs;
-    ob[(size_t)ch * HW + pix] = d * g * gelu_erf_grad(a);
-    ob[(size_t)(ch + p.hid) * HW + pix] = d * ga;
-    if (p.g_out) p.g_out[(size_t)b * p.g_bs + (size_t)ch * HW + pix] = ga * g;
+    *reinterpret_cast<float4*>(ob + (size_t)ch * HW + pix) = make_float4(da[0], da[1], da[2], da[3]);
+    *reinterpret_cast<float4*>(ob + (size_t)(ch + p.hid) * HW + pix) = make_float4(db[0], db[1], db[2], db[3]);
+    if (p.g_out)
+      *reinterpret_cast<float4*>(p.g_out + (size_t)b * p.g_bs + (size_t)ch * HW + pix) =
+          make_float4(gg[0], gg[1], gg[2], gg[3]);
   }
 }
 
 // dW[ch, k] += sum_{b,p} dout[b,ch,p] * in[b,ch,p+off_k].  grid = (chunks, Cn); each CTA strides over
-// (image, pixel) pairs, keeps 9 partial sums per thread, reduces and issues 9 atomics.
+// (image, quad) pairs of its channel, keeps 9 partial sums per thread, reduces and issues 9 atomics.
 __global__ void __launch_bounds__(256)
     dw_wgrad_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
                     float* __restrict__ dw, int B, int H, int W) {
-  const int HW = H * W, ch = blockIdx.y;
-  const long total = (long)B * HW;
+  const int HW = H * W, ch = blockIdx.y, qpp = HW / 4;
+  const long total = (long)B * qpp;
   float acc[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) acc[i] = 0.f;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int b = (int)(e / HW), pix = (int)(e - (long)b * HW);
-    const int y = pix / W, x = pix - y * W;
-    const float d = __ldg(dout + (size_t)b * dout_bs + (size_t)ch * HW + pix);
+    const int b = (int)(e / qpp), pix = (int)(e - (long)b * qpp) * 4;
+    const int y = pix / W, x0 = pix - y * W;
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(dout + (size_t)b * dout_bs + (size_t)ch * HW + pix));
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
     const float* plane = in + (size_t)b * in_bs + (size_t)ch * HW;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if ((unsigned)yy >= (unsigned)H) continue;
+      const Row6 r = load_row6(plane, y + ky - 1, x0, H, W);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if ((unsigned)xx >= (unsigned)W) continue;
-        acc[ky * 3 + kx] = fmaf(d, __ldg(plane + yy * W + xx), acc[ky * 3 + kx]);
-      }
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[ky * 3 + kx] = fmaf(d[j], r.v[j + kx], acc[ky * 3 + kx]);
     }
   }
   __shared__ float red[9][8];
@@ -291,9 +343,15 @@ extern "C" int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64
                            float* dgamma, float* dbeta, int B, int C, int HW, rcot_stream_t st) {
   RCOT_REQUIRE(dz && x && stats && gamma && dx && dgamma && dbeta, "ln_bwd: null pointer");
   RCOT_REQUIRE(B > 0 && B <= 65535 && C > 0 && HW > 0, "ln_bwd: bad sizes");
-  dim3 grid(cdiv(HW, 256), B);
-  ln_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)st>>>(
-      dz, dz_bs, x, x_bs, reinterpret_cast<const float2*>(stats), gamma, dy, dy_bs, dx, dx_bs, dgamma, dbeta, C, HW);
+  // enough CTAs for ~8 per SM, at most 8 pixel groups (256 pixels) per CTA
+  long pg = cdiv(HW, 32);
+  int groups = (int)((pg * B) / (148 * 8));
+  if (groups < 1) groups = 1;
+  if (groups > 8) groups = 8;
+  dim3 grid(cdiv(pg, groups), B);
+  ln_bwd_kernel<<<grid, 256, (2 * C + 512) * sizeof(float), (cudaStream_t)st>>>(
+      dz, dz_bs, x, x_bs, reinterpret_cast<const float2*>(stats), gamma, dy, dy_bs, dx, dx_bs, dgamma, dbeta, C, HW,
+      groups);
   return check_launch("ln_bwd");
 }
 
@@ -310,17 +368,21 @@ extern "C" int rcot_dwconv3x3(const rcot_dw_params* pp, rcot_stream_t st) {
     if (p.mode == 2) RCOT_REQUIRE(p.dg != nullptr, "dwconv3x3: gate backward needs dg");
     planes = p.hid;
   }
-  RCOT_REQUIRE(planes <= 65535, "dwconv3x3: too many channels");
-  dim3 grid(cdiv((long)p.H * p.W, 256), planes, p.B);
-  dwconv_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(p);
+  RCOT_REQUIRE(p.W % 4 == 0, "dwconv3x3: width must be a multiple of 4, got %d", p.W);
+  RCOT_REQUIRE(p.in_bs % 4 == 0 && p.out_bs % 4 == 0 && ((uintptr_t)p.in % 16 == 0) && ((uintptr_t)p.out % 16 == 0),
+               "dwconv3x3: tensors must be 16-byte aligned");
+  const int qpp = p.H * p.W / 4;
+  const long total = (long)p.B * planes * qpp;
+  dwconv_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)st>>>(p, planes, qpp, total);
   return check_launch("dwconv3x3");
 }
 
 extern "C" int rcot_dwconv3x3_wgrad(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, float* dw,
                                     int B, int Cn, int H, int W, rcot_stream_t st) {
   RCOT_REQUIRE(in && dout && dw && B > 0 && Cn > 0 && Cn <= 65535 && H > 0 && W > 0, "dwconv3x3_wgrad: bad arguments");
-  long total = (long)B * H * W;
-  int chunks = (int)((total + 256 * 16 - 1) / (256 * 16));
+  RCOT_REQUIRE(W % 4 == 0 && in_bs % 4 == 0 && dout_bs % 4 == 0, "dwconv3x3_wgrad: width/strides must be multiples of 4");
+  long total = (long)B * H * W / 4;
+  int chunks = (int)((total + 256 * 8 - 1) / (256 * 8));
   if (chunks < 1) chunks = 1;
   if (chunks > 64) chunks = 64;
   dim3 grid(chunks, Cn);

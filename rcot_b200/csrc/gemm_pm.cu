@@ -1,14 +1,17 @@
 // gemm_pm.cu -- "pixel-as-M" implicit GEMM on tcgen05:
 //     out[b, n, p] = epilogue( sum_k A(b, p, k) * W[n, k] )
-// M = 128 pixels of one image per CTA, N = output channels (up to 2 x 256 TMEM accumulators per
-// CTA), K = Cin*ks*ks streamed through a shared-memory ring in chunks of 32.
-//   * A operand: gathered by the CTA's threads (one thread = one pixel row) straight from the
-//     NCHW fp32 activations -- optional concat of two tensors, optional LayerNorm prologue,
-//     forward or transposed (data-gradient) conv geometry -- split to bf16 hi/lo and stored in the
-//     no-swizzle K-major core-matrix layout.
-//   * B operand: weights pre-packed in that layout (pack.cu), one cp.async.bulk per stage.
-//   * D: fp32 in TMEM, read back with tcgen05.ld (thread = pixel, registers = channels) so the
-//     epilogue (bias, LeakyReLU, sign mask, residual, accumulate) writes coalesced NCHW rows.
+// Persistent, warp-specialised CTAs (one per SM), 128 pixels x BN<=256 output channels per tile:
+//   * 8 producer warps gather the A operand straight from the NCHW fp32 activations (two threads per
+//     pixel row; optional concat of two tensors, LayerNorm prologue, forward or transposed conv
+//     geometry), split fp32 -> bf16 hi/lo and store it in the no-swizzle K-major core-matrix layout;
+//     producer thread 0 also brings the pre-packed weight stage in with one cp.async.bulk (TMA engine).
+//   * 1 MMA warp: a single thread issues tcgen05.mma (hi*hi + lo*hi + hi*lo for fp32-class accuracy)
+//     into one of TWO TMEM accumulator buffers, commits stages back to the producers.
+//   * 4 epilogue warps read the finished accumulator with tcgen05.ld (thread = pixel, registers =
+//     channels) and write coalesced NCHW rows with bias / LeakyReLU / sign-mask / residual /
+//     accumulate fused -- while the MMA warp already works on the next tile in the other buffer.
+// Rows are the pixels of the whole batch flattened (b, y, x) unless the weights are per image
+// (MDTA's folded matrices), so small images still fill 128-row tiles.
 // Replaces the ATen conv2d calls listed in include/rcot_b200.h (rcot_pm_params).
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
@@ -16,182 +19,352 @@
 
 namespace rcot {
 
-constexpr int PM_MAX_STAGES = 4;
+constexpr int PM_MAX_STAGES = 6;
+constexpr int PM_PROD_WARPS = 8;
+constexpr int PM_PROD_THREADS = PM_PROD_WARPS * 32;
+constexpr int PM_THREADS = (PM_PROD_WARPS + 1 + 4) * 32;  // producers, MMA warp, 4 epilogue warps
+
+struct PmGeom {
+  int Ktot, nk, BN, passes, stages, tiles_m, tiles_per_img, flat, c1_aligned;
+  long rows_total;
+  uint32_t tmem_cols;
+};
 
 template <int KS, int MODE, int TERMS, bool LN>
-__global__ void __launch_bounds__(128)
-    pm_gemm_kernel(const rcot_pm_params p, const int Ktot, const int nk, const int BN, const int NSUB,
-                   const int stages, const uint32_t tmem_cols) {
+__global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_params p, const PmGeom g) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full_bar[PM_MAX_STAGES], empty_bar[PM_MAX_STAGES], done_bar;
+  __shared__ uint64_t full_bar[PM_MAX_STAGES], empty_bar[PM_MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   constexpr int TA = (TERMS > 1) ? 2 : 1;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.z, pass = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HWr = p.Hr * p.Wr, HWs = p.Hs * p.Ws;
-  const int row_p = blockIdx.x * 128 + tid;
-  const bool valid = row_p < HWr;
-  const int ry = valid ? row_p / p.Wr : 0;
-  const int rx = valid ? row_p - ry * p.Wr : 0;
-
+  const int BN = g.BN, nk = g.nk, stages = g.stages;
   const uint32_t a_tile = 128 * KC * 2;
   const uint32_t b_tile = (uint32_t)BN * KC * 2;
-  const uint32_t b_term = (uint32_t)NSUB * b_tile;
-  const uint32_t stage_bytes = TA * a_tile + TA * b_term;
+  const uint32_t stage_bytes = TA * (a_tile + b_tile);
+  const int total_tiles = g.tiles_m * g.passes;
 
-  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  // LayerNorm affine parameters, interleaved (gamma, beta) and zero-padded to the chunk grid
+  float* ln_gb = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);
+  if (LN) {
+    for (int k = tid; k < nk * KC; k += PM_THREADS) {
+      ln_gb[2 * k] = k < g.Ktot ? __ldg(p.ln_gamma + k) : 0.f;
+      ln_gb[2 * k + 1] = k < g.Ktot ? __ldg(p.ln_beta + k) : 0.f;
+    }
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, g.tmem_cols);
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], PM_PROD_WARPS + 1);   // one arrival per producer warp + the TMA expect_tx
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&done_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);                  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = make_idesc_bf16(128, BN);
 
-  const float* src1 = p.in + (size_t)b * p.in_bs;
-  const float* src2 = p.in2 ? p.in2 + (size_t)b * p.in2_bs : nullptr;
-  float mu = 0.f, rstd = 0.f;
-  if (LN && valid) {
-    float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWs + row_p);
-    mu = st.x;
-    rstd = st.y;
-  }
-  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)b * p.wpack_bs +
-                        (size_t)pass * nk * (2 * b_term);
-
-  for (int c = 0; c < nk; ++c) {
-    const int s = c % stages, use = c / stages;
-    if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-    uint8_t* st = smem + (size_t)s * stage_bytes;
-    uint8_t* a_hi = st;
-    uint8_t* a_lo = st + a_tile;
-    uint8_t* b_st = st + TA * a_tile;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&full_bar[s], TA * b_term);
-      bulk_g2s(b_st, wsrc + (size_t)c * (2 * b_term), TA * b_term, &full_bar[s]);
-    }
+  if (warp < PM_PROD_WARPS) {
+    // =========================================================== producers
+    // Work items are (tile, K-chunk) pairs; the 16 loads of item j+1 are issued before item j is
+    // converted, so global-load latency overlaps the conversion and the barrier waits.
+    const int row = tid & 127, khalf = tid >> 7;  // this thread fills k8 groups {2*khalf, 2*khalf+1}
+    struct TileCtx {
+      const float *b1, *b2;   // image base pointers (+ pixel offset for the 1x1 fast path)
+      const uint8_t* wsrc;
+      float mu, rstd;
+      int ry, rx;
+      bool valid;
+    };
+    auto setup = [&](int t) {
+      TileCtx x;
+      const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
+      int b, pix;
+      if (g.flat) {
+        const long r = (long)mt * 128 + row;
+        x.valid = r < g.rows_total;
+        b = x.valid ? (int)(r / HWr) : 0;
+        pix = x.valid ? (int)(r - (long)b * HWr) : 0;
+      } else {
+        b = mt / g.tiles_per_img;
+        pix = (mt - b * g.tiles_per_img) * 128 + row;
+        x.valid = pix < HWr;
+        if (!x.valid) pix = 0;
+      }
+      x.ry = pix / p.Wr;
+      x.rx = pix - x.ry * p.Wr;
+      const int poff = (KS == 1) ? pix : 0;
+      x.b1 = p.in + (size_t)b * p.in_bs + poff;
+      x.b2 = p.in2 ? p.in2 + (size_t)b * p.in2_bs + poff : nullptr;
+      x.mu = 0.f;
+      x.rstd = 0.f;
+      if (LN && x.valid) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWs + pix);
+        x.mu = st.x;
+        x.rstd = st.y;
+      }
+      x.wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
+               (size_t)pass * nk * (2 * b_tile);
+      return x;
+    };
+    auto load16 = [&](float* v, const TileCtx& x, int c) {
 #pragma unroll
-    for (int k8 = 0; k8 < KC / 8; ++k8) {
-      float v[8];
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k0 = c * KC + (khalf * 2 + kk) * 8;
+        if (KS == 1 && g.c1_aligned) {
+          // 8 consecutive channels of one source tensor, same pixel: pointer + i*HW
+          const float* sp = (k0 < p.C1) ? x.b1 + (size_t)k0 * HWs : x.b2 + (size_t)(k0 - p.C1) * HWs;
+          const bool full = x.valid && (k0 + 8 <= g.Ktot) && !(p.debug & 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = c * KC + k8 * 8 + i;
-        float x = 0.f;
-        if (valid && k < Ktot) {
-          int ch, sy, sx;
-          bool ok = true;
-          if (KS == 1) {
-            ch = k;
-            sy = ry;
-            sx = rx;
-          } else {
-            ch = k / (KS * KS);
-            const int r = k - ch * (KS * KS);
-            const int ky = r / KS, kx = r - ky * KS;
-            if (MODE == 0) {
-              sy = ry * p.stride + ky - p.pad;
-              sx = rx * p.stride + kx - p.pad;
-            } else {
-              const int ty = ry + p.pad - ky, tx = rx + p.pad - kx;
-              sy = ty / p.stride;
-              sx = tx / p.stride;
-              ok = (ty >= 0) && (tx >= 0) && (sy * p.stride == ty) && (sx * p.stride == tx);
+          for (int i = 0; i < 8; ++i) {
+            float val = 0.f;
+            if (full || (x.valid && k0 + i < g.Ktot && !(p.debug & 1))) val = __ldg(sp + (size_t)i * HWs);
+            v[kk * 8 + i] = val;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            float val = 0.f;
+            if (x.valid && k < g.Ktot) {
+              int ch, sy, sx;
+              bool ok = true;
+              if (KS == 1) {
+                ch = k;
+                sy = 0;
+                sx = 0;   // pixel offset already folded into b1/b2
+              } else {
+                ch = k / (KS * KS);
+                const int r = k - ch * (KS * KS);
+                const int ky = r / KS, kx = r - ky * KS;
+                if (MODE == 0) {
+                  sy = x.ry * p.stride + ky - p.pad;
+                  sx = x.rx * p.stride + kx - p.pad;
+                } else {
+                  const int ty = x.ry + p.pad - ky, tx = x.rx + p.pad - kx;
+                  sy = ty / p.stride;
+                  sx = tx / p.stride;
+                  ok = (ty >= 0) && (tx >= 0) && (sy * p.stride == ty) && (sx * p.stride == tx);
+                }
+                ok = ok && ((unsigned)sy < (unsigned)p.Hs) && ((unsigned)sx < (unsigned)p.Ws);
+              }
+              if (ok && !(p.debug & 1)) {
+                const float* sp = (ch < p.C1) ? (x.b1 + (size_t)ch * HWs) : (x.b2 + (size_t)(ch - p.C1) * HWs);
+                val = __ldg(sp + sy * p.Ws + sx);
+              }
             }
-            ok = ok && ((unsigned)sy < (unsigned)p.Hs) && ((unsigned)sx < (unsigned)p.Ws);
-          }
-          if (ok) {
-            const float* sp = (ch < p.C1) ? (src1 + (size_t)ch * HWs) : (src2 + (size_t)(ch - p.C1) * HWs);
-            x = __ldg(sp + sy * p.Ws + sx);
-            if (LN) x = (x - mu) * rstd * __ldg(p.ln_gamma + ch) + __ldg(p.ln_beta + ch);
+            v[kk * 8 + i] = val;
           }
         }
-        v[i] = x;
       }
-      op_store8<TERMS>(a_hi, a_lo, tid, k8, v);
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&full_bar[s], use & 1);
-      tc_fence_after();
-      for (int sub = 0; sub < NSUB; ++sub) {
-        issue_stage<TERMS>(tmem + sub * BN, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_st) + sub * b_tile,
-                           smem_u32(b_st) + b_term + sub * b_tile, idesc, c == 0);
-      }
-      tc_commit(&empty_bar[s]);
-    }
-  }
-  if (tid == 0) tc_commit(&done_bar);
-  mbar_wait(&done_bar, 0);
-  tc_fence_after();
-
-  // ---- epilogue: thread = pixel row, registers = 16 output channels at a time
-  const uint32_t lane_base = tmem_lane_base(tmem);
-  float* outb = p.out + (size_t)b * p.out_bs + (size_t)p.out_coff * HWr;
-  const float* maskb = p.mask_y ? p.mask_y + (size_t)b * p.mask_bs : nullptr;
-  const float* resb = p.residual ? p.residual + (size_t)b * p.res_bs : nullptr;
-  for (int sub = 0; sub < NSUB; ++sub) {
-    const int nbase = (pass * NSUB + sub) * BN;
-    if (nbase >= p.N) break;
-    for (int n0 = 0; n0 < BN; n0 += 16) {
-      if (nbase + n0 >= p.N) break;
+    };
+    uint32_t it = 0;
+    int t = blockIdx.x, c = 0;
+    TileCtx nctx = setup(t < total_tiles ? t : 0);
+    float nxt[16];
+    if (t < total_tiles) load16(nxt, nctx, 0);
+    while (t < total_tiles) {
       float v[16];
-      tmem_ld16(lane_base + sub * BN + n0, v);
-      if (valid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = nbase + n0 + i;
-          if (n < p.N) {
-            float y = v[i];
-            if (p.bias) y += __ldg(p.bias + n);
-            if (p.act) y = y > 0.f ? y : y * p.slope;
-            const size_t idx = (size_t)n * HWr + row_p;
-            if (maskb) y *= (__ldg(maskb + idx) > 0.f) ? 1.f : p.slope;
-            if (resb) y += __ldg(resb + idx);
-            if (p.accumulate) y += outb[idx];
-            outb[idx] = y;
+      for (int i = 0; i < 16; ++i) v[i] = nxt[i];
+      const TileCtx cur = nctx;
+      const int cc = c;
+      if (++c == nk) {
+        c = 0;
+        t += gridDim.x;
+        if (t < total_tiles) nctx = setup(t);
+      }
+      if (t < total_tiles) load16(nxt, nctx, c);
+      // ---- convert + store item (cur, cc)
+      const int s = it % stages;
+      const uint32_t ph = (it / stages) & 1;
+      ++it;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      if (tid == 0) {
+        if (p.debug & 8) {
+          mbar_arrive(&full_bar[s]);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
+          bulk_g2s(st + TA * a_tile, cur.wsrc + (size_t)cc * (2 * b_tile), TA * b_tile, &full_bar[s]);
+        }
+      }
+      if (LN) {
+        const float* gb = ln_gb + (cc * KC + khalf * 16) * 2;   // interleaved (gamma, beta), zero beyond Ktot
+        if (cur.valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 w2 = *reinterpret_cast<const float2*>(gb + 2 * i);
+            v[i] = (v[i] - cur.mu) * cur.rstd * w2.x + w2.y;
           }
         }
       }
+      if (!(p.debug & 32)) {
+        op_store8<TERMS>(st, st + a_tile, row, khalf * 2, v);
+        op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, v + 8);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+  } else if (warp == PM_PROD_WARPS) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&acc_empty[buf], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + buf * BN;
+        for (int c = 0; c < nk; ++c, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+          if (!(p.debug & 4))
+            issue_stage<TERMS>(d, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, c == 0);
+          if (p.debug & 64) mbar_arrive(&empty_bar[s]); else tc_commit(&empty_bar[s]);
+        }
+        if (p.debug & 64) mbar_arrive(&acc_full[buf]); else tc_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // =========================================================== epilogue (warp % 4 = TMEM lane quarter)
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const bool epi_other = p.bias || p.act || p.mask_y || p.accumulate;
+    const bool epi_plain = !epi_other && !p.residual, epi_res = !epi_other && p.residual;
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
+      const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
+      int b, pix;
+      bool valid;
+      if (g.flat) {
+        const long r = (long)mt * 128 + row;
+        valid = r < g.rows_total;
+        b = valid ? (int)(r / HWr) : 0;
+        pix = valid ? (int)(r - (long)b * HWr) : 0;
+      } else {
+        b = mt / g.tiles_per_img;
+        pix = (mt - b * g.tiles_per_img) * 128 + row;
+        valid = pix < HWr;
+      }
+      const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      const int nbase = pass * BN;
+      float* o = p.out + (size_t)b * p.out_bs + (size_t)(p.out_coff + nbase) * HWr + pix;
+      const float* mk = p.mask_y ? p.mask_y + (size_t)b * p.mask_bs + (size_t)nbase * HWr + pix : nullptr;
+      const float* rs = p.residual ? p.residual + (size_t)b * p.res_bs + (size_t)nbase * HWr + pix : nullptr;
+      const bool st_ok = valid && !(p.debug & 2);
+      const size_t step16 = (size_t)16 * HWr;
+      const int ncols = min(BN, p.N - nbase);            // valid columns of this pass
+      const int ngroups = (ncols + 15) >> 4;             // 16-column groups, two TMEM loads in flight
+      uint32_t ra[16], rb[16];
+      auto emit = [&](const uint32_t (&cur)[16], int gi) {
+        const int nrem = ncols - gi * 16;
+        if (st_ok) {
+          if (epi_plain) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nrem) o[(size_t)i * HWr] = __uint_as_float(cur[i]);
+          } else if (epi_res) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nrem) o[(size_t)i * HWr] = __uint_as_float(cur[i]) + __ldg(rs + (size_t)i * HWr);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < nrem) {
+                float y = __uint_as_float(cur[i]);
+                if (p.bias) y += __ldg(p.bias + nbase + gi * 16 + i);
+                if (p.act) y = y > 0.f ? y : y * p.slope;
+                if (mk) y *= (__ldg(mk + (size_t)i * HWr) > 0.f) ? 1.f : p.slope;
+                if (rs) y += __ldg(rs + (size_t)i * HWr);
+                if (p.accumulate) y += o[(size_t)i * HWr];
+                o[(size_t)i * HWr] = y;
+              }
+            }
+          }
+        }
+        o += step16;
+        if (mk) mk += step16;
+        if (rs) rs += step16;
+      };
+      const uint32_t tbase = lane_base + buf * BN;
+      if (!(p.debug & 16)) tmem_ld16_nowait(tbase, ra);
+      for (int gi = 0; gi < ((p.debug & 16) ? 0 : ngroups); gi += 2) {   // two TMEM loads in flight, registers ping-pong
+        tmem_ld_wait();
+        if (gi + 1 < ngroups) tmem_ld16_nowait(tbase + (gi + 1) * 16, rb);
+        emit(ra, gi);
+        if (gi + 1 < ngroups) {
+          tmem_ld_wait();
+          if (gi + 2 < ngroups) tmem_ld16_nowait(tbase + (gi + 2) * 16, ra);
+          emit(rb, gi + 1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem, g.tmem_cols);
 }
+
+static int g_num_sms = 0;
 
 template <int KS, int MODE, int TERMS, bool LN>
 static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
-  const int K = (p.C1 + p.C2) * KS * KS;
-  const int nk = cdiv(K, KC);
+  PmGeom g;
+  g.Ktot = (p.C1 + p.C2) * KS * KS;
+  g.nk = cdiv(g.Ktot, KC);
   NPlan pl = make_nplan(p.N);
+  g.BN = pl.BN;
+  g.passes = pl.passes;
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const size_t stage_bytes = (size_t)TA * (128 * KC * 2) + (size_t)TA * pl.NSUB * pl.BN * KC * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t stage_bytes = (size_t)TA * (128 * KC * 2 + (size_t)pl.BN * KC * 2);
+  const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
+  g.c1_aligned = (p.C2 == 0 || p.C1 % 8 == 0) ? 1 : 0;
+  int stages = (int)((196 * 1024) / stage_bytes);
   if (stages > PM_MAX_STAGES) stages = PM_MAX_STAGES;
-  if (stages > nk) stages = nk < 1 ? 1 : nk;
-  if (stages < 1) stages = 1;
-  const size_t smem = stages * stage_bytes;
+  if (stages < 2) stages = 2;
+  g.stages = stages;
+  const long HWr = (long)p.Hr * p.Wr;
+  g.flat = (p.wpack_bs == 0) ? 1 : 0;
+  g.rows_total = HWr * p.B;
+  g.tiles_per_img = cdiv(HWr, 128);
+  g.tiles_m = g.flat ? cdiv(g.rows_total, 128) : g.tiles_per_img * p.B;
+  g.tmem_cols = tmem_cols_pow2(2 * pl.BN);
+  const size_t smem = stages * stage_bytes + ln_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) {
       set_error("pm_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return RCOT_ERR_CUDA;
     }
     attr_set = true;
   }
-  dim3 grid(cdiv((long)p.Hr * p.Wr, 128), pl.passes, p.B);
-  pm_gemm_kernel<KS, MODE, TERMS, LN><<<grid, 128, smem, stream>>>(p, K, nk, pl.BN, pl.NSUB, stages,
-                                                                     tmem_cols_pow2(pl.NSUB * pl.BN));
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const long total = (long)g.tiles_m * g.passes;
+  const int grid = (int)(total < g_num_sms ? total : g_num_sms);
+  pm_gemm_kernel<KS, MODE, TERMS, LN><<<grid, PM_THREADS, smem, stream>>>(p, g);
   return check_launch("pm_gemm");
 }
 
@@ -209,7 +382,6 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
   RCOT_REQUIRE(p.Hs > 0 && p.Ws > 0 && p.Hr > 0 && p.Wr > 0, "pm_gemm: bad spatial sizes");
   RCOT_REQUIRE(p.terms == 1 || p.terms == 3, "pm_gemm: terms must be 1 or 3");
   RCOT_REQUIRE(p.mode == 0 || p.mode == 1, "pm_gemm: mode must be 0 or 1");
-  RCOT_REQUIRE(p.B <= 65535, "pm_gemm: batch too large for grid.z");
   const bool ln = p.ln_stats != nullptr;
   if (ln) RCOT_REQUIRE(p.ks == 1 && p.ln_gamma && p.ln_beta, "pm_gemm: LayerNorm prologue needs ks==1, gamma, beta");
   if (p.ks == 1)

@@ -149,6 +149,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 columns, no wait: pair with tmem_ld_wait() before the registers are read.
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t tmem_lane_base(uint32_t tmem_base) {
   // lane field is bits [31:16]; each warp may only touch its own 32-lane quarter.
   return tmem_base + ((((threadIdx.x >> 5) & 3u) * 32u) << 16);
@@ -167,36 +189,34 @@ __device__ __host__ inline uint32_t op_offset(int row, int k) {  // k in [0,KC)
 // Byte offset of element (n, k), term (0 = hi, 1 = lo), inside the packed B-operand image of an
 // [N x K] matrix: tiles ordered [pass][k-chunk][term][sub-tile][BN x 32] (see pack.cu / make_nplan).
 __device__ __host__ inline size_t packed_offset(int N, int K, int n, int k, int term) {
-  int BN, NSUB;
-  if (N <= 256) {
-    BN = (N + 15) / 16 * 16;
-    NSUB = 1;
-  } else {
-    const int nst = (N + 255) / 256;
-    BN = ((N + nst - 1) / nst + 15) / 16 * 16;
-    NSUB = 2;
-  }
+  const int nst = (N + 255) / 256;
+  const int BN = ((N + nst - 1) / nst + 15) / 16 * 16;
   const int nk = (K + KC - 1) / KC;
-  const int si = n / BN, np = n - si * BN;
-  const int pass = si / NSUB, sub = si - pass * NSUB;
+  const int pass = n / BN, np = n - pass * BN;
   const int kc = k / KC, kp = k - kc * KC;
   const size_t tile = (size_t)BN * KC * 2;
-  return ((((size_t)pass * nk + kc) * 2 + term) * NSUB + sub) * tile + op_offset(np, kp);
+  return (((size_t)pass * nk + kc) * 2 + term) * tile + op_offset(np, kp);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-// Split 8 fp32 values into bf16 hi and lo (x ~= hi + lo, |err| <= 2^-17 |x|).
+// Split 8 fp32 values into bf16 hi and lo (x ~= hi + lo, |err| <= 2^-17 |x|).  Pairs are converted
+// with the packed cvt.rn.bf16x2.f32 (F2FP, full rate); hi is widened back with shifts/masks.
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  __nv_bfloat16 h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = __float2bfloat16_rn(v[i]);
-    l[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h[i]));
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);   // .x = low half = v[2i]
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+    h[i] = hb;
+    const float r0 = v[2 * i] - __uint_as_float(hb << 16);
+    const float r1 = v[2 * i + 1] - __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
   }
-  hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-  lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 // Store 8 consecutive-k values of one operand row (k8 = k/8 within the stage).
 template <int TERMS>

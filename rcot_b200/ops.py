@@ -30,6 +30,7 @@ class PMParams(C.Structure):
         ("out", C.c_void_p), ("out_bs", C.c_int64), ("out_coff", C.c_int32), ("act", C.c_int32),
         ("slope", C.c_float), ("accumulate", C.c_int32), ("bias", C.c_void_p),
         ("mask_y", C.c_void_p), ("mask_bs", C.c_int64), ("residual", C.c_void_p), ("res_bs", C.c_int64),
+        ("debug", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -176,7 +177,7 @@ def pack_single(w: torch.Tensor, kind: str):
 # ------------------------------------------------------------------ pixel-as-M GEMM
 def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None, out_hw=None, out_coff=0,
             ln=None, bias=None, act=False, slope=0.2, mask_y=None, residual=None, accumulate=False,
-            wpack_bs=0, terms=None):
+            wpack_bs=0, terms=None, debug=0):
     """out[b, coff+n, p] = epi(sum_k A(b,p,k) W[n,k]).  ``ln`` = (stats[B,HW,2], gamma, beta)."""
     B, C1, Hs, Ws = x.shape
     in_bs = _img_view(x, "x")
@@ -201,6 +202,7 @@ def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None
     p.wpack, p.wpack_bs, p.N, p.terms = wpack_ptr, wpack_bs, N, (TERMS if terms is None else terms)
     p.out, p.out_bs, p.out_coff = out.data_ptr(), out_bs, out_coff
     p.act, p.slope, p.accumulate = int(act), slope, int(accumulate)
+    p.debug = debug
     p.bias = None if bias is None else _f32(bias).data_ptr()
     if mask_y is not None:
         p.mask_y, p.mask_bs = mask_y.data_ptr(), _img_view(mask_y, "mask_y")
@@ -409,8 +411,9 @@ class Profiler:
     """Per-op CUDA-event timing on the launching stream plus the op's ALGORITHMIC bytes (every
     operand counted once: what an ideal kernel must move), for bench.py's roofline block."""
 
-    def __init__(self):
+    def __init__(self, detail=False):
         self.records = []
+        self.detail = detail        # key ops by shape as well (offline analysis)
 
     def summary(self):
         torch.cuda.synchronize()
@@ -442,7 +445,11 @@ def _instrument(name, bytes_fn):
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            PROF.records.append((name, e0, e1, int(bytes_fn(a, k, r))))
+            key = name
+            if PROF.detail:
+                shp = [tuple(t.shape) for t in a if isinstance(t, torch.Tensor)][:2]
+                key = f"{name} {shp} N={a[2] if name == 'pm_gemm' else ''} ks={k.get('ks', 1)} mode={k.get('mode', 0)}"
+            PROF.records.append((key, e0, e1, int(bytes_fn(a, k, r))))
             return r
         wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
         return wrapped
