@@ -97,8 +97,11 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         x.valid = pix < HWr;
         if (!x.valid) pix = 0;
       }
-      x.ry = pix / p.Wr;
-      x.rx = pix - x.ry * p.Wr;
+      {
+        const int ry = pix / p.Wr, rx = pix - ry * p.Wr;
+        x.ry = (MODE == 0) ? ry * p.stride - p.pad : ry + p.pad;
+        x.rx = (MODE == 0) ? rx * p.stride - p.pad : rx + p.pad;
+      }
       const int poff = (KS == 1) ? pix : 0;
       x.b1 = p.in + (size_t)b * p.in_bs + poff;
       x.b2 = p.in2 ? p.in2 + (size_t)b * p.in2_bs + poff : nullptr;
@@ -114,52 +117,64 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       return x;
     };
     auto load16 = [&](float* v, const TileCtx& x, int c) {
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int k0 = c * KC + (khalf * 2 + kk) * 8;
-        if (KS == 1 && g.c1_aligned) {
-          // 8 consecutive channels of one source tensor, same pixel: pointer + i*HW
+      const int k0 = c * KC + khalf * 16;   // this thread's 16 consecutive K indices of the chunk
+      if (KS == 1) {
+        if (x.valid && g.c1_aligned && k0 + 16 <= g.Ktot) {
+          // fast path: 16 channels of ONE source tensor at this pixel -> base + i*HW, no predicates
           const float* sp = (k0 < p.C1) ? x.b1 + (size_t)k0 * HWs : x.b2 + (size_t)(k0 - p.C1) * HWs;
-          const bool full = x.valid && (k0 + 8 <= g.Ktot) && !(p.debug & 1);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float val = 0.f;
-            if (full || (x.valid && k0 + i < g.Ktot && !(p.debug & 1))) val = __ldg(sp + (size_t)i * HWs);
-            v[kk * 8 + i] = val;
-          }
-        } else {
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(sp + (size_t)i * HWs);
+          return;
+        }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = k0 + i;
-            float val = 0.f;
-            if (x.valid && k < g.Ktot) {
-              int ch, sy, sx;
-              bool ok = true;
-              if (KS == 1) {
-                ch = k;
-                sy = 0;
-                sx = 0;   // pixel offset already folded into b1/b2
-              } else {
-                ch = k / (KS * KS);
-                const int r = k - ch * (KS * KS);
-                const int ky = r / KS, kx = r - ky * KS;
-                if (MODE == 0) {
-                  sy = x.ry * p.stride + ky - p.pad;
-                  sx = x.rx * p.stride + kx - p.pad;
-                } else {
-                  const int ty = x.ry + p.pad - ky, tx = x.rx + p.pad - kx;
-                  sy = ty / p.stride;
-                  sx = tx / p.stride;
-                  ok = (ty >= 0) && (tx >= 0) && (sy * p.stride == ty) && (sx * p.stride == tx);
-                }
-                ok = ok && ((unsigned)sy < (unsigned)p.Hs) && ((unsigned)sx < (unsigned)p.Ws);
-              }
-              if (ok && !(p.debug & 1)) {
-                const float* sp = (ch < p.C1) ? (x.b1 + (size_t)ch * HWs) : (x.b2 + (size_t)(ch - p.C1) * HWs);
-                val = __ldg(sp + sy * p.Ws + sx);
-              }
+        for (int i = 0; i < 16; ++i) {
+          const int k = k0 + i;
+          float val = 0.f;
+          if (x.valid && k < g.Ktot)
+            val = __ldg((k < p.C1) ? (x.b1 + (size_t)k * HWs) : (x.b2 + (size_t)(k - p.C1) * HWs));
+          v[i] = val;
+        }
+        return;
+      }
+      // general conv geometry: decompose k0 once, then step (ch, ky, kx)
+      constexpr int KK = KS * KS;
+      int ch = k0 / KK;
+      const int r0 = k0 - ch * KK;
+      int ky = r0 / KS, kx = r0 - ky * KS;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float val = 0.f;
+        if (x.valid && k0 + i < g.Ktot) {
+          int sy, sx;
+          bool ok;
+          if (MODE == 0) {
+            sy = x.ry + ky;     // ry pre-scaled: ry*stride - pad
+            sx = x.rx + kx;
+            ok = true;
+          } else {
+            const int ty = x.ry - ky, tx = x.rx - kx;   // ry pre-offset: ry + pad
+            if (p.stride == 1) {
+              sy = ty;
+              sx = tx;
+              ok = true;
+            } else {            // stride 2 (checked by the launcher)
+              sy = ty >> 1;
+              sx = tx >> 1;
+              ok = ((ty | tx) & 1) == 0;
             }
-            v[kk * 8 + i] = val;
+          }
+          ok = ok && ((unsigned)sy < (unsigned)p.Hs) && ((unsigned)sx < (unsigned)p.Ws);
+          if (ok) {
+            const float* sp = (ch < p.C1) ? (x.b1 + (size_t)ch * HWs) : (x.b2 + (size_t)(ch - p.C1) * HWs);
+            val = __ldg(sp + sy * p.Ws + sx);
+          }
+        }
+        v[i] = val;
+        if (++kx == KS) {
+          kx = 0;
+          if (++ky == KS) {
+            ky = 0;
+            ++ch;
           }
         }
       }
@@ -188,12 +203,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* st = smem + (size_t)s * stage_bytes;
       if (tid == 0) {
-        if (p.debug & 8) {
-          mbar_arrive(&full_bar[s]);
-        } else {
-          mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
-          bulk_g2s(st + TA * a_tile, cur.wsrc + (size_t)cc * (2 * b_tile), TA * b_tile, &full_bar[s]);
-        }
+        mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
+        bulk_g2s(st + TA * a_tile, cur.wsrc + (size_t)cc * (2 * b_tile), TA * b_tile, &full_bar[s]);
       }
       if (LN) {
         const float* gb = ln_gb + (cc * KC + khalf * 16) * 2;   // interleaved (gamma, beta), zero beyond Ktot
@@ -205,36 +216,35 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
           }
         }
       }
-      if (!(p.debug & 32)) {
-        op_store8<TERMS>(st, st + a_tile, row, khalf * 2, v);
-        op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, v + 8);
-      }
+      op_store8<TERMS>(st, st + a_tile, row, khalf * 2, v);
+      op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, v + 8);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
     }
   } else if (warp == PM_PROD_WARPS) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BN);
-      uint32_t it = 0, tcount = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
-        const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(&acc_empty[buf], aph ^ 1);
+    // =========================================================== MMA issuer (whole warp waits, lane 0 issues)
+    const uint32_t idesc = make_idesc_bf16(128, BN);
+    uint32_t it = 0, tcount = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&acc_empty[buf], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem + buf * BN;
+      for (int c = 0; c < nk; ++c, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (it / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d = tmem + buf * BN;
-        for (int c = 0; c < nk; ++c, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
+        if (lane == 0) {
           const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-          if (!(p.debug & 4))
-            issue_stage<TERMS>(d, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, c == 0);
-          if (p.debug & 64) mbar_arrive(&empty_bar[s]); else tc_commit(&empty_bar[s]);
+          issue_stage<TERMS>(d, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, c == 0);
+          tc_commit(&empty_bar[s]);
         }
-        if (p.debug & 64) mbar_arrive(&acc_full[buf]); else tc_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (lane == 0) tc_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // =========================================================== epilogue (warp % 4 = TMEM lane quarter)
@@ -264,51 +274,73 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       float* o = p.out + (size_t)b * p.out_bs + (size_t)(p.out_coff + nbase) * HWr + pix;
       const float* mk = p.mask_y ? p.mask_y + (size_t)b * p.mask_bs + (size_t)nbase * HWr + pix : nullptr;
       const float* rs = p.residual ? p.residual + (size_t)b * p.res_bs + (size_t)nbase * HWr + pix : nullptr;
-      const bool st_ok = valid && !(p.debug & 2);
-      const size_t step16 = (size_t)16 * HWr;
+      const bool st_ok = valid;
       const int ncols = min(BN, p.N - nbase);            // valid columns of this pass
-      const int ngroups = (ncols + 15) >> 4;             // 16-column groups, two TMEM loads in flight
+      const int ngroups = (ncols + 15) >> 4;             // 16-column groups
       uint32_t ra[16], rb[16];
-      auto emit = [&](const uint32_t (&cur)[16], int gi) {
+      float qa[16], qb[16];                              // residual values, fetched one group ahead
+      auto ldres = [&](float (&q)[16], int gi) {
         const int nrem = ncols - gi * 16;
-        if (st_ok) {
-          if (epi_plain) {
+        const float* r0 = rs + (size_t)(gi * 16) * HWr;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nrem) o[(size_t)i * HWr] = __uint_as_float(cur[i]);
-          } else if (epi_res) {
+        for (int i = 0; i < 16; ++i) q[i] = (st_ok && i < nrem) ? __ldg(r0 + (size_t)i * HWr) : 0.f;
+      };
+      auto emit = [&](const uint32_t (&cur)[16], const float (&q)[16], int gi) {
+        const int nrem = ncols - gi * 16;
+        if (!st_ok) return;
+        float* og = o + (size_t)(gi * 16) * HWr;
+        if (epi_plain) {
+          if (nrem >= 16) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nrem) o[(size_t)i * HWr] = __uint_as_float(cur[i]) + __ldg(rs + (size_t)i * HWr);
+            for (int i = 0; i < 16; ++i) og[(size_t)i * HWr] = __uint_as_float(cur[i]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i < nrem) {
-                float y = __uint_as_float(cur[i]);
-                if (p.bias) y += __ldg(p.bias + nbase + gi * 16 + i);
-                if (p.act) y = y > 0.f ? y : y * p.slope;
-                if (mk) y *= (__ldg(mk + (size_t)i * HWr) > 0.f) ? 1.f : p.slope;
-                if (rs) y += __ldg(rs + (size_t)i * HWr);
-                if (p.accumulate) y += o[(size_t)i * HWr];
-                o[(size_t)i * HWr] = y;
-              }
+            for (int i = 0; i < 16; ++i)
+              if (i < nrem) og[(size_t)i * HWr] = __uint_as_float(cur[i]);
+          }
+        } else if (epi_res) {
+          if (nrem >= 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) og[(size_t)i * HWr] = __uint_as_float(cur[i]) + q[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nrem) og[(size_t)i * HWr] = __uint_as_float(cur[i]) + q[i];
+          }
+        } else {
+          const float* mg = mk ? mk + (size_t)(gi * 16) * HWr : nullptr;
+          const float* rg = rs ? rs + (size_t)(gi * 16) * HWr : nullptr;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < nrem) {
+              float y = __uint_as_float(cur[i]);
+              if (p.bias) y += __ldg(p.bias + nbase + gi * 16 + i);
+              if (p.act) y = y > 0.f ? y : y * p.slope;
+              if (mg) y *= (__ldg(mg + (size_t)i * HWr) > 0.f) ? 1.f : p.slope;
+              if (rg) y += __ldg(rg + (size_t)i * HWr);
+              if (p.accumulate) y += og[(size_t)i * HWr];
+              og[(size_t)i * HWr] = y;
             }
           }
         }
-        o += step16;
-        if (mk) mk += step16;
-        if (rs) rs += step16;
       };
       const uint32_t tbase = lane_base + buf * BN;
-      if (!(p.debug & 16)) tmem_ld16_nowait(tbase, ra);
-      for (int gi = 0; gi < ((p.debug & 16) ? 0 : ngroups); gi += 2) {   // two TMEM loads in flight, registers ping-pong
+      tmem_ld16_nowait(tbase, ra);
+      if (epi_res) ldres(qa, 0);
+      for (int gi = 0; gi < ngroups; gi += 2) {   // TMEM + residual loads run one group ahead of the stores
         tmem_ld_wait();
-        if (gi + 1 < ngroups) tmem_ld16_nowait(tbase + (gi + 1) * 16, rb);
-        emit(ra, gi);
+        if (gi + 1 < ngroups) {
+          tmem_ld16_nowait(tbase + (gi + 1) * 16, rb);
+          if (epi_res) ldres(qb, gi + 1);
+        }
+        emit(ra, qa, gi);
         if (gi + 1 < ngroups) {
           tmem_ld_wait();
-          if (gi + 2 < ngroups) tmem_ld16_nowait(tbase + (gi + 2) * 16, ra);
-          emit(rb, gi + 1);
+          if (gi + 2 < ngroups) {
+            tmem_ld16_nowait(tbase + (gi + 2) * 16, ra);
+            if (epi_res) ldres(qa, gi + 2);
+          }
+          emit(rb, qb, gi + 1);
         }
       }
       tc_fence_before();
@@ -334,7 +366,7 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   constexpr int TA = (TERMS > 1) ? 2 : 1;
   const size_t stage_bytes = (size_t)TA * (128 * KC * 2 + (size_t)pl.BN * KC * 2);
   const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
-  g.c1_aligned = (p.C2 == 0 || p.C1 % 8 == 0) ? 1 : 0;
+  g.c1_aligned = (p.C2 == 0 || p.C1 % 16 == 0) ? 1 : 0;
   int stages = (int)((196 * 1024) / stage_bytes);
   if (stages > PM_MAX_STAGES) stages = PM_MAX_STAGES;
   if (stages < 2) stages = 2;
@@ -386,7 +418,7 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
   if (ln) RCOT_REQUIRE(p.ks == 1 && p.ln_gamma && p.ln_beta, "pm_gemm: LayerNorm prologue needs ks==1, gamma, beta");
   if (p.ks == 1)
     RCOT_REQUIRE(p.stride == 1 && p.pad == 0 && p.Hs == p.Hr && p.Ws == p.Wr, "pm_gemm: 1x1 needs stride 1, pad 0");
-  RCOT_REQUIRE(p.stride >= 1, "pm_gemm: stride must be >= 1");
+  RCOT_REQUIRE(p.stride == 1 || p.stride == 2, "pm_gemm: stride must be 1 or 2");
 #define PM_DISPATCH(KS, MODE, LN)                                           \
   return (p.terms == 3) ? launch_pm<KS, MODE, 3, LN>(p, stream) : launch_pm<KS, MODE, 1, LN>(p, stream)
   switch (p.ks) {

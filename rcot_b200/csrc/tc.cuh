@@ -39,6 +39,28 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Pure polling wait (no suspension), bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 3000000000LL) {
+      printf("rcot: mbarrier spin wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a barrier that never completes traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
