@@ -105,6 +105,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def make_config(P, B, world):
+    return {"workload": f"one full adversarial iteration (F-sub + GP + T-sub, 3 optimizer steps), {P}x{P} patches, "
+                        f"per-GPU batch {B}, paired, de_id mix [1,3]",
+            "patch": P, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": "working set per step (tens of GB) >> 126 MB L2; no explicit flush"}
+
+
 def block_algorithmic_bytes(B, P):
     """per TransformerBlock call fwd 5*B*C*H*W*4 + W, bwd 8*B*C*H*W*4 + 2W; sum over the 102
     calls of one T_net forward: sum C*N = 49.35 M elements per 128^2 image, block weights 0.2567 GB."""
@@ -154,8 +161,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
             "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * Bs / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"one full adversarial iteration (F-sub + GP + T-sub), {args.patch}x{args.patch} patches",
-                       "patch": args.patch, "per_gpu_batch": args.batch, "paired": True},
+            "config": make_config(args.patch, args.batch, args.gpus),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{done} iteration(s) of the same step at batch {Bs} (bounded sample), PyTorch CPU fp32, "
                                        f"{cores} threads; oracle/train_ref.py"},
@@ -255,15 +261,14 @@ def run_b200(args):
                         "CUDA-event time, taken on one extra step right after the timed region"}
     barrier()
     if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 storage, bf16x3 split products on tcgen05 (fp32-class)" if args.terms == 3 else "bf16 products, fp32 storage/accumulate",
             "data": "synthetic",
-            "config": {"workload": f"one full adversarial iteration (F-sub + GP + T-sub, 3 optimizer steps), {P}x{P} patches, "
-                                   f"per-GPU batch {B}, paired, de_id mix [1,3]",
-                       "patch": P, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "working set per step (tens of GB) >> 126 MB L2; no explicit flush"},
+            "config": make_config(P, B, world),
             "clocks": sampler.result(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms2.item() / K},
