@@ -222,14 +222,16 @@ def run_b200(args):
     value = B * world * K / (ms / 1000.0)
 
     # ---- end to end: pinned host batches -> trainer.train_one -> losses read back every step
+    # (host batches hold the GLOBAL batch, identical on every rank; train_one takes this rank's shard)
+    host_g = host if world == 1 else synth_host_batches(4, B * world, P, seed=123)
     h2d = sum(t.numel() * t.element_size() for t in (host[0][1], host[0][2], host[0][0][1])) + 4 * B
     torch.manual_seed(1)
     for i in range(2):
-        trainer.train_one(step, host[i % 4], i, lr)
+        trainer.train_one(step, host_g[i % 4], i, lr)
     barrier()
     e0.record()
     for i in range(K):
-        r, _, _ = trainer.train_one(step, host[i % 4], i, lr)
+        r, _, _ = trainer.train_one(step, host_g[i % 4], i, lr)
         losses = torch.stack([r["loss_F"], r["loss_T"], r["loss_mse"]]).tolist()      # D2H + sync each step
     e1.record()
     barrier()
