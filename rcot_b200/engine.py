@@ -75,10 +75,18 @@ class ParamSet:
 class Tape:
     """Reverse-mode tape over engine ops. Gradients are keyed by tensor identity."""
 
-    def __init__(self, enabled=True):
+    def __init__(self, enabled=True, save_hidden=False):
         self.enabled = enabled
+        self.save_hidden = save_hidden   # keep the blocks' hidden tensors instead of recomputing them in backward
         self.ops = []
         self.grads = {}
+        self.calls = {}
+
+    def slot(self, key):
+        """How many times `key` (a block) has been invoked on this tape so far."""
+        n = self.calls.get(key, 0)
+        self.calls[key] = n + 1
+        return n
 
     def record(self, out, bwd):
         if self.enabled:
@@ -149,6 +157,19 @@ class AttnScratch:
         return self.W12pack
 
 
+class AttnSaved:
+    """Per (block, invocation) copies of what MDTA's backward needs from its forward: row norms, softmax,
+    normalised Gram and the packed M^T.  Allocated once and reused every iteration (zero-initialised pack
+    padding persists because the kernels always write the same entries)."""
+
+    def __init__(self, B, C, heads, device):
+        c = C // heads
+        self.sumsq = torch.zeros(B, 2 * C, device=device)
+        self.A = torch.empty(B, heads, c, c, device=device)
+        self.Gt = torch.empty(B, heads, c, c, device=device)
+        self.MTpack = torch.zeros(B * ops.packed_bytes(C, C), dtype=torch.uint8, device=device)
+
+
 # ---------------------------------------------------------------------------------- Restormer block
 class BlockSpec:
     """Names and sizes of one TransformerBlock inside a ParamSet."""
@@ -156,6 +177,7 @@ class BlockSpec:
     def __init__(self, ps: ParamSet, prefix: str, C: int, heads: int, has_norm=True, has_attn=True, has_ffn=True):
         self.ps, self.pre, self.C, self.heads = ps, prefix, C, heads
         self.has_norm, self.has_attn, self.has_ffn = has_norm, has_attn, has_ffn
+        self.saved_cache = {}
         if has_attn:
             a = prefix + "attn."
             ps.add_pack(a + "qkv.weight", "fwd")
@@ -172,23 +194,27 @@ def _ln_args(ps, name, stats):
     return (stats, ps.p[name + ".body.weight"], ps.p[name + ".body.bias"])
 
 
-def mdta_fwd(bs: BlockSpec, x, norm_name, residual, need_bwd):
-    """y = [x +] project_out(attn(dwconv(qkv(LN(x))))).  Returns (y, ctx)."""
+def mdta_fwd(bs: BlockSpec, x, norm_name, residual, need_bwd, store=None):
+    """y = [x +] project_out(attn(dwconv(qkv(LN(x))))).  Returns (y, ctx).
+    ``store`` (AttnSaved) receives the small tensors the backward needs; default: the shared scratch."""
     ps, C, h = bs.ps, bs.C, bs.heads
     a = bs.pre + "attn."
     B, _, H, W = x.shape
     sc = AttnScratch.get(B, C, h, x.device)
+    st = sc if store is None else store
     stats = ops.ln_stats(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
     pre = ops.pm_gemm(x, ps.pack(a + "qkv.weight", "fwd"), 3 * C, ln=ln)
     ops.zero_(sc.zbuf)
-    qkv = ops.dwconv(pre, ps.p[a + "qkv_dwconv.weight"], sumsq=sc.sumsq, nsq=2 * C)
+    if store is not None:
+        ops.zero_(store.sumsq)
+    qkv = ops.dwconv(pre, ps.p[a + "qkv_dwconv.weight"], sumsq=st.sumsq, nsq=2 * C)
     c = C // h
     ops.pk_gemm(qkv[:, :C], qkv[:, C:2 * C], sc.G, ldo=c, per_image=True, groups=h, out_gs=c * c)
-    ops.attn_fwd(sc.G, sc.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], sc.A, sc.Gt, sc.Mpack,
-                 sc.MTpack if need_bwd else None, B, C, h)
+    ops.attn_fwd(sc.G, st.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], st.A, st.Gt, sc.Mpack,
+                 st.MTpack if need_bwd else None, B, C, h)
     y = ops.pm_gemm(qkv[:, 2 * C:], sc.Mpack.data_ptr(), C, wpack_bs=sc.pb, residual=x if residual else None)
-    return y, (stats, pre, qkv, sc)
+    return y, (stats, pre, qkv, sc, st)
 
 
 def mdta_bwd(bs: BlockSpec, x, dy, norm_name, residual, ctx):
@@ -196,13 +222,15 @@ def mdta_bwd(bs: BlockSpec, x, dy, norm_name, residual, ctx):
     ps, C, h = bs.ps, bs.C, bs.heads
     a = bs.pre + "attn."
     B, _, H, W = x.shape
-    stats, pre, qkv, sc = ctx
+    stats, pre, qkv, sc, st = ctx
+    if st is not sc:
+        ops.zero_(sc.P)          # the forward that zeroed the shared scratch may be long gone
     ops.pk_gemm(dy, qkv[:, 2 * C:], sc.P, ldo=C, per_image=True)
-    ops.attn_bwd(sc.P, sc.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], sc.A, sc.Gt,
+    ops.attn_bwd(sc.P, st.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], st.A, st.Gt,
                  ps.g[a + "project_out.weight"], ps.g[a + "temperature"], sc.w12(), B, C, h)
     dqkv = torch.empty_like(qkv)
     ops.pm_gemm(qkv[:, :2 * C], sc.w12().data_ptr(), 2 * C, wpack_bs=sc.pb12, out=dqkv, out_coff=0)
-    ops.pm_gemm(dy, sc.MTpack.data_ptr(), C, wpack_bs=sc.pb, out=dqkv, out_coff=2 * C)
+    ops.pm_gemm(dy, st.MTpack.data_ptr(), C, wpack_bs=sc.pb, out=dqkv, out_coff=2 * C)
     dw = ps.p[a + "qkv_dwconv.weight"]
     dpre = ops.dwconv(dqkv, dw, flip=True)
     ops.dwconv_wgrad(pre, dqkv, ps.g[a + "qkv_dwconv.weight"])
@@ -215,7 +243,7 @@ def mdta_bwd(bs: BlockSpec, x, dy, norm_name, residual, ctx):
                       ps.g[norm_name + ".body.bias"], dy=dy if residual else None, dx=dz)
 
 
-def gdfn_fwd(bs: BlockSpec, x, norm_name, residual):
+def gdfn_fwd(bs: BlockSpec, x, norm_name, residual, keep=False):
     ps, C = bs.ps, bs.C
     f = bs.pre + "ffn."
     hid = bs.hid
@@ -224,17 +252,22 @@ def gdfn_fwd(bs: BlockSpec, x, norm_name, residual):
     u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
     g = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=1)
     y = ops.pm_gemm(g, ps.pack(f + "project_out.weight", "fwd"), C, residual=x if residual else None)
-    return y
+    return (y, (stats, u)) if keep else y
 
 
-def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual):
-    """Recomputes the hidden tensors from x, returns dx (fresh tensor)."""
+def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual, kept=None):
+    """Returns dx (fresh tensor). The hidden tensor u and the LN statistics come from ``kept`` (saved by the
+    forward) or are recomputed from x."""
     ps, C = bs.ps, bs.C
     f = bs.pre + "ffn."
     hid = bs.hid
-    stats = ops.ln_stats(x) if norm_name else None
+    if kept is not None:
+        stats, u = kept
+    else:
+        stats = ops.ln_stats(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
-    u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
+    if kept is None:
+        u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
     dg = ops.pm_gemm(dy, ps.pack(f + "project_out.weight", "dgrad"), hid)
     g = torch.empty_like(dg)
     dab = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=2, dg=dg, g_out=g, out=torch.empty_like(u))
@@ -253,7 +286,24 @@ def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual):
 
 
 def block_fwd(bs: BlockSpec, x, tape: Tape | None):
-    """TransformerBlock: x + MDTA(LN1(x)), then + GDFN(LN2(.)). Saves only the block input."""
+    """TransformerBlock: x + MDTA(LN1(x)), then + GDFN(LN2(.)).
+    Backward either recomputes the hidden tensors from the saved block input (small memory), or -- with
+    tape.save_hidden -- reuses pre/qkv/u and the small attention matrices kept by the forward
+    (12.3 C*H*W floats per block: 78 GB at B=32, P=128, which the 180 GB of HBM3e accommodate)."""
+    if tape is not None and tape.enabled and tape.save_hidden:
+        B = x.shape[0]
+        key = (B, tape.slot(id(bs)))
+        store = bs.saved_cache.get(key)
+        if store is None:
+            store = bs.saved_cache[key] = AttnSaved(B, bs.C, bs.heads, x.device)
+        xm, ctx = mdta_fwd(bs, x, bs.pre + "norm1", True, True, store=store)
+        y, kept = gdfn_fwd(bs, xm, bs.pre + "norm2", True, keep=True)
+
+        def bwd_saved(dy, x=x, xm=xm, ctx=ctx, kept=kept):
+            dxm = gdfn_bwd(bs, xm, dy, bs.pre + "norm2", True, kept=kept)
+            tape.add_grad(x, mdta_bwd(bs, x, dxm, bs.pre + "norm1", True, ctx))
+        tape.record(y, bwd_saved)
+        return y
     xm, _ = mdta_fwd(bs, x, bs.pre + "norm1", True, False)
     y = gdfn_fwd(bs, xm, bs.pre + "norm2", True)
     if tape is not None and tape.enabled:

@@ -46,12 +46,13 @@ class FlatOptimizer:
 
 
 class OTTrainStep:
-    def __init__(self, Tprog, Fprog, optimizer="RMSprop", sigma=1.0, Sigma=10000.0, group=None):
+    def __init__(self, Tprog, Fprog, optimizer="RMSprop", sigma=1.0, Sigma=10000.0, group=None, save_hidden=None):
         self.T, self.F = Tprog, Fprog
         self.sigma, self.Sigma = float(sigma), float(Sigma)
         self.T_opt = FlatOptimizer(Tprog.ps, optimizer)
         self.F_opt = FlatOptimizer(Fprog.ps, optimizer)
         self.group = group
+        self.save_hidden = save_hidden      # None: decide per batch from free HBM
         self.world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(group)
@@ -67,7 +68,12 @@ class OTTrainStep:
         T, F = self.T, self.F
         B, _, P, _ = degraded.shape
         Bg = B * self.world
-        tape = Tape()
+        save = self.save_hidden
+        if save is None:
+            # hidden tensors of all 102 blocks: 12.3 * 49.35 M floats per 128x128 image
+            need = 12.3 * 49.35e6 * 4 * B * (P / 128.0) ** 2
+            save = need < 0.55 * torch.cuda.get_device_properties(degraded.device).total_memory
+        tape = Tape(save_hidden=bool(save))
         out = T.forward(degraded, tape)
         # ---------------- F-sub
         F.ps.zero_grad()

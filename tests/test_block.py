@@ -34,9 +34,10 @@ def _check(name, got, ref, rtol=1e-3, atol=1e-4):
     assert bad == 0, name
 
 
+@pytest.mark.parametrize("save", [False, True])
 @pytest.mark.parametrize("C,heads,H,W", [(48, 1, 16, 16), (96, 1, 8, 16), (96, 2, 8, 8), (96, 4, 8, 8),
                                          (192, 4, 8, 8), (384, 8, 4, 4), (384, 4, 4, 8)])
-def test_block_fwd_bwd(cuda_lib, C, heads, H, W):
+def test_block_fwd_bwd(cuda_lib, C, heads, H, W, save):
     from oracle import restormer_ref as R
     from rcot_b200 import engine
 
@@ -53,7 +54,7 @@ def test_block_fwd_bwd(cuda_lib, C, heads, H, W):
     ps = engine.ParamSet({k: v for k, v in sd.items()}, "cuda")
     bs = engine.BlockSpec(ps, "b.", C, heads)
     ps.finalize()
-    tape = engine.Tape()
+    tape = engine.Tape(save_hidden=save)   # save: keep hidden tensors; else recompute them in backward
     xd = x.cuda()
     y = engine.block_fwd(bs, xd, tape)
     _check("y", y, y64.detach())
@@ -83,3 +84,29 @@ def test_block_grad_accumulates(cuda_lib):
     y = engine.block_fwd(bs, x, tape)
     tape.backward(y, dy.clone())
     torch.testing.assert_close(ps.grad, 2 * once, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("save", [False, True])
+def test_shared_block_invoked_twice_on_one_tape(cuda_lib, save):
+    """y = blk(blk(x)) with ONE set of weights (as T_net's decoder modules are used by both passes)."""
+    from oracle import restormer_ref as R
+    from rcot_b200 import engine
+
+    g = torch.Generator().manual_seed(12)
+    C, heads = 96, 2
+    sd = _block_params(C, heads, g)
+    x = torch.randn(2, C, 8, 8, generator=g)
+    dy = torch.randn(2, C, 8, 8, generator=g)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    R.transformer_block(R.transformer_block(x64, sd64, "b.", heads), sd64, "b.", heads).backward(dy.double())
+    ps = engine.ParamSet(sd, "cuda")
+    bs = engine.BlockSpec(ps, "b.", C, heads)
+    ps.finalize()
+    tape = engine.Tape(save_hidden=save)
+    xd = x.cuda()
+    y = engine.block_fwd(bs, engine.block_fwd(bs, xd, tape), tape)
+    leaves = tape.backward(y, dy.cuda().clone())
+    _check("dx", tape.grad_of(leaves, xd), x64.grad)
+    for k in sd:
+        _check(k, ps.g[k], sd64[k].grad)
