@@ -13,18 +13,28 @@
 
 namespace rcot {
 
-constexpr int PK_THREADS = 256;
-constexpr int PK_STAGES = 2;
+constexpr int PK_PROD_WARPS = 16;
+constexpr int PK_PROD_THREADS = PK_PROD_WARPS * 32;
+constexpr int PK_THREADS = PK_PROD_THREADS + 32;   // + one MMA-issuing warp
+constexpr int PK_MAX_STAGES = 4;
+constexpr int PK_BT = 2;                           // B-operand row tasks per producer thread (BN <= 256)
 
+// Producer thread t (16 warps) owns k8 = t & 3 (8 consecutive pixels of the 32-pixel chunk), A row t >> 2
+// and B rows (t >> 2) + 128*j: four neighbouring lanes read 128 contiguous bytes of one channel row
+// (the padded LBO of the operand layout keeps the matching shared-memory stores conflict free).
+// The loads of chunk i+1 are issued into registers before chunk i is converted (bf16 hi/lo split)
+// and stored, so global latency overlaps the conversion; one MMA warp issues tcgen05.mma and hands
+// stages back through mbarriers; after the K loop the producer warps drain the TMEM accumulator
+// with fp32 atomics (split-K).
 template <int TERMS, bool GENERAL, bool LN>
-__global__ void __launch_bounds__(PK_THREADS)
+__global__ void __launch_bounds__(PK_THREADS, 1)
     pk_gemm_kernel(const rcot_pk_params p, const int BN, const int nt, const int cpi, const int per_cta,
-                   const int total_chunks, const uint32_t tmem_cols) {
+                   const int total_chunks, const int stages, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t empty_bar[PK_STAGES], done_bar;
+  __shared__ uint64_t full_bar[PK_MAX_STAGES], empty_bar[PK_MAX_STAGES], done_bar;
   __shared__ uint32_t tmem_base_s;
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt_i = blockIdx.x / nt, nt_i = blockIdx.x - mt_i * nt;
   const int m0 = mt_i * 128, n0 = nt_i * BN;
   const int g = blockIdx.z % p.groups;
@@ -33,12 +43,15 @@ __global__ void __launch_bounds__(PK_THREADS)
   const int KK = p.ks * p.ks;
   const int Ntot = (p.CB1 + p.CB2) * KK;
 
-  const uint32_t a_tile = 128 * KC * 2, b_tile = (uint32_t)BN * KC * 2;
+  const uint32_t a_tile = op_tile_bytes(128), b_tile = op_tile_bytes(BN);
   const uint32_t stage_bytes = TA * (a_tile + b_tile);
 
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   if (tid == 0) {
-    for (int s = 0; s < PK_STAGES; ++s) mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], PK_PROD_WARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
   }
@@ -46,128 +59,186 @@ __global__ void __launch_bounds__(PK_THREADS)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = make_idesc_bf16(128, BN);
 
   const int c_begin = blockIdx.y * per_cta;
   int c_end = c_begin + per_cta;
   if (c_end > total_chunks) c_end = total_chunks;
+  const int nchunks = c_end - c_begin;
 
-  for (int gc = c_begin; gc < c_end; ++gc) {
-    const int it = gc - c_begin;
-    const int s = it % PK_STAGES, use = it / PK_STAGES;
-    if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-    int b, q0;
-    if (p.per_image) {
-      b = bz;
-      q0 = gc * KC;
-    } else {
-      b = gc / cpi;
-      q0 = (gc - b * cpi) * KC;
+  if (warp < PK_PROD_WARPS) {
+    const int k8 = tid & 3, r0 = tid >> 2;   // 4 neighbouring lanes read 128 contiguous bytes of one row
+    const int nbt = (BN + 127) >> 7;          // B row tasks actually used (uniform)
+    struct Regs {
+      float a[8];
+      float b[PK_BT][8];
+      float2 st;                              // LayerNorm (mean, rstd) of pixel q0 + lane
+    };
+    // ---- everything that does not depend on the chunk is hoisted out of the K loop
+    const bool a_ok = (m0 + r0) < p.CA;
+    const float* a_row = p.a + (size_t)(g * p.CA + (a_ok ? m0 + r0 : 0)) * HWa + k8 * 8;
+    bool b_ok[PK_BT];
+    const float* b_row[PK_BT];
+    int64_t b_bstride[PK_BT];
+    float ga[PK_BT], be[PK_BT];
+    int b_cb[PK_BT], b_ky[PK_BT], b_kx[PK_BT];
+#pragma unroll
+    for (int j = 0; j < PK_BT; ++j) {
+      const int r = r0 + 128 * j, n = n0 + r;
+      b_ok[j] = (j < nbt) && (r < BN) && (n < Ntot);
+      const int cb = b_ok[j] ? n / KK : 0, rr = b_ok[j] ? n - cb * KK : 0;
+      b_cb[j] = cb;
+      b_ky[j] = rr / p.ks;
+      b_kx[j] = rr - b_ky[j] * p.ks;
+      const bool second = cb >= p.CB1;
+      b_row[j] = second ? p.b2 + (size_t)(cb - p.CB1) * HWb : p.b + (size_t)(g * p.CB1 + cb) * HWb;
+      b_bstride[j] = second ? p.b2_bs : p.b_bs;
+      ga[j] = (LN && b_ok[j]) ? __ldg(p.ln_gamma + n) : 0.f;
+      be[j] = (LN && b_ok[j]) ? __ldg(p.ln_beta + n) : 0.f;
     }
-    uint8_t* st = smem + (size_t)s * stage_bytes;
-    uint8_t* a_hi = st;
-    uint8_t* a_lo = st + a_tile;
-    uint8_t* b_hi = st + TA * a_tile;
-    uint8_t* b_lo = b_hi + b_tile;
-
-    // ---- A operand: rows = channels m0.., k = pixels q0..q0+31
-    const float* ab = p.a + (size_t)b * p.a_bs + (size_t)g * p.CA * HWa;
-    for (int task = tid; task < 128 * (KC / 8); task += PK_THREADS) {
-      const int r = task >> 2, k8 = task & 3;
-      const int m = m0 + r, q = q0 + k8 * 8;
-      float v[8];
-      if (m < p.CA && q + 8 <= HWa && !GENERAL) {
-        const float4* src = reinterpret_cast<const float4*>(ab + (size_t)m * HWa + q);
-        const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
-        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-        v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-      } else {
+    const bool all_full = (HWa % KC) == 0;    // every chunk has 32 valid pixels
+    auto ld8 = [&](float* v, const float* src) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+      v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    };
+    auto load = [&](Regs& R, int b, int q0) {
+      const int q = q0 + k8 * 8;
+      if (!GENERAL && all_full) {
+        // fast path: aligned 32-byte reads, no per-element predicates
+        if (a_ok) ld8(R.a, a_row + (size_t)b * p.a_bs + q0);
+        else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (m < p.CA && q + i < HWa) ? __ldg(ab + (size_t)m * HWa + q + i) : 0.f;
-      }
-      op_store8<TERMS>(a_hi, a_lo, r, k8, v);
-    }
-    // ---- B operand: rows = (cb, ky, kx) n0.., k = pixels
-    for (int task = tid; task < BN * (KC / 8); task += PK_THREADS) {
-      const int r = task >> 2, k8 = task & 3;
-      const int n = n0 + r, q = q0 + k8 * 8;
-      float v[8];
-      if (n >= Ntot) {
+          for (int i = 0; i < 8; ++i) R.a[i] = 0.f;
+        }
+        if (LN) R.st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWb + q0 + lane);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      } else if (!GENERAL) {
-        // 1x1: n is the channel; contiguous pixels (HW % 8 == 0 guaranteed by the launcher)
-        const float* sp = (n < p.CB1) ? p.b + (size_t)b * p.b_bs + (size_t)(g * p.CB1 + n) * HWb
-                                      : p.b2 + (size_t)b * p.b2_bs + (size_t)(n - p.CB1) * HWb;
-        if (q + 8 <= HWa) {
-          const float4* src = reinterpret_cast<const float4*>(sp + q);
-          const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
-          v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-          v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-          if (LN) {
-            const float4* stp = reinterpret_cast<const float4*>(p.ln_stats + ((size_t)b * HWb + q) * 2);
-            const float ga = __ldg(p.ln_gamma + n), be = __ldg(p.ln_beta + n);
+        for (int j = 0; j < PK_BT; ++j) {
+          if (b_ok[j]) ld8(R.b[j], b_row[j] + (size_t)b * b_bstride[j] + q);
+          else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 s2 = __ldg(stp + j);  // (mean, rstd) of two pixels
-              v[2 * j] = (v[2 * j] - s2.x) * s2.y * ga + be;
-              v[2 * j + 1] = (v[2 * j + 1] - s2.z) * s2.w * ga + be;
-            }
+            for (int i = 0; i < 8; ++i) R.b[j][i] = 0.f;
           }
+        }
+        return;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        R.a[i] = (a_ok && q + i < HWa) ? __ldg(a_row + (size_t)b * p.a_bs + q0 + i) : 0.f;
+      if (LN) {
+        const int ql = q0 + lane;
+        R.st = ql < HWa ? __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWb + ql)
+                        : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < PK_BT; ++j) {
+        const float* sp = b_row[j] + (size_t)b * b_bstride[j];
+        if (!b_ok[j]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) R.b[j][i] = 0.f;
+        } else if (!GENERAL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) R.b[j][i] = (q + i < HWa) ? __ldg(sp + q + i) : 0.f;
         } else {
+          int qy = q / p.Wa, qx = q - qy * p.Wa;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float x = 0.f;
             if (q + i < HWa) {
-              x = __ldg(sp + q + i);
-              if (LN) {
-                const float2 s2 = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWb + q + i);
-                x = (x - s2.x) * s2.y * __ldg(p.ln_gamma + n) + __ldg(p.ln_beta + n);
-              }
+              const int sy = qy * p.stride + b_ky[j] - p.pad, sx = qx * p.stride + b_kx[j] - p.pad;
+              if ((unsigned)sy < (unsigned)p.Hb && (unsigned)sx < (unsigned)p.Wb) x = __ldg(sp + sy * p.Wb + sx);
             }
-            v[i] = x;
-          }
-        }
-      } else {
-        const int cb = n / KK, rr = n - cb * KK;
-        const int ky = rr / p.ks, kx = rr - ky * p.ks;
-        const float* sp = (cb < p.CB1) ? p.b + (size_t)b * p.b_bs + (size_t)(g * p.CB1 + cb) * HWb
-                                       : p.b2 + (size_t)b * p.b2_bs + (size_t)(cb - p.CB1) * HWb;
-        int qy = q / p.Wa, qx = q - qy * p.Wa;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float x = 0.f;
-          if (q + i < HWa) {
-            const int sy = qy * p.stride + ky - p.pad, sx = qx * p.stride + kx - p.pad;
-            if ((unsigned)sy < (unsigned)p.Hb && (unsigned)sx < (unsigned)p.Wb) x = __ldg(sp + sy * p.Wb + sx);
-          }
-          v[i] = x;
-          if (++qx == p.Wa) {
-            qx = 0;
-            ++qy;
+            R.b[j][i] = x;
+            if (++qx == p.Wa) {
+              qx = 0;
+              ++qy;
+            }
           }
         }
       }
-      op_store8<TERMS>(b_hi, b_lo, r, k8, v);
+    };
+    // (image, first pixel) of the chunk being prefetched, advanced without divisions
+    int nb = p.per_image ? bz : c_begin / cpi;
+    int nq0 = (p.per_image ? c_begin : c_begin - nb * cpi) * KC;
+    Regs nxt;
+    if (nchunks > 0) load(nxt, nb, nq0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      Regs cur = nxt;
+      const int cq0 = nq0;
+      nq0 += KC;
+      if (!p.per_image && nq0 >= cpi * KC) {
+        nq0 = 0;
+        ++nb;
+      }
+      if (it + 1 < nchunks) load(nxt, nb, nq0);
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      uint8_t* a_hi = st;
+      uint8_t* a_lo = st + a_tile;
+      uint8_t* b_hi = st + TA * a_tile;
+      uint8_t* b_lo = b_hi + b_tile;
+      op_store8<TERMS>(a_hi, a_lo, r0, k8, cur.a);
+      float mu[8], rs[8];
+      if (LN) {
+        const int q = cq0 + k8 * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {   // statistics of this thread's 8 pixels, held by lanes k8*8+i
+          mu[i] = __shfl_sync(0xffffffffu, cur.st.x, k8 * 8 + i);
+          const float rv = __shfl_sync(0xffffffffu, cur.st.y, k8 * 8 + i);
+          rs[i] = (all_full || q + i < HWa) ? rv : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PK_BT; ++j) {
+        if (j >= nbt) break;
+        const int r = r0 + 128 * j;
+        if (r < BN) {
+          if (LN && b_ok[j]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur.b[j][i] = rs[i] != 0.f ? (cur.b[j][i] - mu[i]) * rs[i] * ga[j] + be[j] : 0.f;
+          }
+          op_store8<TERMS>(b_hi, b_lo, r, k8, cur.b[j]);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+      }
     }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+  } else {
+    // ---- MMA issuer warp
+    const uint32_t idesc = make_idesc_bf16(128, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      issue_stage<TERMS>(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), idesc, it == 0);
-      tc_commit(&empty_bar[s]);
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        issue_stage<TERMS>(tmem, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, it == 0);
+        tc_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+      }
     }
+    if (lane == 0 && nchunks > 0) tc_commit(&done_bar);
   }
-  if (c_end > c_begin) {
-    if (tid == 0) tc_commit(&done_bar);
+  if (warp < PK_PROD_WARPS && nchunks > 0) {
     mbar_wait(&done_bar, 0);
     tc_fence_after();
     // ---- epilogue: thread = row m (TMEM lane), the two warp groups split the columns
     const uint32_t lane_base = tmem_lane_base(tmem);
-    const int m = m0 + (warp & 3) * 32 + (tid & 31);
-    const int half = warp >> 2;
+    const int m = m0 + (warp & 3) * 32 + lane;
+    const int part = warp >> 2;               // 4 column parts
     const int ncols8 = BN / 8;
-    const int c8_begin = half ? ncols8 / 2 : 0, c8_end = half ? ncols8 : ncols8 / 2;
+    const int c8_begin = (ncols8 * part) / 4, c8_end = (ncols8 * (part + 1)) / 4;
     float* ob = p.out + (size_t)g * p.out_gs + (p.per_image ? (size_t)bz * p.out_bs : 0);
     for (int c8 = c8_begin; c8 < c8_end; ++c8) {
       if (n0 + c8 * 8 >= Ntot) break;
@@ -206,11 +277,14 @@ static int launch_pk(const rcot_pk_params& p, cudaStream_t stream) {
   int per_cta = cdiv(total_chunks, S);
   S = cdiv(total_chunks, per_cta);
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const size_t smem = (size_t)PK_STAGES * TA * (128 * KC * 2 + (size_t)BN * KC * 2);
+  const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(BN));
+  int stages = (int)((190 * 1024) / stage_bytes);
+  if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
+  const size_t smem = stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pk_gemm_kernel<TERMS, GENERAL, LN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
     if (e != cudaSuccess) {
       set_error("pk_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return RCOT_ERR_CUDA;
@@ -220,7 +294,7 @@ static int launch_pk(const rcot_pk_params& p, cudaStream_t stream) {
   RCOT_REQUIRE(zdim <= 65535 && S <= 65535, "pk_gemm: grid too large");
   dim3 grid(mt * nt, S, zdim);
   pk_gemm_kernel<TERMS, GENERAL, LN><<<grid, PK_THREADS, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks,
-                                                                        tmem_cols_pow2(BN));
+                                                                        stages, tmem_cols_pow2(BN));
   return check_launch("pk_gemm");
 }
 

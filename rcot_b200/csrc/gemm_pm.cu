@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HWr = p.Hr * p.Wr, HWs = p.Hs * p.Ws;
   const int BN = g.BN, nk = g.nk, stages = g.stages;
-  const uint32_t a_tile = 128 * KC * 2;
-  const uint32_t b_tile = (uint32_t)BN * KC * 2;
+  const uint32_t a_tile = op_tile_bytes(128);
+  const uint32_t b_tile = op_tile_bytes(BN);
   const uint32_t stage_bytes = TA * (a_tile + b_tile);
   const int total_tiles = g.tiles_m * g.passes;
 
@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         }
       }
     };
-    uint32_t it = 0;
+    int ps_ = 0;
+    uint32_t pph_ = 0;
     int t = blockIdx.x, c = 0;
     TileCtx nctx = setup(t < total_tiles ? t : 0);
     float nxt[16];
@@ -197,9 +198,12 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       }
       if (t < total_tiles) load16(nxt, nctx, c);
       // ---- convert + store item (cur, cc)
-      const int s = it % stages;
-      const uint32_t ph = (it / stages) & 1;
-      ++it;
+      const int s = ps_;
+      const uint32_t ph = pph_;
+      if (++ps_ == stages) {
+        ps_ = 0;
+        pph_ ^= 1;
+      }
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* st = smem + (size_t)s * stage_bytes;
       if (tid == 0) {
@@ -225,15 +229,15 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
   } else if (warp == PM_PROD_WARPS) {
     // =========================================================== MMA issuer (whole warp waits, lane 0 issues)
     const uint32_t idesc = make_idesc_bf16(128, BN);
-    uint32_t it = 0, tcount = 0;
+    uint32_t tcount = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&acc_empty[buf], aph ^ 1);
       tc_fence_after();
       const uint32_t d = tmem + buf * BN;
-      for (int c = 0; c < nk; ++c, ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
+      for (int c = 0; c < nk; ++c) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
@@ -242,6 +246,10 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
           tc_commit(&empty_bar[s]);
         }
         __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
       if (lane == 0) tc_commit(&acc_full[buf]);
       __syncwarp();
@@ -364,7 +372,7 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   g.BN = pl.BN;
   g.passes = pl.passes;
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const size_t stage_bytes = (size_t)TA * (128 * KC * 2 + (size_t)pl.BN * KC * 2);
+  const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(pl.BN));
   const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
   g.c1_aligned = (p.C2 == 0 || p.C1 % 16 == 0) ? 1 : 0;
   int stages = (int)((196 * 1024) / stage_bytes);

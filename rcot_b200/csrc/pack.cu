@@ -35,7 +35,7 @@ __global__ void pack_weights_kernel(const rcot_pack_desc* __restrict__ descs) {
 extern "C" size_t rcot_packed_bytes(int N, int K) {
   using namespace rcot;
   NPlan pl = make_nplan(N);
-  return (size_t)pl.passes * pl.BN * cdiv(K, KC) * KC * 2 * 2;
+  return (size_t)pl.passes * cdiv(K, KC) * 2 * op_tile_bytes(pl.BN);
 }
 
 extern "C" int rcot_pack_weights(const rcot_pack_desc* descs, int n, size_t max_elems, rcot_stream_t stream_) {

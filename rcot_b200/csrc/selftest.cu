@@ -11,8 +11,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
                                                           float* __restrict__ D, int N, int K) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int STAGES = 2;
-  constexpr int A_TILE = 128 * KC * 2;  // bytes of one bf16 A tile
-  constexpr int B_TILE = 256 * KC * 2;
+  constexpr int A_TILE = op_tile_bytes(128);  // bytes of one bf16 A tile
+  constexpr int B_TILE = op_tile_bytes(256);
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t done_bar;
@@ -83,7 +83,7 @@ extern "C" int rcot_selftest_tc(const float* A, const float* B, float* D, int N,
   RCOT_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "selftest: N must be a multiple of 16 in [16,256], got %d", N);
   RCOT_REQUIRE(K >= KC && K % KC == 0, "selftest: K must be a positive multiple of %d, got %d", KC, K);
   RCOT_REQUIRE(terms == 1 || terms == 3, "selftest: terms must be 1 or 3");
-  const int smem = 2 * (2 * 128 * KC * 2 + 2 * 256 * KC * 2);
+  const int smem = 2 * (2 * op_tile_bytes(128) + 2 * op_tile_bytes(256));
   if (terms == 3) {
     cudaFuncSetAttribute(tc_selftest_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     tc_selftest_kernel<3><<<1, 128, smem, stream>>>(A, B, D, N, K);

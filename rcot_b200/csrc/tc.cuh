@@ -5,7 +5,7 @@
 // Operand layout (shared memory, "core matrix" = 8 rows x 16 bytes, stored as 128
 // contiguous bytes): element (row r, k) of a [rows x KC] bf16 tile lives at
 //     (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2        bytes
-// with LBO = 128 (core matrices adjacent in K are contiguous) and SBO = (KC/8)*128.
+// with LBO = 160 (core matrix + 32 B pad, see OP_LBO) and SBO = (KC/8)*LBO.
 // Threads produce the operands (fp32 -> bf16 hi [+ lo]), so no TMA swizzle mode has
 // to be matched; weights are pre-packed in this layout in HBM and brought in with
 // cp.async.bulk (UBLKCP).
@@ -200,8 +200,12 @@ __device__ __forceinline__ uint32_t tmem_lane_base(uint32_t tmem_base) {
 
 // ------------------------------------------------------------------ operand packing
 constexpr int KC = 32;                 // K elements per pipeline stage
-constexpr uint32_t OP_LBO = 128;       // bytes between core matrices adjacent in K
-constexpr uint32_t OP_SBO = (KC / 8) * 128;  // bytes between 8-row groups
+// LBO = 160 (a 128-byte core matrix + 32 bytes of padding): with 128 the four K-adjacent core matrices of
+// a row group start in the same shared-memory banks, and a quarter-warp that stores {2 rows x 4 k-groups}
+// (the coalescing-friendly mapping of the pixel-as-K kernel) would hit 4-way bank conflicts.
+constexpr uint32_t OP_LBO = 160;                 // bytes between core matrices adjacent in K
+constexpr uint32_t OP_SBO = (KC / 8) * OP_LBO;   // bytes between 8-row groups
+__host__ __device__ constexpr uint32_t op_tile_bytes(int rows) { return (uint32_t)(rows / 8) * OP_SBO; }
 
 __device__ __host__ inline uint32_t op_offset(int row, int k) {  // k in [0,KC)
   return (uint32_t)(row >> 3) * OP_SBO + (uint32_t)(k >> 3) * OP_LBO + (uint32_t)(row & 7) * 16u +
@@ -216,7 +220,7 @@ __device__ __host__ inline size_t packed_offset(int N, int K, int n, int k, int 
   const int nk = (K + KC - 1) / KC;
   const int pass = n / BN, np = n - pass * BN;
   const int kc = k / KC, kp = k - kc * KC;
-  const size_t tile = (size_t)BN * KC * 2;
+  const size_t tile = op_tile_bytes(BN);
   return (((size_t)pass * nk + kc) * 2 + term) * tile + op_offset(np, kp);
 }
 
