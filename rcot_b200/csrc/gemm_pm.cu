@@ -181,22 +181,50 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
     };
     int ps_ = 0;
     uint32_t pph_ = 0;
-    int t = blockIdx.x, c = 0;
-    TileCtx nctx = setup(t < total_tiles ? t : 0);
-    float nxt[16];
-    if (t < total_tiles) load16(nxt, nctx, 0);
-    while (t < total_tiles) {
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = nxt[i];
-      const TileCtx cur = nctx;
-      const int cc = c;
+    // The loads of items j+1 and j+2 are in flight while item j is converted (two-deep register prefetch:
+    // 2 x 16 loads x 256 threads = 32 KB outstanding per SM).
+    int t = blockIdx.x, c = 0;                          // walker: the next item to issue loads for
+    TileCtx xw = setup(t < total_tiles ? t : 0);
+    auto step_walker = [&]() {
       if (++c == nk) {
         c = 0;
         t += gridDim.x;
-        if (t < total_tiles) nctx = setup(t);
+        if (t < total_tiles) xw = setup(t);
       }
-      if (t < total_tiles) load16(nxt, nctx, c);
+    };
+    float n1[16], n2[16];
+    TileCtx x1 = xw, x2 = xw;
+    int c1 = 0, c2 = 0;
+    bool ok1 = t < total_tiles, ok2 = false;
+    if (ok1) {
+      load16(n1, xw, c);
+      step_walker();
+      ok2 = t < total_tiles;
+      if (ok2) {
+        x2 = xw;
+        c2 = c;
+        load16(n2, xw, c);
+        step_walker();
+      }
+    }
+    while (ok1) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = n1[i];
+      const TileCtx cur = x1;
+      const int cc = c1;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) n1[i] = n2[i];
+      x1 = x2;
+      c1 = c2;
+      ok1 = ok2;
+      ok2 = ok2 && (t < total_tiles);
+      if (ok2) {
+        x2 = xw;
+        c2 = c;
+        load16(n2, xw, c);
+        step_walker();
+      }
       // ---- convert + store item (cur, cc)
       const int s = ps_;
       const uint32_t ph = pph_;
