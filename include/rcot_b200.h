@@ -153,6 +153,10 @@ int rcot_dwconv3x3(const rcot_dw_params* p, rcot_stream_t stream);
 int rcot_dwconv3x3_wgrad(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, float* dw, int B,
                          int Cn, int H, int W, rcot_stream_t stream);
 
+/* both halves of the depthwise backward in one pass: din = dw^T(dout), dw += corr(in, dout) */
+int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w, float* din,
+                       int64_t din_bs, float* dw, int B, int Cn, int H, int W, rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- MDTA small-matrix steps
  * Net_Restormer.py:39-49: normalize(q), normalize(k), softmax(q k^T * temperature), attn @ v,
  * project_out -- folded into the per-image matrix M = W_out * blockdiag(A). */

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256)
 // so the per-channel sums over pixels are warp shuffles into shared slots no other warp touches; the
 // per-pixel sums over channels are combined across the 8 warps through shared memory.  A CTA walks
 // `groups` consecutive 32-pixel groups before it flushes its channel sums with one atomicAdd each.
+template <int NCH>   // NCH > 0: C == 8*NCH and the (dz, xhat) values of the first sweep stay in registers
 __global__ void __launch_bounds__(256)
     ln_bwd_kernel(const float* __restrict__ dz, int64_t dz_bs, const float* __restrict__ x, int64_t x_bs,
                   const float2* __restrict__ stats, const float* __restrict__ gamma, const float* dy, int64_t dy_bs,
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256)
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
+  constexpr int R = NCH > 0 ? NCH : 1;
   for (int gi = 0; gi < groups; ++gi) {
     const int p = (blockIdx.x * groups + gi) * 32 + lane;
     const bool valid = p < HW;
@@ -67,20 +69,45 @@ __global__ void __launch_bounds__(256)
       rstd = st.y;
     }
     float sg = 0.f, sgx = 0.f;
-    for (int c = wy; c < C; c += 8) {
-      float d = 0.f, xh = 0.f;
-      if (valid) {
-        d = __ldg(dzp + (size_t)c * HW);
-        xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+    float rd[R], rx[R];
+    if (NCH > 0) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {   // all loads first: 2*NCH independent requests per thread
+        const int c = wy + 8 * k;
+        rd[k] = valid ? __ldg(dzp + (size_t)c * HW) : 0.f;
+        rx[k] = valid ? __ldg(xp + (size_t)c * HW) : 0.f;
       }
-      const float g = d * __ldg(gamma + c);
-      sg += g;
-      sgx = fmaf(g, xh, sgx);
-      const float wg = warp_sum(d * xh);
-      const float wb = warp_sum(d);
-      if (lane == 0) {
-        sacc[c] += wg;
-        sacc[C + c] += wb;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int c = wy + 8 * k;
+        const float xh = valid ? (rx[k] - mu) * rstd : 0.f;
+        rx[k] = xh;
+        const float g = rd[k] * __ldg(gamma + c);
+        sg += g;
+        sgx = fmaf(g, xh, sgx);
+        const float wg = warp_sum(rd[k] * xh);
+        const float wb = warp_sum(rd[k]);
+        if (lane == 0) {
+          sacc[c] += wg;
+          sacc[C + c] += wb;
+        }
+      }
+    } else {
+      for (int c = wy; c < C; c += 8) {
+        float d = 0.f, xh = 0.f;
+        if (valid) {
+          d = __ldg(dzp + (size_t)c * HW);
+          xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+        }
+        const float g = d * __ldg(gamma + c);
+        sg += g;
+        sgx = fmaf(g, xh, sgx);
+        const float wg = warp_sum(d * xh);
+        const float wb = warp_sum(d);
+        if (lane == 0) {
+          sacc[c] += wg;
+          sacc[C + c] += wb;
+        }
       }
     }
     spix[wy * 32 + lane] = sg;
@@ -98,12 +125,23 @@ __global__ void __launch_bounds__(256)
     if (valid) {
       const float* dyp = dy ? dy + (size_t)b * dy_bs + p : nullptr;
       float* dxp = dx + (size_t)b * dx_bs + p;
-      for (int c = wy; c < C; c += 8) {
-        const float d = __ldg(dzp + (size_t)c * HW);
-        const float xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
-        float r = rstd * (d * __ldg(gamma + c) - mg - xh * mgx);
-        if (dyp) r += dyp[(size_t)c * HW];
-        dxp[(size_t)c * HW] = r;
+      if (NCH > 0) {
+        float ry[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + 8 * k) * HW] : 0.f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int c = wy + 8 * k;
+          dxp[(size_t)c * HW] = rstd * (rd[k] * __ldg(gamma + c) - mg - rx[k] * mgx) + ry[k];
+        }
+      } else {
+        for (int c = wy; c < C; c += 8) {
+          const float d = __ldg(dzp + (size_t)c * HW);
+          const float xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
+          float r = rstd * (d * __ldg(gamma + c) - mg - xh * mgx);
+          if (dyp) r += dyp[(size_t)c * HW];
+          dxp[(size_t)c * HW] = r;
+        }
       }
     }
     __syncthreads();
@@ -268,6 +306,65 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Backward of the depthwise conv in ONE pass over its two inputs:
+//   din = dw^T(dout)  (same stencil with flipped taps)   and   dW[ch,k] += sum dout * in(shifted by k).
+// grid = (chunks, Cn): a CTA owns one channel and strides over (image, quad) pairs.
+__global__ void __launch_bounds__(256)
+    dw_bwd_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
+                  const float* __restrict__ w, float* __restrict__ din, int64_t din_bs, float* __restrict__ dw, int B,
+                  int H, int W) {
+  const int HW = H * W, ch = blockIdx.y, qpp = HW / 4;
+  const long total = (long)B * qpp;
+  float wf[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wf[i] = __ldg(w + ch * 9 + 8 - i);   // flipped taps
+  float acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / qpp), pix = (int)(e - (long)b * qpp) * 4;
+    const int y = pix / W, x0 = pix - y * W;
+    const float* dplane = dout + (size_t)b * dout_bs + (size_t)ch * HW;
+    const float* iplane = in + (size_t)b * in_bs + (size_t)ch * HW;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const Row6 r = load_row6(dplane, y + ky - 1, x0, H, W);
+      if (ky == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = r.v[j + 1];
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf(r.v[j + kx], wf[ky * 3 + kx], o[j]);
+    }
+    *reinterpret_cast<float4*>(din + (size_t)b * din_bs + (size_t)ch * HW + pix) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const Row6 r = load_row6(iplane, y + ky - 1, x0, H, W);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[ky * 3 + kx] = fmaf(d[j], r.v[j + kx], acc[ky * 3 + kx]);
+    }
+  }
+  __shared__ float red[9][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) red[i][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += red[threadIdx.x][k];
+    atomicAdd(dw + ch * 9 + threadIdx.x, s);
+  }
+}
+
 // ------------------------------------------------------------------ pixel (un)shuffle, r = 2
 // inverse=0 (PixelShuffle):   out[b, c, 2y+i, 2x+j] = in[b, 4c+2i+j, y, x]     in: [4C,H,W]  out: [C,2H,2W]
 // inverse=1 (PixelUnshuffle): out[b, 4c+2i+j, y, x] = in[b, c, 2y+i, 2x+j]     in: [C,2H,2W] out: [4C,H,W]
@@ -349,9 +446,16 @@ extern "C" int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64
   if (groups < 1) groups = 1;
   if (groups > 8) groups = 8;
   dim3 grid(cdiv(pg, groups), B);
-  ln_bwd_kernel<<<grid, 256, (2 * C + 512) * sizeof(float), (cudaStream_t)st>>>(
-      dz, dz_bs, x, x_bs, reinterpret_cast<const float2*>(stats), gamma, dy, dy_bs, dx, dx_bs, dgamma, dbeta, C, HW,
-      groups);
+  const size_t sm = (2 * C + 512) * sizeof(float);
+  const float2* st2 = reinterpret_cast<const float2*>(stats);
+#define LNB(NCH)                                                                                                  \
+  ln_bwd_kernel<NCH><<<grid, 256, sm, (cudaStream_t)st>>>(dz, dz_bs, x, x_bs, st2, gamma, dy, dy_bs, dx, dx_bs, \
+                                                          dgamma, dbeta, C, HW, groups)
+  if (C == 48) LNB(6);
+  else if (C == 96) LNB(12);
+  else if (C == 192) LNB(24);
+  else LNB(0);
+#undef LNB
   return check_launch("ln_bwd");
 }
 
@@ -388,6 +492,24 @@ extern "C" int rcot_dwconv3x3_wgrad(const float* in, int64_t in_bs, const float*
   dim3 grid(chunks, Cn);
   dw_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(in, in_bs, dout, dout_bs, dw, B, H, W);
   return check_launch("dwconv3x3_wgrad");
+}
+
+extern "C" int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w,
+                                  float* din, int64_t din_bs, float* dw, int B, int Cn, int H, int W,
+                                  rcot_stream_t st) {
+  RCOT_REQUIRE(in && dout && w && din && dw && B > 0 && Cn > 0 && Cn <= 65535 && H > 0 && W > 0,
+               "dwconv3x3_bwd: bad arguments");
+  RCOT_REQUIRE(W % 4 == 0 && in_bs % 4 == 0 && dout_bs % 4 == 0 && din_bs % 4 == 0,
+               "dwconv3x3_bwd: width/strides must be multiples of 4");
+  long total = (long)B * H * W / 4;
+  // enough CTAs per channel to fill the machine, at least ~4 quads per thread
+  long want = (148L * 8 + Cn - 1) / Cn;
+  long maxc = (total + 256 * 4 - 1) / (256 * 4);
+  int chunks = (int)(want < maxc ? want : maxc);
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, Cn);
+  dw_bwd_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, B, H, W);
+  return check_launch("dwconv3x3_bwd");
 }
 
 extern "C" int rcot_pixel_shuffle(const float* in, int64_t in_bs, float* out, int64_t out_bs, int B, int C, int H,

@@ -231,9 +231,7 @@ def mdta_bwd(bs: BlockSpec, x, dy, norm_name, residual, ctx):
     dqkv = torch.empty_like(qkv)
     ops.pm_gemm(qkv[:, :2 * C], sc.w12().data_ptr(), 2 * C, wpack_bs=sc.pb12, out=dqkv, out_coff=0)
     ops.pm_gemm(dy, st.MTpack.data_ptr(), C, wpack_bs=sc.pb, out=dqkv, out_coff=2 * C)
-    dw = ps.p[a + "qkv_dwconv.weight"]
-    dpre = ops.dwconv(dqkv, dw, flip=True)
-    ops.dwconv_wgrad(pre, dqkv, ps.g[a + "qkv_dwconv.weight"])
+    dpre = ops.dwconv_bwd(pre, dqkv, ps.p[a + "qkv_dwconv.weight"], ps.g[a + "qkv_dwconv.weight"])
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
     ops.pk_gemm(dpre, x, ps.g[a + "qkv.weight"], ldo=C, ln=ln)
     dz = ops.pm_gemm(dpre, ps.pack(a + "qkv.weight", "dgrad"), C, residual=None if norm_name or not residual else dy)
@@ -273,8 +271,7 @@ def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual, kept=None):
     dab = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=2, dg=dg, g_out=g, out=torch.empty_like(u))
     ops.pk_gemm(dy, g, ps.g[f + "project_out.weight"], ldo=hid)
     del g, dg
-    du = ops.dwconv(dab, ps.p[f + "dwconv.weight"], flip=True)
-    ops.dwconv_wgrad(u, dab, ps.g[f + "dwconv.weight"])
+    du = ops.dwconv_bwd(u, dab, ps.p[f + "dwconv.weight"], ps.g[f + "dwconv.weight"])
     del dab, u
     ops.pk_gemm(du, x, ps.g[f + "project_in.weight"], ldo=C, ln=ln)
     dz = ops.pm_gemm(du, ps.pack(f + "project_in.weight", "dgrad"), C,

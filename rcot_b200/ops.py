@@ -284,6 +284,17 @@ def dwconv_wgrad(x, dout, dw):
     return dw
 
 
+def dwconv_bwd(x, dout, w, dw):
+    """din = dw^T(dout); dw += corr(x, dout)  (x = the depthwise conv's forward input)."""
+    B, Cn, H, W = x.shape
+    din = torch.empty_like(dout)
+    _lib.check(L().rcot_dwconv3x3_bwd(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(dout),
+                                      C.c_int64(_img_view(dout, "dout")), _ptr(_f32(w)), _ptr(din),
+                                      C.c_int64(_img_view(din, "din")), _ptr(_f32(dw)), B, Cn, H, W, _stream()),
+               "dwconv3x3_bwd")
+    return din
+
+
 # ------------------------------------------------------------------ MDTA small-matrix steps
 def attn_fwd(G, sumsq, temperature, w_out, A, Gt, Mpack, MTpack, B, Cc, heads):
     p = AttnParams()
@@ -470,6 +481,7 @@ ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
 ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)
 dwconv = _instrument("dwconv", lambda a, k, r: _nb(a[0], r, k.get("dg"), k.get("g_out")))(dwconv)
 dwconv_wgrad = _instrument("dwconv_wgrad", lambda a, k, r: _nb(a[0], a[1]))(dwconv_wgrad)
+dwconv_bwd = _instrument("dwconv_bwd", lambda a, k, r: _nb(a[0], a[1], r))(dwconv_bwd)
 attn_fwd = _instrument("attn_fwd", lambda a, k, r: _nb(a[0], a[3]) * 2)(attn_fwd)
 attn_bwd = _instrument("attn_bwd", lambda a, k, r: _nb(a[0], a[3]) * 3)(attn_bwd)
 pixel_shuffle = _instrument("pixel_shuffle", lambda a, k, r: _nb(a[0], a[0]))(pixel_shuffle)

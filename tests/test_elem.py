@@ -145,3 +145,20 @@ def test_pixel_shuffle_axpby(cuda_lib):
     al = torch.rand(2, generator=g)
     torch.testing.assert_close(ops.axpby(xd, y.cuda(), a_vec=al.cuda()).cpu(),
                                al.view(2, 1, 1, 1) * x + (1 - al.view(2, 1, 1, 1)) * y)
+
+
+def test_dwconv_bwd_fused(cuda_lib):
+    """din and dW of the depthwise conv from one kernel vs autograd."""
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(16)
+    B, Cn, H, W = 3, 37, 10, 16
+    x = torch.randn(B, Cn, H, W, generator=g)
+    w = torch.randn(Cn, 1, 3, 3, generator=g) / 3
+    dout = torch.randn(B, Cn, H, W, generator=g)
+    x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    F.conv2d(x64, w64, padding=1, groups=Cn).backward(dout.double())
+    prev = torch.randn(Cn, 1, 3, 3, generator=g)
+    dw = prev.cuda().clone()
+    din = ops.dwconv_bwd(x.cuda(), dout.cuda(), w.cuda(), dw)
+    _close("din", din, x64.grad)
+    _close("dw", dw, prev.double() + w64.grad)
