@@ -245,7 +245,14 @@ def run_b200(args):
     # ---- per-kernel CUDA-event timing of the same step (one extra step, outside the timed regions)
     roof, kernels = None, None
     peak, peak_src = peaks()
+    phases = None
     if not args.no_profile:
+        # phase breakdown of one more step (events only at 7 section boundaries)
+        step.timing = []
+        resident_step(0)
+        torch.cuda.synchronize()
+        phases = {k: round(v, 3) for k, v in step.sections_ms().items()}
+        step.timing = None
         ops.PROF = ops.Profiler()
         resident_step(0)
         summ = ops.PROF.summary()
@@ -278,6 +285,15 @@ def run_b200(args):
     if roof:
         line["roofline"] = roof
         line["kernels"] = kernels
+        line["phases_ms"] = phases
+        # the fused MDTA+GDFN target of SURVEY 8(d): 13*B*C*H*W*4 + 3W bytes per block fwd+bwd, summed over the
+        # 102 block calls, against the measured T_net forward+backward time (which also holds the 26 glue convs)
+        tb = phases["T_forward"] + phases["T_backward"]
+        ab = block_algorithmic_bytes(B, P)
+        line["roofline_blocks"] = {"bound": "hbm", "what": "T_net forward + backward (102 MDTA+GDFN blocks + glue), "
+                                   "algorithmic bytes of the FUSED block target (SURVEY 8d)", "bytes": ab, "ms": round(tb, 3),
+                                   "achieved": ab / 1e9 / (tb / 1e3), "peak": peak, "unit": "GB/s",
+                                   "frac": ab / 1e9 / (tb / 1e3) / peak}
     if not args.no_cpu_baseline and world == 1:
         try:
             rate, cores, done = cpu_reference_rate(P, 2, 1, 1, budget_s=60.0)

@@ -44,7 +44,7 @@ typedef struct {
   void* dst;
   int32_t N, K;
   int32_t R, s_kouter, s_n;
-  int32_t reserved;
+  int32_t s_kinner;     /* stride of (k % R); 0 means 1 */
 } rcot_pack_desc;
 
 size_t rcot_packed_bytes(int N, int K);
@@ -85,8 +85,9 @@ typedef struct {
   int64_t mask_bs;
   const float* residual; /* same indexing as out (without coff): result += residual */
   int64_t res_bs;
-  int32_t debug;        /* bring-up only: 1 skip gather loads, 2 skip epilogue stores, 4 skip MMA issue */
-  int32_t reserved;
+  int32_t debug;        /* unused (bring-up knobs) */
+  int32_t tap_major;    /* ks > 1: K is ordered (ky, kx, channel); needs C1 % 32 == 0 and no concat: a K-chunk
+                           is 32 channels at ONE tap, so the gather is a strided read like the 1x1 case */
 } rcot_pm_params;
 
 int rcot_pm_gemm(const rcot_pm_params* p, rcot_stream_t stream);

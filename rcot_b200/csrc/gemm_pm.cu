@@ -136,6 +136,39 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         }
         return;
       }
+      if (p.tap_major) {
+        // K = (ky, kx, channel): this chunk is 32 channels at one tap -> one bounds test, strided reads
+        const int cpt = p.C1 >> 5;                    // chunks per tap
+        const int tap = c / cpt;
+        const int ch0 = (c - tap * cpt) * KC + khalf * 16;
+        const int ky = tap / KS, kx = tap - ky * KS;
+        int sy, sx;
+        bool ok = x.valid;
+        if (MODE == 0) {
+          sy = x.ry + ky;
+          sx = x.rx + kx;
+        } else {
+          const int ty = x.ry - ky, tx = x.rx - kx;
+          if (p.stride == 1) {
+            sy = ty;
+            sx = tx;
+          } else {
+            sy = ty >> 1;
+            sx = tx >> 1;
+            ok = ok && (((ty | tx) & 1) == 0);
+          }
+        }
+        ok = ok && ((unsigned)sy < (unsigned)p.Hs) && ((unsigned)sx < (unsigned)p.Ws);
+        if (ok) {
+          const float* sp = x.b1 + (size_t)ch0 * HWs + sy * p.Ws + sx;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(sp + (size_t)i * HWs);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        return;
+      }
       // general conv geometry: decompose k0 once, then step (ch, ky, kx)
       constexpr int KK = KS * KS;
       int ch = k0 / KK;
@@ -455,6 +488,8 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
   if (p.ks == 1)
     RCOT_REQUIRE(p.stride == 1 && p.pad == 0 && p.Hs == p.Hr && p.Ws == p.Wr, "pm_gemm: 1x1 needs stride 1, pad 0");
   RCOT_REQUIRE(p.stride == 1 || p.stride == 2, "pm_gemm: stride must be 1 or 2");
+  if (p.tap_major)
+    RCOT_REQUIRE(p.ks > 1 && p.C2 == 0 && p.C1 % 32 == 0, "pm_gemm: tap_major needs ks > 1, no concat, C1 %% 32 == 0");
 #define PM_DISPATCH(KS, MODE, LN)                                           \
   return (p.terms == 3) ? launch_pm<KS, MODE, 3, LN>(p, stream) : launch_pm<KS, MODE, 1, LN>(p, stream)
   switch (p.ks) {

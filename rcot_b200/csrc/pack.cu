@@ -21,7 +21,8 @@ __global__ void pack_weights_kernel(const rcot_pack_desc* __restrict__ descs) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(e / Kp), k = (int)(e - (size_t)n * Kp);   // n, k in the padded index space
     float w = 0.f;
-    if (n < d.N && k < d.K) w = d.src[(size_t)(k / d.R) * d.s_kouter + (k % d.R) + (size_t)n * d.s_n];
+    if (n < d.N && k < d.K)
+      w = d.src[(size_t)(k / d.R) * d.s_kouter + (size_t)(k % d.R) * (d.s_kinner ? d.s_kinner : 1) + (size_t)n * d.s_n];
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
     // padded rows of the last pass: n may exceed N but stays inside the padded image

@@ -319,22 +319,26 @@ class ConvSpec:
         self.ps, self.name, self.ks, self.pad = ps, name, ks, pad
         w = ps.p[name]
         self.Cout, self.Cin = w.shape[0], w.shape[1]
-        ps.add_pack(name, "fwd")
+        # (the two 1x1 convs that take a concatenated input keep the channel-major order)
+        self.kf = ops.conv_pack_kind(w, False, concat=name.startswith("reduce_chan"))
+        self.kd = ops.conv_pack_kind(w, True)
+        ps.add_pack(name, self.kf)
         if need_dgrad:
-            ps.add_pack(name, "dgrad")
+            ps.add_pack(name, self.kd)
 
 
 def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True, need_res_grad=True):
     """Dense conv (stride 1, no bias), optional concat input [x, x2] and residual epilogue."""
     ps = cs.ps
-    y = ops.pm_gemm(x, ps.pack(cs.name, "fwd"), cs.Cout, ks=cs.ks, pad=cs.pad, x2=x2, residual=residual)
+    y = ops.pm_gemm(x, ps.pack(cs.name, cs.kf), cs.Cout, ks=cs.ks, pad=cs.pad, x2=x2, residual=residual,
+                    tap_major=cs.kf.endswith("_tap"))
     if tape is not None and tape.enabled:
         def bwd(dy):
             Cin = cs.Cin
             ops.pk_gemm(dy, x, ps.g[cs.name].view(cs.Cout, -1), ldo=Cin * cs.ks * cs.ks, ks=cs.ks, pad=cs.pad, b2=x2)
             if need_dx:
-                dx = ops.pm_gemm(dy, ps.pack(cs.name, "dgrad"), Cin, ks=cs.ks, pad=cs.pad, mode=1,
-                                 out_hw=(x.shape[2], x.shape[3]))
+                dx = ops.pm_gemm(dy, ps.pack(cs.name, cs.kd), Cin, ks=cs.ks, pad=cs.pad, mode=1,
+                                 out_hw=(x.shape[2], x.shape[3]), tap_major=cs.kd.endswith("_tap"))
                 if x2 is None:
                     tape.add_grad(x, dx)
                 else:

@@ -35,9 +35,13 @@ class FnetProgram:
         self.P = patch_size
         self.ps = ParamSet(named_params, device)
         self.grad_names = set(named_params)
+        self.kf, self.kd = {}, {}
         for idx, *_ in CONVS:
-            self.ps.add_pack(f"features.{idx}.weight", "fwd")
-            self.ps.add_pack(f"features.{idx}.weight", "dgrad")
+            n = f"features.{idx}.weight"
+            self.kf[idx] = ops.conv_pack_kind(self.ps.p[n], False)
+            self.kd[idx] = ops.conv_pack_kind(self.ps.p[n], True)
+            self.ps.add_pack(n, self.kf[idx])
+            self.ps.add_pack(n, self.kd[idx])
         self.ps.finalize()
         # everything except fc2.bias (last tensor): the range the GP optimizer step covers
         self.n_without_fc2_bias = self.ps.offsets["fc2.bias"]
@@ -59,11 +63,12 @@ class FnetProgram:
         for li, (idx, cin, cout, k, s, p, has_b) in enumerate(CONVS):
             w = f"features.{idx}."
             if masks is None:
-                t = ops.pm_gemm(t, ps.pack(w + "weight", "fwd"), cout, ks=k, stride=s, pad=p,
-                                bias=ps.p[w + "bias"] if has_b else None, act=True, slope=SLOPE)
+                t = ops.pm_gemm(t, ps.pack(w + "weight", self.kf[idx]), cout, ks=k, stride=s, pad=p,
+                                bias=ps.p[w + "bias"] if has_b else None, act=True, slope=SLOPE,
+                                tap_major=self.kf[idx].endswith("_tap"))
             else:
-                t = ops.pm_gemm(t, ps.pack(w + "weight", "fwd"), cout, ks=k, stride=s, pad=p, mask_y=masks[li + 1],
-                                slope=SLOPE)
+                t = ops.pm_gemm(t, ps.pack(w + "weight", self.kf[idx]), cout, ks=k, stride=s, pad=p,
+                                mask_y=masks[li + 1], slope=SLOPE, tap_major=self.kf[idx].endswith("_tap"))
             acts.append(t)
         flat = t.view(t.shape[0], -1)
         if masks is None:
@@ -108,11 +113,12 @@ class FnetProgram:
                 if has_b:
                     ops.channel_sum(delta, ps.g[w + "bias"])
             if li > 0:
-                delta = ops.pm_gemm(delta, ps.pack(w + "weight", "dgrad"), cin, ks=k, stride=s, pad=p, mode=1,
-                                    out_hw=(src.shape[2], src.shape[3]), mask_y=src, slope=SLOPE)
+                delta = ops.pm_gemm(delta, ps.pack(w + "weight", self.kd[idx]), cin, ks=k, stride=s, pad=p, mode=1,
+                                    out_hw=(src.shape[2], src.shape[3]), mask_y=src, slope=SLOPE,
+                                    tap_major=self.kd[idx].endswith("_tap"))
             elif need_dx:
-                dx = ops.pm_gemm(delta, ps.pack(w + "weight", "dgrad"), cin, ks=k, stride=s, pad=p, mode=1,
-                                 out_hw=(src.shape[2], src.shape[3]))
+                dx = ops.pm_gemm(delta, ps.pack(w + "weight", self.kd[idx]), cin, ks=k, stride=s, pad=p, mode=1,
+                                 out_hw=(src.shape[2], src.shape[3]), tap_major=self.kd[idx].endswith("_tap"))
         return dx, (deltas + [d_h1, d_h2, d_f] if keep_deltas else None)
 
     # ------------------------------------------------------------------ the three uses

@@ -16,7 +16,7 @@ TERMS = 3  # default GEMM precision: 3 = bf16x3 split (fp32-class), 1 = single b
 
 class PackDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int32), ("K", C.c_int32),
-                ("R", C.c_int32), ("s_kouter", C.c_int32), ("s_n", C.c_int32), ("reserved", C.c_int32)]
+                ("R", C.c_int32), ("s_kouter", C.c_int32), ("s_n", C.c_int32), ("s_kinner", C.c_int32)]
 
 
 class PMParams(C.Structure):
@@ -30,7 +30,7 @@ class PMParams(C.Structure):
         ("out", C.c_void_p), ("out_bs", C.c_int64), ("out_coff", C.c_int32), ("act", C.c_int32),
         ("slope", C.c_float), ("accumulate", C.c_int32), ("bias", C.c_void_p),
         ("mask_y", C.c_void_p), ("mask_bs", C.c_int64), ("residual", C.c_void_p), ("res_bs", C.c_int64),
-        ("debug", C.c_int32), ("reserved", C.c_int32),
+        ("debug", C.c_int32), ("tap_major", C.c_int32),
     ]
 
 
@@ -111,13 +111,26 @@ def packed_bytes(N: int, K: int) -> int:
 
 
 def pack_layout(kind: str, w: torch.Tensor):
-    """(N, K, R, s_kouter, s_n) of the [N x K] view of conv weight ``w`` [Cout, Cin, kh, kw]."""
+    """(N, K, R, s_kouter, s_n, s_kinner) of the [N x K] view of conv weight ``w`` [Cout, Cin, kh, kw]."""
     Cout, Cin, kh, kw = w.shape
-    if kind == "fwd":      # B[n=co][k=(ci,ky,kx)]
-        return Cout, Cin * kh * kw, Cin * kh * kw + 1, 0, Cin * kh * kw
-    if kind == "dgrad":    # B[n=ci][k=(co,ky,kx)]
-        return Cin, Cout * kh * kw, kh * kw, Cin * kh * kw, kh * kw
+    KK = kh * kw
+    if kind == "fwd":        # B[n=co][k=(ci,ky,kx)]
+        return Cout, Cin * KK, Cin * KK + 1, 0, Cin * KK, 1
+    if kind == "dgrad":      # B[n=ci][k=(co,ky,kx)]
+        return Cin, Cout * KK, KK, Cin * KK, KK, 1
+    if kind == "fwd_tap":    # B[n=co][k=(ky,kx,ci)]
+        return Cout, Cin * KK, Cin, 1, Cin * KK, KK
+    if kind == "dgrad_tap":  # B[n=ci][k=(ky,kx,co)]
+        return Cin, Cout * KK, Cout, 1, KK, Cin * KK
     raise ValueError(kind)
+
+
+def conv_pack_kind(w: torch.Tensor, dgrad: bool, concat: bool = False) -> str:
+    """Tap-major K order whenever the gathered tensor's channel count allows the fast producer path."""
+    Cout, Cin, kh, kw = w.shape
+    gathered = Cout if dgrad else Cin
+    tap = kh * kw > 1 and gathered % 32 == 0 and not concat
+    return ("dgrad" if dgrad else "fwd") + ("_tap" if tap else "")
 
 
 class PackTable:
@@ -132,10 +145,10 @@ class PackTable:
         self.max_elems = 0
 
     def add(self, w: torch.Tensor, kind: str) -> int:
-        N, K, R, sk, sn = pack_layout(kind, w)
+        N, K, R, sk, sn, ski = pack_layout(kind, w)
         off = self.total
         nb = packed_bytes(N, K)
-        self.entries.append((w, N, K, R, sk, sn, off))
+        self.entries.append((w, N, K, R, sk, sn, off, ski))
         self.total += (nb + 255) // 256 * 256
         self.max_elems = max(self.max_elems, nb // 4)
         return len(self.entries) - 1
@@ -143,8 +156,8 @@ class PackTable:
     def finalize(self):
         self.buf = torch.empty(max(self.total, 256), dtype=torch.uint8, device=self.device)
         arr = (PackDesc * len(self.entries))()
-        for i, (w, N, K, R, sk, sn, off) in enumerate(self.entries):
-            arr[i] = PackDesc(w.data_ptr(), self.buf.data_ptr() + off, N, K, R, sk, sn, 0)
+        for i, (w, N, K, R, sk, sn, off, ski) in enumerate(self.entries):
+            arr[i] = PackDesc(w.data_ptr(), self.buf.data_ptr() + off, N, K, R, sk, sn, ski)
         raw = bytes(arr)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
         return self
@@ -177,7 +190,7 @@ def pack_single(w: torch.Tensor, kind: str):
 # ------------------------------------------------------------------ pixel-as-M GEMM
 def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None, out_hw=None, out_coff=0,
             ln=None, bias=None, act=False, slope=0.2, mask_y=None, residual=None, accumulate=False,
-            wpack_bs=0, terms=None, debug=0):
+            wpack_bs=0, terms=None, debug=0, tap_major=False):
     """out[b, coff+n, p] = epi(sum_k A(b,p,k) W[n,k]).  ``ln`` = (stats[B,HW,2], gamma, beta)."""
     B, C1, Hs, Ws = x.shape
     in_bs = _img_view(x, "x")
@@ -203,6 +216,7 @@ def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None
     p.out, p.out_bs, p.out_coff = out.data_ptr(), out_bs, out_coff
     p.act, p.slope, p.accumulate = int(act), slope, int(accumulate)
     p.debug = debug
+    p.tap_major = int(tap_major)
     p.bias = None if bias is None else _f32(bias).data_ptr()
     if mask_y is not None:
         p.mask_y, p.mask_bs = mask_y.data_ptr(), _img_view(mask_y, "mask_y")

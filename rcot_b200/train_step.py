@@ -53,9 +53,24 @@ class OTTrainStep:
         self.F_opt = FlatOptimizer(Fprog.ps, optimizer)
         self.group = group
         self.save_hidden = save_hidden      # None: decide per batch from free HBM
+        self.timing = None                  # set to [] to collect (section, start_event, end_event) per iteration
         self.world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(group)
+
+    def _mark(self, name):
+        """Section boundary for bench.py's phase breakdown (CUDA events on the launching stream)."""
+        if self.timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timing.append((name, ev))
+
+    def sections_ms(self):
+        """{section: ms} from the marks of the last iteration (call after a synchronize)."""
+        out = {}
+        for (n0, e0), (_, e1) in zip(self.timing[:-1], self.timing[1:]):
+            out[n0] = out.get(n0, 0.0) + e0.elapsed_time(e1)
+        return out
 
     def _allreduce(self, t):
         if self.world > 1:
@@ -74,19 +89,23 @@ class OTTrainStep:
             need = 12.3 * 49.35e6 * 4 * B * (P / 128.0) ** 2
             save = need < 0.55 * torch.cuda.get_device_properties(degraded.device).total_memory
         tape = Tape(save_hidden=bool(save))
+        self._mark("T_forward")
         out = T.forward(degraded, tape)
+        self._mark("F_critic_step")
         # ---------------- F-sub
         F.ps.zero_grad()
         loss_F = F.critic_step(target, out, Bg)
         self._allreduce(F.ps.grad)
         self.F_opt.step(lr)
         # ---------------- gradient penalty (on the updated potential)
+        self._mark("F_penalty_step")
         F.ps.zero_grad()
         interp = ops.axpby(target, out, a_vec=alpha)
         loss_gp = F.penalty_step(interp, Bg)
         self._allreduce(F.ps.grad)
         self.F_opt.step(lr, n=F.n_without_fc2_bias)      # fc2.bias has no gradient here -> skipped
         # ---------------- T-sub
+        self._mark("T_cost_and_F_input_grad")
         T.ps.zero_grad()
         f, dF = F.input_grad(out, -1.0 / Bg)
         acc = torch.zeros(4, device=out.device)          # [sum res^2, fourier, sum |out-target|, sum f]
@@ -98,9 +117,12 @@ class OTTrainStep:
         n_global = float(Bg * 3 * P * P)
         dout = torch.empty_like(out)
         ops.cost_stage2(out, degraded, tgt, gfou, dF, acc, dout, self.sigma, self.Sigma, n_global)
+        self._mark("T_backward")
         tape.backward(out, dout)
+        self._mark("T_allreduce_and_optimizer")
         self._allreduce(T.ps.grad[:T.ps.n_used])
         self.T_opt.step(lr / 2, n=T.ps.n_used)           # never-used modules have grad None -> skipped
+        self._mark("end")
         rmse = torch.sqrt(acc[0] / n_global)
         loss_T = -acc[3] / Bg + self.sigma * (rmse + acc[1])
         if paired:

@@ -88,6 +88,16 @@ def test_conv_fwd_dgrad(cuda_lib, Cin, Cout, k, s, p, H, W, bias, act):
     pkT = ops.pack_single(wd, "dgrad")
     dx = ops.pm_gemm(dy.cuda(), pkT.ptr(0), Cin, ks=k, stride=s, pad=p, mode=1, out_hw=(H, W))
     _close(dx, refdx)
+    # tap-major K order (ky, kx, channel): the fast producer path used whenever channels % 32 == 0
+    if Cin % 32 == 0:
+        pkt = ops.pack_single(wd, "fwd_tap")
+        out_t = ops.pm_gemm(x.cuda(), pkt.ptr(0), Cout, ks=k, stride=s, pad=p, bias=None if b is None else b.cuda(),
+                            act=act, tap_major=True)
+        _close(out_t, ref)
+    if Cout % 32 == 0:
+        pktT = ops.pack_single(wd, "dgrad_tap")
+        dx_t = ops.pm_gemm(dy.cuda(), pktT.ptr(0), Cin, ks=k, stride=s, pad=p, mode=1, out_hw=(H, W), tap_major=True)
+        _close(dx_t, refdx)
     # sign-mask epilogue + accumulate: out = prev + dx * (mask>0 ? 1 : 0.2)
     mask = torch.randn(2, Cin, H, W, generator=g)
     prev = torch.randn(2, Cin, H, W, generator=g)
