@@ -197,12 +197,35 @@ __device__ __forceinline__ void stencil4(const float* __restrict__ plane, const 
   }
 }
 
+// Two vertically adjacent output rows (y, y+1) from the four input rows y-1 .. y+2: 8 outputs per
+// 4 row fetches instead of 6.
+__device__ __forceinline__ void stencil4x2(const float* __restrict__ plane, const float* w, int y, int x0, int H, int W,
+                                           float* o0, float* o1) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o0[j] = 0.f;
+    o1[j] = 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const Row6 v = load_row6(plane, y + r - 1, x0, H, W);
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r < 3) o0[j] = fmaf(v.v[j + kx], w[r * 3 + kx], o0[j]);
+        if (r > 0) o1[j] = fmaf(v.v[j + kx], w[(r - 1) * 3 + kx], o1[j]);
+      }
+  }
+}
+
 // mode 0: out[ch] = dw(in[ch])                (flip=1: transposed = data gradient)
 //         optional sumsq[b*nsq + ch] += sum_p out^2 for ch < nsq   (MDTA row norms of q and k)
 // mode 1: out[j] = gelu(dw(in[j])) * dw(in[j+hid]),  j < hid            (GDFN gate)
 // mode 2: a = dw(in[j]), b = dw(in[j+hid]); out[j] = dg*b*gelu'(a); out[j+hid] = dg*gelu(a);
 //         optional g_out[j] = gelu(a)*b                                 (GDFN gate backward)
-// Work is flattened over (image, plane, quad) so small feature maps still fill the machine.
+// Work is flattened over (image, plane, row pair, quad column) so small feature maps still fill the machine;
+// each thread produces a 4-wide x 2-high patch (H is even at every level).
 __global__ void __launch_bounds__(256) dwconv_kernel(const rcot_dw_params p, const int planes, const int qpp,
                                                      const long total) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,22 +233,26 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const rcot_dw_params p, con
   const long pl = active ? idx / qpp : 0;
   const int quad = active ? (int)(idx - pl * qpp) : 0;
   const int b = (int)(pl / planes), ch = (int)(pl - (long)b * planes);
-  const int HW = p.H * p.W;
-  const int pix = quad * 4;
-  const int y = pix / p.W, x0 = pix - y * p.W;
+  const int HW = p.H * p.W, qw = p.W >> 2;
+  const int yp = quad / qw;
+  const int y = yp * 2, x0 = (quad - yp * qw) * 4;
+  const int pix = y * p.W + x0;
   const float* inb = p.in + (size_t)b * p.in_bs;
   float w0[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) w0[i] = __ldg(p.w + ch * 9 + (p.flip ? 8 - i : i));
   if (p.mode == 0) {
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
     if (active) {
-      stencil4(inb + (size_t)ch * HW, w0, y, x0, p.H, p.W, o);
-      *reinterpret_cast<float4*>(p.out + (size_t)b * p.out_bs + (size_t)ch * HW + pix) =
-          make_float4(o[0], o[1], o[2], o[3]);
+      stencil4x2(inb + (size_t)ch * HW, w0, y, x0, p.H, p.W, o0, o1);
+      float* op = p.out + (size_t)b * p.out_bs + (size_t)ch * HW + pix;
+      *reinterpret_cast<float4*>(op) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+      *reinterpret_cast<float4*>(op + p.W) = make_float4(o1[0], o1[1], o1[2], o1[3]);
     }
     if (p.sumsq) {  // uniform branch
-      float sq = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3];
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sq += o0[j] * o0[j] + o1[j] * o1[j];
       const bool mine = active && ch < p.nsq;
       if (qpp % 32 == 0) {  // a warp never straddles two planes
         sq = warp_sum(mine ? sq : 0.f);
@@ -240,30 +267,69 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const rcot_dw_params p, con
   float w1[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) w1[i] = __ldg(p.w + (ch + p.hid) * 9 + i);
-  float a[4], g[4];
-  stencil4(inb + (size_t)ch * HW, w0, y, x0, p.H, p.W, a);
-  stencil4(inb + (size_t)(ch + p.hid) * HW, w1, y, x0, p.H, p.W, g);
-  if (p.mode == 1) {
-    *reinterpret_cast<float4*>(p.out + (size_t)b * p.out_bs + (size_t)ch * HW + pix) =
-        make_float4(gelu_erf(a[0]) * g[0], gelu_erf(a[1]) * g[1], gelu_erf(a[2]) * g[2], gelu_erf(a[3]) * g[3]);
-  } else {
-    const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.dg + (size_t)b * p.dg_bs + (size_t)ch * HW + pix));
-    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-    float da[4], db[4], gg[4];
+  float a[2][4], g[2][4];
+  stencil4x2(inb + (size_t)ch * HW, w0, y, x0, p.H, p.W, a[0], a[1]);
+  stencil4x2(inb + (size_t)(ch + p.hid) * HW, w1, y, x0, p.H, p.W, g[0], g[1]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float ga = gelu_erf(a[j]);
-      da[j] = d[j] * g[j] * gelu_erf_grad(a[j]);
-      db[j] = d[j] * ga;
-      gg[j] = ga * g[j];
+  for (int r = 0; r < 2; ++r) {
+    const int pr = pix + r * p.W;
+    if (p.mode == 1) {
+      *reinterpret_cast<float4*>(p.out + (size_t)b * p.out_bs + (size_t)ch * HW + pr) =
+          make_float4(gelu_erf(a[r][0]) * g[r][0], gelu_erf(a[r][1]) * g[r][1], gelu_erf(a[r][2]) * g[r][2],
+                      gelu_erf(a[r][3]) * g[r][3]);
+    } else {
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.dg + (size_t)b * p.dg_bs + (size_t)ch * HW + pr));
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+      float da[4], db[4], gg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float ga = gelu_erf(a[r][j]);
+        da[j] = d[j] * g[r][j] * gelu_erf_grad(a[r][j]);
+        db[j] = d[j] * ga;
+        gg[j] = ga * g[r][j];
+      }
+      float* ob = p.out + (size_t)b * p.out_bs;
+      *reinterpret_cast<float4*>(ob + (size_t)ch * HW + pr) = make_float4(da[0], da[1], da[2], da[3]);
+      *reinterpret_cast<float4*>(ob + (size_t)(ch + p.hid) * HW + pr) = make_float4(db[0], db[1], db[2], db[3]);
+      if (p.g_out)
+        *reinterpret_cast<float4*>(p.g_out + (size_t)b * p.g_bs + (size_t)ch * HW + pr) =
+            make_float4(gg[0], gg[1], gg[2], gg[3]);
     }
-    float* ob = p.out + (size_t)b * p.out_bs;
-    *reinterpret_cast<float4*>(ob + (size_t)ch * HW + pix) = make_float4(da[0], da[1], da[2], da[3]);
-    *reinterpret_cast<float4*>(ob + (size_t)(ch + p.hid) * HW + pix) = make_float4(db[0], db[1], db[2], db[3]);
-    if (p.g_out)
-      *reinterpret_cast<float4*>(p.g_out + (size_t)b * p.g_bs + (size_t)ch * HW + pix) =
-          make_float4(gg[0], gg[1], gg[2], gg[3]);
   }
+}
+
+// Fallback for feature maps whose width is not a multiple of 4 or whose height is odd (whole-image
+// inference at arbitrary sizes, reference tester.py:107): one output per thread, modes 0 and 1 only.
+__global__ void __launch_bounds__(256) dwconv_scalar_kernel(const rcot_dw_params p, const int planes, const long total) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int HW = p.H * p.W;
+  const long pl = idx / HW;
+  const int pix = (int)(idx - pl * HW);
+  const int b = (int)(pl / planes), ch = (int)(pl - (long)b * planes);
+  const int y = pix / p.W, x = pix - y * p.W;
+  const float* inb = p.in + (size_t)b * p.in_bs;
+  auto tap9 = [&](int c, bool flip) {
+    const float* plane = inb + (size_t)c * HW;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if ((unsigned)yy >= (unsigned)p.H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if ((unsigned)xx >= (unsigned)p.W) continue;
+        const int k = ky * 3 + kx;
+        acc = fmaf(__ldg(plane + yy * p.W + xx), __ldg(p.w + c * 9 + (flip ? 8 - k : k)), acc);
+      }
+    }
+    return acc;
+  };
+  float o = tap9(ch, p.flip != 0);
+  if (p.mode == 1) o = gelu_erf(o) * tap9(ch + p.hid, false);
+  p.out[(size_t)b * p.out_bs + (size_t)ch * HW + pix] = o;
+  if (p.mode == 0 && p.sumsq && ch < p.nsq) atomicAdd(p.sumsq + (size_t)b * p.nsq + ch, o * o);
 }
 
 // dW[ch, k] += sum_{b,p} dout[b,ch,p] * in[b,ch,p+off_k].  grid = (chunks, Cn); each CTA strides over
@@ -313,7 +379,7 @@ __global__ void __launch_bounds__(256)
     dw_bwd_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
                   const float* __restrict__ w, float* __restrict__ din, int64_t din_bs, float* __restrict__ dw, int B,
                   int H, int W) {
-  const int HW = H * W, ch = blockIdx.y, qpp = HW / 4;
+  const int HW = H * W, ch = blockIdx.y, qw = W >> 2, qpp = (H >> 1) * qw;   // 4 x 2 patches per plane
   const long total = (long)B * qpp;
   float wf[9];
 #pragma unroll
@@ -322,32 +388,45 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int i = 0; i < 9; ++i) acc[i] = 0.f;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int b = (int)(e / qpp), pix = (int)(e - (long)b * qpp) * 4;
-    const int y = pix / W, x0 = pix - y * W;
+    const int b = (int)(e / qpp), quad = (int)(e - (long)b * qpp);
+    const int yp = quad / qw;
+    const int y = yp * 2, x0 = (quad - yp * qw) * 4;
     const float* dplane = dout + (size_t)b * dout_bs + (size_t)ch * HW;
     const float* iplane = in + (size_t)b * in_bs + (size_t)ch * HW;
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    float d0[4], d1[4];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const Row6 r = load_row6(dplane, y + ky - 1, x0, H, W);
-      if (ky == 1) {
+    for (int r = 0; r < 4; ++r) {   // dout rows y-1 .. y+2 feed din rows y and y+1
+      const Row6 v = load_row6(dplane, y + r - 1, x0, H, W);
+      if (r == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) d[j] = r.v[j + 1];
+        for (int j = 0; j < 4; ++j) d0[j] = v.v[j + 1];
+      }
+      if (r == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d1[j] = v.v[j + 1];
       }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fmaf(r.v[j + kx], wf[ky * 3 + kx], o[j]);
+        for (int j = 0; j < 4; ++j) {
+          if (r < 3) o0[j] = fmaf(v.v[j + kx], wf[r * 3 + kx], o0[j]);
+          if (r > 0) o1[j] = fmaf(v.v[j + kx], wf[(r - 1) * 3 + kx], o1[j]);
+        }
     }
-    *reinterpret_cast<float4*>(din + (size_t)b * din_bs + (size_t)ch * HW + pix) = make_float4(o[0], o[1], o[2], o[3]);
+    float* dp = din + (size_t)b * din_bs + (size_t)ch * HW + y * W + x0;
+    *reinterpret_cast<float4*>(dp) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+    *reinterpret_cast<float4*>(dp + W) = make_float4(o1[0], o1[1], o1[2], o1[3]);
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const Row6 r = load_row6(iplane, y + ky - 1, x0, H, W);
+    for (int r = 0; r < 4; ++r) {   // in rows y-1 .. y+2 against the two centre rows of dout
+      const Row6 v = load_row6(iplane, y + r - 1, x0, H, W);
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[ky * 3 + kx] = fmaf(d[j], r.v[j + kx], acc[ky * 3 + kx]);
+        for (int j = 0; j < 4; ++j) {
+          if (r < 3) acc[r * 3 + kx] = fmaf(d0[j], v.v[j + kx], acc[r * 3 + kx]);
+          if (r > 0) acc[(r - 1) * 3 + kx] = fmaf(d1[j], v.v[j + kx], acc[(r - 1) * 3 + kx]);
+        }
     }
   }
   __shared__ float red[9][8];
@@ -472,10 +551,15 @@ extern "C" int rcot_dwconv3x3(const rcot_dw_params* pp, rcot_stream_t st) {
     if (p.mode == 2) RCOT_REQUIRE(p.dg != nullptr, "dwconv3x3: gate backward needs dg");
     planes = p.hid;
   }
-  RCOT_REQUIRE(p.W % 4 == 0, "dwconv3x3: width must be a multiple of 4, got %d", p.W);
+  if (p.W % 4 != 0 || p.H % 2 != 0) {
+    RCOT_REQUIRE(p.mode != 2, "dwconv3x3: gate backward needs width %% 4 == 0 and even height, got %dx%d", p.H, p.W);
+    const long tot = (long)p.B * planes * p.H * p.W;
+    dwconv_scalar_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)st>>>(p, planes, tot);
+    return check_launch("dwconv3x3");
+  }
   RCOT_REQUIRE(p.in_bs % 4 == 0 && p.out_bs % 4 == 0 && ((uintptr_t)p.in % 16 == 0) && ((uintptr_t)p.out % 16 == 0),
                "dwconv3x3: tensors must be 16-byte aligned");
-  const int qpp = p.H * p.W / 4;
+  const int qpp = p.H * p.W / 8;   // 4 x 2 output patches per plane
   const long total = (long)p.B * planes * qpp;
   dwconv_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)st>>>(p, planes, qpp, total);
   return check_launch("dwconv3x3");
@@ -499,12 +583,12 @@ extern "C" int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* d
                                   rcot_stream_t st) {
   RCOT_REQUIRE(in && dout && w && din && dw && B > 0 && Cn > 0 && Cn <= 65535 && H > 0 && W > 0,
                "dwconv3x3_bwd: bad arguments");
-  RCOT_REQUIRE(W % 4 == 0 && in_bs % 4 == 0 && dout_bs % 4 == 0 && din_bs % 4 == 0,
-               "dwconv3x3_bwd: width/strides must be multiples of 4");
-  long total = (long)B * H * W / 4;
+  RCOT_REQUIRE(W % 4 == 0 && H % 2 == 0 && in_bs % 4 == 0 && dout_bs % 4 == 0 && din_bs % 4 == 0,
+               "dwconv3x3_bwd: width/strides must be multiples of 4 and height even");
+  long total = (long)B * H * W / 8;
   // enough CTAs per channel to fill the machine, at least ~4 quads per thread
   long want = (148L * 8 + Cn - 1) / Cn;
-  long maxc = (total + 256 * 4 - 1) / (256 * 4);
+  long maxc = (total + 256 * 2 - 1) / (256 * 2);
   int chunks = (int)(want < maxc ? want : maxc);
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, Cn);

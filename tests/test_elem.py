@@ -103,7 +103,7 @@ def test_layernorm_bwd(cuda_lib):
 def test_dwconv_variants(cuda_lib):
     from rcot_b200 import ops
     g = torch.Generator().manual_seed(6)
-    B, hid, H, W = 2, 127, 9, 12
+    B, hid, H, W = 2, 127, 10, 12
     Cn = 2 * hid
     u = torch.randn(B, Cn, H, W, generator=g)
     w = torch.randn(Cn, 1, 3, 3, generator=g) / 3
@@ -162,3 +162,18 @@ def test_dwconv_bwd_fused(cuda_lib):
     din = ops.dwconv_bwd(x.cuda(), dout.cuda(), w.cuda(), dw)
     _close("din", din, x64.grad)
     _close("dw", dw, prev.double() + w64.grad)
+
+
+def test_dwconv_odd_sizes(cuda_lib):
+    """Whole-image inference reaches feature maps like 25x39: the scalar fallback path."""
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    B, hid, H, W = 2, 9, 5, 7
+    u = torch.randn(B, 2 * hid, H, W, generator=g)
+    w = torch.randn(2 * hid, 1, 3, 3, generator=g) / 3
+    full = F.conv2d(u.double(), w.double(), padding=1, groups=2 * hid)
+    a, b = full.chunk(2, 1)
+    sumsq = torch.zeros(B, 6, device="cuda")
+    _close("plain", ops.dwconv(u.cuda(), w.cuda(), sumsq=sumsq, nsq=6), full)
+    _close("sumsq", sumsq, (full[:, :6] ** 2).sum((2, 3)))
+    _close("gate", ops.dwconv(u.cuda(), w.cuda(), mode=1), F.gelu(a) * b)
