@@ -263,8 +263,16 @@ def run_b200(args):
                    for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
         top, tv = max(summ.items(), key=lambda kv: kv[1]["ms"])
         achieved = tv["bytes"] / 1e9 / (tv["ms"] / 1e3)
+        # DRAM bytes per launch of that kernel from the committed ncu capture of the same workload (if present)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("kernel") == top and tj.get("per_gpu_batch") == B and tj.get("patch") == P:
+                traffic = tj["dram_bytes_per_launch"]
         roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                "peak_source": peak_src,
                 "launches": tv["launches"], "avg_launch_ms": tv["ms"] / tv["launches"],
                 "note": "achieved = algorithmic bytes of all launches of this kernel in one step / their summed "
                         "CUDA-event time, taken on one extra step right after the timed region"}

@@ -20,3 +20,9 @@ tot = sum(v["ms"] for v in summ.values())
 print("total", tot)
 for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:int(sys.argv[1]) if len(sys.argv) > 1 else 45]:
     print(f'{v["ms"]:8.2f} ms {v["ms"]/tot*100:5.1f}% n={v["launches"]:4d} avg={v["ms"]/v["launches"]*1000:8.1f} us  {v["bytes"]/1e9/(v["ms"]/1e3):7.0f} GB/s  {k}')
+import re, collections
+by = collections.defaultdict(float)
+for k, v in summ.items():
+    m = re.search(r"\(\d+, \d+, (\d+), \d+\)", k)
+    by[m.group(1) if m else "other"] += v["ms"]
+print("ms by feature-map height:", {k: round(v, 1) for k, v in sorted(by.items(), key=lambda kv: -kv[1])})
