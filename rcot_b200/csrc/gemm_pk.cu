@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         if (LN) R.st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWb + q0 + lane);
 #pragma unroll
         for (int j = 0; j < PK_BT; ++j) {
-          if (b_ok[j]) ld8(R.b[j], b_row[j] + (size_t)b * b_bstride[j] + q);
+          if (b_ok[j]) ld8(R.b[j], b_row[j] + (size_t)b * (LN ? p.b_bs : b_bstride[j]) + q);
           else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) R.b[j][i] = 0.f;
@@ -159,19 +159,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
     // (image, first pixel) of the chunk being prefetched, advanced without divisions
     int nb = p.per_image ? bz : c_begin / cpi;
     int nq0 = (p.per_image ? c_begin : c_begin - nb * cpi) * KC;
-    Regs nxt;
-    if (nchunks > 0) load(nxt, nb, nq0);
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < nchunks; ++it) {
-      Regs cur = nxt;
-      const int cq0 = nq0;
+    auto advance = [&]() {            // walker -> next chunk
       nq0 += KC;
       if (!p.per_image && nq0 >= cpi * KC) {
         nq0 = 0;
         ++nb;
       }
-      if (it + 1 < nchunks) load(nxt, nb, nq0);
+    };
+    auto process = [&](Regs& cur, int cq0) {   // convert + store one prefetched chunk into stage s
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* st = smem + (size_t)s * stage_bytes;
       uint8_t* a_hi = st;
@@ -179,27 +176,24 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       uint8_t* b_hi = st + TA * a_tile;
       uint8_t* b_lo = b_hi + b_tile;
       op_store8<TERMS>(a_hi, a_lo, r0, k8, cur.a);
-      float mu[8], rs[8];
       if (LN) {
+        // statistics of this thread's 8 pixels are held by lanes k8*8+i of the warp (all lanes shuffle)
         const int q = cq0 + k8 * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {   // statistics of this thread's 8 pixels, held by lanes k8*8+i
-          mu[i] = __shfl_sync(0xffffffffu, cur.st.x, k8 * 8 + i);
+        for (int i = 0; i < 8; ++i) {
+          const float mu = __shfl_sync(0xffffffffu, cur.st.x, k8 * 8 + i);
           const float rv = __shfl_sync(0xffffffffu, cur.st.y, k8 * 8 + i);
-          rs[i] = (all_full || q + i < HWa) ? rv : 0.f;
+          const bool in = all_full || q + i < HWa;
+#pragma unroll
+          for (int j = 0; j < PK_BT; ++j)
+            cur.b[j][i] = (in && b_ok[j]) ? (cur.b[j][i] - mu) * rv * ga[j] + be[j] : 0.f;
         }
       }
 #pragma unroll
       for (int j = 0; j < PK_BT; ++j) {
         if (j >= nbt) break;
         const int r = r0 + 128 * j;
-        if (r < BN) {
-          if (LN && b_ok[j]) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cur.b[j][i] = rs[i] != 0.f ? (cur.b[j][i] - mu[i]) * rs[i] * ga[j] + be[j] : 0.f;
-          }
-          op_store8<TERMS>(b_hi, b_lo, r, k8, cur.b[j]);
-        }
+        if (r < BN) op_store8<TERMS>(b_hi, b_lo, r, k8, cur.b[j]);
       }
       fence_async_smem();
       __syncwarp();
@@ -207,6 +201,50 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       if (++s == stages) {
         s = 0;
         ph ^= 1;
+      }
+    };
+    if (LN) {
+      // (the LayerNorm variant is register-bound at 544 threads: one prefetch set + a copy is the cheaper shape)
+      Regs nxt;
+      int qn = nq0;
+      if (nchunks > 0) {
+        load(nxt, nb, nq0);
+        advance();
+      }
+      for (int it = 0; it < nchunks; ++it) {
+        Regs cur = nxt;
+        const int qc = qn;
+        if (it + 1 < nchunks) {
+          qn = nq0;
+          load(nxt, nb, nq0);
+          advance();
+        }
+        process(cur, qc);
+      }
+    } else {
+      // two register sets in ping-pong: the loads of chunk i+1 fly while chunk i is converted, no copies
+      Regs ra, rb;
+      int qa = nq0, qb = 0;
+      if (nchunks > 0) {
+        load(ra, nb, nq0);
+        advance();
+      }
+      for (int it = 0; it < nchunks; it += 2) {
+        const bool has_b = it + 1 < nchunks;
+        if (has_b) {
+          qb = nq0;
+          load(rb, nb, nq0);
+          advance();
+        }
+        process(ra, qa);
+        if (has_b) {
+          if (it + 2 < nchunks) {
+            qa = nq0;
+            load(ra, nb, nq0);
+            advance();
+          }
+          process(rb, qb);
+        }
       }
     }
   } else {
