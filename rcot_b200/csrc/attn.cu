@@ -29,6 +29,14 @@ __device__ __forceinline__ void store_split(uint8_t* base, int N, int K, int n, 
   *reinterpret_cast<__nv_bfloat16*>(base + packed_offset(N, K, n, k, 1)) = lo;
 }
 
+// 8 consecutive k (k0 % 8 == 0) of row n: one 16-byte core-matrix row in the hi image and one in the lo image.
+__device__ __forceinline__ void store_split8(uint8_t* base, int N, int K, int n, int k0, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  *reinterpret_cast<uint4*>(base + packed_offset(N, K, n, k0, 0)) = hi;
+  *reinterpret_cast<uint4*>(base + packed_offset(N, K, n, k0, 1)) = lo;
+}
+
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p) {
   extern __shared__ float sm[];
   const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
@@ -71,16 +79,32 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p)
     }
   }
   __syncthreads();
-  // M[co, (h,j)] = sum_i W_out[co, (h,i)] * A[i,j]
-  uint8_t* Mp = reinterpret_cast<uint8_t*>(p.Mpack) + (size_t)b * p.pack_bs;
-  uint8_t* MTp = p.MTpack ? reinterpret_cast<uint8_t*>(p.MTpack) + (size_t)b * p.pack_bs : nullptr;
+  // M[co, (h,j)] = sum_i W_out[co, (h,i)] * A[i,j]  -> shared memory, then 16-byte packed stores
+  float* sM = snk + c;       // [C * c]
   for (int e = tid; e < C * c; e += blockDim.x) {
     const int co = e / c, j = e - co * c;
     const float* wrow = p.w_out + (size_t)co * C + h * c;
     float acc = 0.f;
     for (int i = 0; i < c; ++i) acc = fmaf(__ldg(wrow + i), sA[i * c + j], acc);
-    store_split(Mp, C, C, co, h * c + j, acc);
-    if (MTp) store_split(MTp, C, C, h * c + j, co, acc);
+    sM[e] = acc;
+  }
+  __syncthreads();
+  uint8_t* Mp = reinterpret_cast<uint8_t*>(p.Mpack) + (size_t)b * p.pack_bs;
+  uint8_t* MTp = p.MTpack ? reinterpret_cast<uint8_t*>(p.MTpack) + (size_t)b * p.pack_bs : nullptr;
+  const int c8 = c >> 3;
+  for (int t = tid; t < C * c8; t += blockDim.x) {          // M: row n = co, 8 consecutive k = h*c + j
+    const int co = t / c8, j0 = (t - co * c8) * 8;
+    store_split8(Mp, C, C, co, h * c + j0, sM + co * c + j0);
+  }
+  if (MTp) {
+    const int C8 = C >> 3;
+    for (int t = tid; t < c * C8; t += blockDim.x) {        // M^T: row n = h*c + j, 8 consecutive k = co
+      const int co0 = (t / c) * 8, j = t - (t / c) * c;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = sM[(co0 + i) * c + j];
+      store_split8(MTp, C, C, h * c + j, co0, v);
+    }
   }
 }
 
@@ -186,13 +210,26 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
   // buffer per (C, heads) configuration, so every other entry stays zero.
   uint8_t* Wp = reinterpret_cast<uint8_t*>(p.W12pack) + (size_t)b * p.pack12_bs;
   const int N2 = 2 * C;
-  for (int e = tid; e < c * c; e += blockDim.x) {
+  for (int e = tid; e < c * c; e += blockDim.x) {            // B_q = dGt / (|q_i| |k_j|), in place
     const int i = e / c, j = e - i * c;
-    const float nq = fmaxf(snq[i], 1e-12f), nk = fmaxf(snk[j], 1e-12f);
-    const float bq = sD[e] / (nq * nk);
-    store_split(Wp, N2, N2, h * c + i, C + h * c + j, bq);
-    store_split(Wp, N2, N2, C + h * c + j, h * c + i, bq);
+    sD[e] = sD[e] / (fmaxf(snq[i], 1e-12f) * fmaxf(snk[j], 1e-12f));
   }
+  __syncthreads();
+  const int c8 = c >> 3;
+  for (int t = tid; t < c * c8; t += blockDim.x) {
+    {   // dq rows: n = h*c + i, 8 consecutive k = C + h*c + j
+      const int i = t / c8, j0 = (t - i * c8) * 8;
+      store_split8(Wp, N2, N2, h * c + i, C + h * c + j0, sD + i * c + j0);
+    }
+    {   // dk rows: n = C + h*c + j, 8 consecutive k = h*c + i
+      const int j = t % c, i0 = (t / c) * 8;
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = sD[(i0 + q) * c + j];
+      store_split8(Wp, N2, N2, C + h * c + j, h * c + i0, v);
+    }
+  }
+  // (the diagonal entries below live in the q->dq and k->dk blocks, which nothing above writes)
   for (int i = tid; i < c; i += blockDim.x) {
     // d/dq of q/max(|q|,eps): the projection term vanishes when the clamp is active
     const float cq = snq[i] >= 1e-12f ? -srq[i] / (snq[i] * snq[i]) : 0.f;
@@ -220,7 +257,17 @@ extern "C" int rcot_attn_fwd(const rcot_attn_params* pp, rcot_stream_t st) {
   if (rc) return rc;
   RCOT_REQUIRE(p.G && p.Mpack, "attn_fwd: null pointer");
   const int c = p.C / p.heads;
-  const size_t smem = ((size_t)c * c + 2 * c) * sizeof(float);
+  const size_t smem = ((size_t)c * c + 2 * c + (size_t)p.C * c) * sizeof(float);
+  RCOT_REQUIRE(c % 8 == 0 && p.C % 8 == 0, "attn_fwd: channels per head must be a multiple of 8");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return RCOT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
   dim3 grid(p.heads, p.B);
   attn_fwd_kernel<<<grid, 256, smem, (cudaStream_t)st>>>(p);
   return check_launch("attn_fwd");

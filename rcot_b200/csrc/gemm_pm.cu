@@ -225,40 +225,22 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         if (t < total_tiles) xw = setup(t);
       }
     };
-    float n1[16], n2[16];
-    TileCtx x1 = xw, x2 = xw;
-    int c1 = 0, c2 = 0;
-    bool ok1 = t < total_tiles, ok2 = false;
-    if (ok1) {
-      load16(n1, xw, c);
-      step_walker();
-      ok2 = t < total_tiles;
-      if (ok2) {
-        x2 = xw;
-        c2 = c;
-        load16(n2, xw, c);
-        step_walker();
-      }
-    }
-    while (ok1) {
+    struct Slot {          // one prefetched work item: 16 operand values + where they belong
       float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = n1[i];
-      const TileCtx cur = x1;
-      const int cc = c1;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) n1[i] = n2[i];
-      x1 = x2;
-      c1 = c2;
-      ok1 = ok2;
-      ok2 = ok2 && (t < total_tiles);
-      if (ok2) {
-        x2 = xw;
-        c2 = c;
-        load16(n2, xw, c);
+      TileCtx x;
+      int c;
+      bool ok;
+    };
+    auto fetch = [&](Slot& S) {
+      S.ok = t < total_tiles;
+      if (S.ok) {
+        S.x = xw;
+        S.c = c;
+        load16(S.v, xw, c);
         step_walker();
       }
-      // ---- convert + store item (cur, cc)
+    };
+    auto process = [&](Slot& S) {   // convert + store one item into the next pipeline stage
       const int s = ps_;
       const uint32_t ph = pph_;
       if (++ps_ == stages) {
@@ -269,23 +251,38 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       uint8_t* st = smem + (size_t)s * stage_bytes;
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
-        bulk_g2s(st + TA * a_tile, cur.wsrc + (size_t)cc * (2 * b_tile), TA * b_tile, &full_bar[s]);
+        bulk_g2s(st + TA * a_tile, S.x.wsrc + (size_t)S.c * (2 * b_tile), TA * b_tile, &full_bar[s]);
       }
       if (LN) {
-        const float* gb = ln_gb + (cc * KC + khalf * 16) * 2;   // interleaved (gamma, beta), zero beyond Ktot
-        if (cur.valid) {
+        const float* gb = ln_gb + (S.c * KC + khalf * 16) * 2;   // interleaved (gamma, beta), zero beyond Ktot
+        if (S.x.valid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 w2 = *reinterpret_cast<const float2*>(gb + 2 * i);
-            v[i] = (v[i] - cur.mu) * cur.rstd * w2.x + w2.y;
+            S.v[i] = (S.v[i] - S.x.mu) * S.x.rstd * w2.x + w2.y;
           }
         }
       }
-      op_store8<TERMS>(st, st + a_tile, row, khalf * 2, v);
-      op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, v + 8);
+      op_store8<TERMS>(st, st + a_tile, row, khalf * 2, S.v);
+      op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, S.v + 8);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+    };
+    // three register sets rotate (no copies): while one item is converted, the loads of the next two fly
+    Slot A, B, C;
+    fetch(A);
+    fetch(B);
+    while (true) {
+      fetch(C);
+      if (!A.ok) break;
+      process(A);
+      fetch(A);
+      if (!B.ok) break;
+      process(B);
+      fetch(B);
+      if (!C.ok) break;
+      process(C);
     }
   } else if (warp == PM_PROD_WARPS) {
     // =========================================================== MMA issuer (whole warp waits, lane 0 issues)
