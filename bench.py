@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--patch", type=int, default=128)
     ap.add_argument("--terms", type=int, default=3, help="3: bf16x3 split products (fp32-class), 1: bf16 products")
+    ap.add_argument("--graph", action="store_true", help="replay each iteration as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -105,9 +106,9 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_config(P, B, world):
+def make_config(P, B, world, graph=False):
     return {"workload": f"one full adversarial iteration (F-sub + GP + T-sub, 3 optimizer steps), {P}x{P} patches, "
-                        f"per-GPU batch {B}, paired, de_id mix [1,3]",
+                        f"per-GPU batch {B}, paired, de_id mix [1,3]" + (", CUDA-graph replay" if graph else ""),
             "patch": P, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
             "l2": "working set per step (tens of GB) >> 126 MB L2; no explicit flush"}
 
@@ -183,7 +184,7 @@ def run_b200(args):
     ops.TERMS = args.terms
     B, P, K, W = args.batch, args.patch, args.steps, max(args.warmup, 3)
     trainer.opt = trainer.parser.parse_args(["--batchSize", str(B * world), "--patch_size", str(P), "--pairnum", "1000000000",
-                                             "--no_dump"])
+                                             "--no_dump"] + (["--cuda_graph"] if args.graph else []))
     torch.manual_seed(0)
     Tnet = N.T_net(decoder=True).cuda()
     Fnet = N.F_net(patch_size=P).cuda()
@@ -200,7 +201,8 @@ def run_b200(args):
 
     def resident_step(i):
         d, t, ids = dev[i % 4]
-        return step.iteration(d, t, ids, alphas[i % 4], True, lr)
+        run = step.iteration_graphed if (args.graph and ops.PROF is None and step.timing is None) else step.iteration
+        return run(d, t, ids, alphas[i % 4], True, lr)
 
     for i in range(W):
         resident_step(i)
@@ -285,7 +287,7 @@ def run_b200(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 storage, bf16x3 split products on tcgen05 (fp32-class)" if args.terms == 3 else "bf16 products, fp32 storage/accumulate",
             "data": "synthetic",
-            "config": make_config(P, B, world),
+            "config": make_config(P, B, world, args.graph),
             "clocks": sampler.result(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms2.item() / K},

@@ -231,6 +231,12 @@ int rcot_rmsprop(float* p, const float* g, float* sq, int64_t n, float lr, float
                  rcot_stream_t stream);
 int rcot_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
               int step, float gscale, rcot_stream_t stream);
+/* same, with the step-dependent scalars in DEVICE memory so a captured CUDA graph can be replayed while the
+ * schedule moves: hyper = {lr, 1-b1^t, 1-b2^t} (RMSprop reads hyper[0] only); effective lr = hyper[0]*lr_mult */
+int rcot_rmsprop_h(float* p, const float* g, float* sq, int64_t n, const float* hyper, float lr_mult, float alpha,
+                   float eps, float gscale, rcot_stream_t stream);
+int rcot_adam_h(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float lr_mult, float b1,
+                float b2, float eps, float gscale, rcot_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -179,9 +179,10 @@ __global__ void signed_sum_kernel(const float* __restrict__ x, float* __restrict
 
 __global__ void __launch_bounds__(256)
     rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, long n, float lr,
-                   float alpha, float eps, float gscale) {
+                   float alpha, float eps, float gscale, const float* __restrict__ hyper) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (hyper) lr *= __ldg(hyper);   // device-resident learning rate (CUDA-graph replays), lr = multiplier
   const float gv = g[i] * gscale;
   const float s = alpha * sq[i] + (1.f - alpha) * gv * gv;
   sq[i] = s;
@@ -190,9 +191,15 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float gscale) {
+                long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float gscale,
+                const float* __restrict__ hyper) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (hyper) {   // device-resident (lr, 1-b1^t, 1-b2^t) for CUDA-graph replays
+    lr *= __ldg(hyper);
+    bc1 = __ldg(hyper + 1);
+    bc2 = __ldg(hyper + 2);
+  }
   const float gv = g[i] * gscale;
   const float mm = b1 * m[i] + (1.f - b1) * gv;
   const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
@@ -257,14 +264,28 @@ extern "C" int rcot_signed_sum(const float* x, float* out, int n, int n_neg, flo
 extern "C" int rcot_rmsprop(float* p, const float* g, float* sq, int64_t n, float lr, float alpha, float eps,
                             float gscale, rcot_stream_t st) {
   RCOT_REQUIRE(p && g && sq && n > 0, "rmsprop: bad arguments");
-  rmsprop_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, sq, n, lr, alpha, eps, gscale);
+  rmsprop_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, sq, n, lr, alpha, eps, gscale, nullptr);
   return check_launch("rmsprop");
+}
+
+extern "C" int rcot_rmsprop_h(float* p, const float* g, float* sq, int64_t n, const float* hyper, float lr_mult,
+                              float alpha, float eps, float gscale, rcot_stream_t st) {
+  RCOT_REQUIRE(p && g && sq && hyper && n > 0, "rmsprop_h: bad arguments");
+  rmsprop_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, sq, n, lr_mult, alpha, eps, gscale, hyper);
+  return check_launch("rmsprop_h");
 }
 
 extern "C" int rcot_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
                          float eps, int step, float gscale, rcot_stream_t st) {
   RCOT_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adam: bad arguments");
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, gscale);
+  adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, gscale, nullptr);
   return check_launch("adam");
+}
+
+extern "C" int rcot_adam_h(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float lr_mult,
+                           float b1, float b2, float eps, float gscale, rcot_stream_t st) {
+  RCOT_REQUIRE(p && g && m && v && hyper && n > 0, "adam_h: bad arguments");
+  adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, n, lr_mult, b1, b2, eps, 1.f, 1.f, gscale, hyper);
+  return check_launch("adam_h");
 }

@@ -426,6 +426,16 @@ def rmsprop(p, g, sq, n, lr, alpha=0.99, eps=1e-8, gscale=1.0):
                                 C.c_float(eps), C.c_float(gscale), _stream()), "rmsprop")
 
 
+def rmsprop_h(p, g, sq, n, hyper, lr_mult=1.0, alpha=0.99, eps=1e-8, gscale=1.0):
+    _lib.check(L().rcot_rmsprop_h(_ptr(p), _ptr(g), _ptr(sq), C.c_int64(n), _ptr(hyper), C.c_float(lr_mult),
+                                  C.c_float(alpha), C.c_float(eps), C.c_float(gscale), _stream()), "rmsprop_h")
+
+
+def adam_h(p, g, m, v, n, hyper, lr_mult=1.0, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
+    _lib.check(L().rcot_adam_h(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(n), _ptr(hyper), C.c_float(lr_mult),
+                               C.c_float(b1), C.c_float(b2), C.c_float(eps), C.c_float(gscale), _stream()), "adam_h")
+
+
 def adam(p, g, m, v, n, lr, step, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
     _lib.check(L().rcot_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(n), C.c_float(lr), C.c_float(b1),
                              C.c_float(b2), C.c_float(eps), step, C.c_float(gscale), _stream()), "adam")
@@ -512,3 +522,5 @@ gp_coef = _instrument("gp_coef", lambda a, k, r: 0)(gp_coef)
 signed_sum = _instrument("signed_sum", lambda a, k, r: 0)(signed_sum)
 rmsprop = _instrument("rmsprop", lambda a, k, r: a[3] * 4 * 5)(rmsprop)
 adam = _instrument("adam", lambda a, k, r: a[4] * 4 * 7)(adam)
+rmsprop_h = _instrument("rmsprop", lambda a, k, r: a[3] * 4 * 5)(rmsprop_h)
+adam_h = _instrument("adam", lambda a, k, r: a[4] * 4 * 7)(adam_h)

@@ -196,3 +196,29 @@ def test_short_training_trajectory_tracks_oracle(gold, cuda_lib):
         tol_T, tol_m = (1e-4, 1e-4) if i == 0 else (3e-2, 2e-2)
         assert abs(lt - o["loss_T"]) <= tol_T * abs(o["loss_T"])
         assert abs(lm - o["loss_mse"]) <= tol_m * abs(o["loss_mse"])
+
+
+def test_cuda_graph_replay_matches_eager(gold, cuda_lib):
+    """iteration_graphed (one captured CUDA graph per iteration, device-resident learning rate) vs eager."""
+    from oracle.make_golden import synth_batch
+    from rcot_b200.train_step import OTTrainStep
+    P, B = gold["P"], gold["B"]
+    runs = []
+    for graphed in (False, True):
+        Tp, Fp = _programs(gold)
+        step = OTTrainStep(Tp, Fp, "RMSprop", sigma=1.0, Sigma=10000.0)
+        losses = []
+        for i in range(3):
+            deg, tgt = synth_batch(200 + i, B, P)
+            alpha = torch.rand(B, generator=torch.Generator().manual_seed(i)).cuda()
+            fn = step.iteration_graphed if graphed else step.iteration
+            r = fn(deg.cuda(), tgt.cuda(), gold["de_id"].cuda(), alpha, True, 1e-4 * (0.5 if i == 2 else 1.0))
+            losses.append(torch.stack([r["loss_F"], r["loss_gp"], r["loss_T"], r["loss_mse"]]).cpu().double())
+        runs.append((losses, Tp.ps.flat.clone(), step.T_opt.steps, step.F_opt.steps))
+    (le, pe, ts_e, fs_e), (lg, pg, ts_g, fs_g) = runs
+    assert (ts_e, fs_e) == (ts_g, fs_g) == (3, 6)
+    torch.testing.assert_close(lg[0], le[0], rtol=1e-5, atol=1e-7)       # same weights, same kernels
+    for a, b in zip(lg[1:], le[1:]):                                      # later: only summation-order noise
+        assert abs(a[2] - b[2]) <= 2e-2 * abs(b[2]) and abs(a[3] - b[3]) <= 2e-2 * abs(b[3])
+    # every weight moved by the same three RMSprop steps up to sign flips of ~zero gradients
+    assert (pe - pg).abs().max().item() <= 3 * 10 * 1e-4 + 1e-6

@@ -59,6 +59,8 @@ parser.add_argument("--seed", type=int, default=None, help="fixed seed (default:
 parser.add_argument("--synthetic", type=int, default=0, help="train on this many seeded synthetic pairs")
 parser.add_argument("--no_dump", action="store_true", help="skip checksample PNG dumps")
 parser.add_argument("--max_iters", type=int, default=0, help="stop each epoch after this many iterations (0 = all)")
+parser.add_argument("--cuda_graph", action="store_true",
+                    help="replay each iteration as one CUDA graph (for small per-GPU batches; needs a fixed batch size)")
 
 opt = None
 DE_IDS = {'denoise_15': 0, 'denoise_25': 1, 'denoise_50': 2, 'derain': 3, 'dehaze': 4, 'deblur': 5, 'lowlight': 6,
@@ -156,7 +158,8 @@ def train_one(step, batch, iteration, lr):
     de_id = torch.as_tensor(de_id).to(dev, non_blocking=True).long()
     alpha = alpha.to(dev, non_blocking=True)
     paired = iteration < opt.pairnum // opt.batchSize
-    return step.iteration(degraded.contiguous(), target.contiguous(), de_id, alpha, paired, lr), degraded, target
+    run = step.iteration_graphed if getattr(opt, "cuda_graph", False) else step.iteration
+    return run(degraded.contiguous(), target.contiguous(), de_id, alpha, paired, lr), degraded, target
 
 
 def train(training_data_loader, T_optimizer, F_optimizer, Tnet, Fnet, epoch):
