@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       const int ngroups = (ncols + 15) >> 4;             // 16-column groups
       uint32_t ra[16], rb[16];
       float qa[16], qb[16];                              // residual values, fetched one group ahead
+      float ln_s0 = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;       // shifted sums for the optional LayerNorm statistics
+      const bool want_stats = p.stats_out != nullptr;
       auto ldres = [&](float (&q)[16], int gi) {
         const int nrem = ncols - gi * 16;
         const float* r0 = rs + (size_t)(gi * 16) * HWr;
@@ -355,23 +357,26 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         const int nrem = ncols - gi * 16;
         if (!st_ok) return;
         float* og = o + (size_t)(gi * 16) * HWr;
-        if (epi_plain) {
+        if (epi_plain || epi_res) {
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(cur[i]) + (epi_res ? q[i] : 0.f);
           if (nrem >= 16) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) og[(size_t)i * HWr] = __uint_as_float(cur[i]);
+            for (int i = 0; i < 16; ++i) og[(size_t)i * HWr] = y[i];
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (i < nrem) og[(size_t)i * HWr] = __uint_as_float(cur[i]);
+              if (i < nrem) og[(size_t)i * HWr] = y[i];
           }
-        } else if (epi_res) {
-          if (nrem >= 16) {
+          if (want_stats) {
+            if (gi == 0) ln_s0 = y[0];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) og[(size_t)i * HWr] = __uint_as_float(cur[i]) + q[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nrem) og[(size_t)i * HWr] = __uint_as_float(cur[i]) + q[i];
+            for (int i = 0; i < 16; ++i) {
+              const float d = (i < nrem) ? y[i] - ln_s0 : 0.f;
+              ln_s1 += d;
+              ln_s2 = fmaf(d, d, ln_s2);
+            }
           }
         } else {
           const float* mg = mk ? mk + (size_t)(gi * 16) * HWr : nullptr;
@@ -408,6 +413,12 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
           }
           emit(rb, qb, gi + 1);
         }
+      }
+      if (want_stats && st_ok) {
+        const float inv = 1.f / (float)p.N;
+        const float m = ln_s1 * inv;
+        const float var = fmaxf(ln_s2 * inv - m * m, 0.f);
+        reinterpret_cast<float2*>(p.stats_out)[(size_t)b * HWr + pix] = make_float2(ln_s0 + m, 1.0f / sqrtf(var + 1e-5f));
       }
       tc_fence_before();
       __syncwarp();
@@ -485,6 +496,9 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
   if (p.ks == 1)
     RCOT_REQUIRE(p.stride == 1 && p.pad == 0 && p.Hs == p.Hr && p.Ws == p.Wr, "pm_gemm: 1x1 needs stride 1, pad 0");
   RCOT_REQUIRE(p.stride == 1 || p.stride == 2, "pm_gemm: stride must be 1 or 2");
+  if (p.stats_out)
+    RCOT_REQUIRE(p.N <= 256 && !p.bias && !p.act && !p.mask_y && !p.accumulate && p.out_coff == 0,
+                 "pm_gemm: stats_out needs N <= 256 and the plain / residual epilogue");
   if (p.tap_major)
     RCOT_REQUIRE(p.ks > 1 && p.C2 == 0 && p.C1 % 32 == 0, "pm_gemm: tap_major needs ks > 1, no concat, C1 %% 32 == 0");
 #define PM_DISPATCH(KS, MODE, LN)                                           \

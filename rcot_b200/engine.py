@@ -190,6 +190,13 @@ class BlockSpec:
                 ps.add_pack(f + n, "dgrad")
 
 
+def _stats_of(x):
+    """Per-pixel LayerNorm (mean, rstd) of x: left on the tensor by the GEMM epilogue that produced it
+    (pm_gemm stats_out), else one ln_stats launch."""
+    st = getattr(x, "_rcot_ln_stats", None)
+    return st if st is not None else ops.ln_stats(x)
+
+
 def _ln_args(ps, name, stats):
     return (stats, ps.p[name + ".body.weight"], ps.p[name + ".body.bias"])
 
@@ -202,7 +209,7 @@ def mdta_fwd(bs: BlockSpec, x, norm_name, residual, need_bwd, store=None):
     B, _, H, W = x.shape
     sc = AttnScratch.get(B, C, h, x.device)
     st = sc if store is None else store
-    stats = ops.ln_stats(x) if norm_name else None
+    stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
     pre = ops.pm_gemm(x, ps.pack(a + "qkv.weight", "fwd"), 3 * C, ln=ln)
     ops.zero_(sc.zbuf)
@@ -213,7 +220,8 @@ def mdta_fwd(bs: BlockSpec, x, norm_name, residual, need_bwd, store=None):
     ops.pk_gemm(qkv[:, :C], qkv[:, C:2 * C], sc.G, ldo=c, per_image=True, groups=h, out_gs=c * c)
     ops.attn_fwd(sc.G, st.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], st.A, st.Gt, sc.Mpack,
                  st.MTpack if need_bwd else None, B, C, h)
-    y = ops.pm_gemm(qkv[:, 2 * C:], sc.Mpack.data_ptr(), C, wpack_bs=sc.pb, residual=x if residual else None)
+    y = ops.pm_gemm(qkv[:, 2 * C:], sc.Mpack.data_ptr(), C, wpack_bs=sc.pb, residual=x if residual else None,
+                    stats_out=bool(norm_name))      # feeds LN2 of the same block
     return y, (stats, pre, qkv, sc, st)
 
 
@@ -245,12 +253,13 @@ def gdfn_fwd(bs: BlockSpec, x, norm_name, residual, keep=False):
     ps, C = bs.ps, bs.C
     f = bs.pre + "ffn."
     hid = bs.hid
-    stats = ops.ln_stats(x) if norm_name else None
+    stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
     u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
     g = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=1)
-    y = ops.pm_gemm(g, ps.pack(f + "project_out.weight", "fwd"), C, residual=x if residual else None)
-    return (y, (stats, u)) if keep else y
+    y = ops.pm_gemm(g, ps.pack(f + "project_out.weight", "fwd"), C, residual=x if residual else None,
+                    stats_out=bool(norm_name))      # feeds LN1 of the next block
+    return (y, (stats, u, g)) if keep else y
 
 
 def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual, kept=None):
@@ -259,16 +268,18 @@ def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual, kept=None):
     ps, C = bs.ps, bs.C
     f = bs.pre + "ffn."
     hid = bs.hid
+    g_kept = None
     if kept is not None:
-        stats, u = kept
+        stats, u, g_kept = kept
     else:
-        stats = ops.ln_stats(x) if norm_name else None
+        stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
     if kept is None:
         u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
     dg = ops.pm_gemm(dy, ps.pack(f + "project_out.weight", "dgrad"), hid)
-    g = torch.empty_like(dg)
-    dab = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=2, dg=dg, g_out=g, out=torch.empty_like(u))
+    g = g_kept if g_kept is not None else torch.empty_like(dg)
+    dab = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=2, dg=dg, g_out=None if g_kept is not None else g,
+                     out=torch.empty_like(u))
     ops.pk_gemm(dy, g, ps.g[f + "project_out.weight"], ldo=hid)
     del g, dg
     du = ops.dwconv_bwd(u, dab, ps.p[f + "dwconv.weight"], ps.g[f + "dwconv.weight"])

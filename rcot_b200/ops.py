@@ -30,7 +30,7 @@ class PMParams(C.Structure):
         ("out", C.c_void_p), ("out_bs", C.c_int64), ("out_coff", C.c_int32), ("act", C.c_int32),
         ("slope", C.c_float), ("accumulate", C.c_int32), ("bias", C.c_void_p),
         ("mask_y", C.c_void_p), ("mask_bs", C.c_int64), ("residual", C.c_void_p), ("res_bs", C.c_int64),
-        ("debug", C.c_int32), ("tap_major", C.c_int32),
+        ("stats_out", C.c_void_p), ("debug", C.c_int32), ("tap_major", C.c_int32),
     ]
 
 
@@ -190,7 +190,7 @@ def pack_single(w: torch.Tensor, kind: str):
 # ------------------------------------------------------------------ pixel-as-M GEMM
 def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None, out_hw=None, out_coff=0,
             ln=None, bias=None, act=False, slope=0.2, mask_y=None, residual=None, accumulate=False,
-            wpack_bs=0, terms=None, debug=0, tap_major=False):
+            wpack_bs=0, terms=None, debug=0, tap_major=False, stats_out=False):
     """out[b, coff+n, p] = epi(sum_k A(b,p,k) W[n,k]).  ``ln`` = (stats[B,HW,2], gamma, beta)."""
     B, C1, Hs, Ws = x.shape
     in_bs = _img_view(x, "x")
@@ -217,12 +217,19 @@ def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None
     p.act, p.slope, p.accumulate = int(act), slope, int(accumulate)
     p.debug = debug
     p.tap_major = int(tap_major)
+    st = None
+    if stats_out and N <= 256 and out_coff == 0:
+        # LayerNorm statistics of the output rows come out of the epilogue; the consumer finds them on the tensor
+        st = torch.empty(B, Hr * Wr, 2, device=x.device, dtype=torch.float32)
+        p.stats_out = st.data_ptr()
     p.bias = None if bias is None else _f32(bias).data_ptr()
     if mask_y is not None:
         p.mask_y, p.mask_bs = mask_y.data_ptr(), _img_view(mask_y, "mask_y")
     if residual is not None:
         p.residual, p.res_bs = residual.data_ptr(), _img_view(residual, "residual")
     _lib.check(L().rcot_pm_gemm(C.byref(p), _stream()), "pm_gemm")
+    if st is not None:
+        out._rcot_ln_stats = st
     return out
 
 

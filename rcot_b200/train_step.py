@@ -97,8 +97,8 @@ class OTTrainStep:
         Bg = B * self.world
         save = self.save_hidden
         if save is None:
-            # hidden tensors of all 102 blocks: 12.3 * 49.35 M floats per 128x128 image
-            need = 12.3 * 49.35e6 * 4 * B * (P / 128.0) ** 2
+            # hidden tensors of all 102 blocks: 15 * 49.35 M floats per 128x128 image (pre, qkv, u, g, mid-block x)
+            need = 15.0 * 49.35e6 * 4 * B * (P / 128.0) ** 2
             save = need < 0.55 * torch.cuda.get_device_properties(degraded.device).total_memory
         tape = Tape(save_hidden=bool(save))
         self._mark("T_forward")
