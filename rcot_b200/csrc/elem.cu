@@ -504,6 +504,12 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace rcot
 
+namespace rcot {   // dwconv.cu: lean kernels for aligned feature maps; return 0 when a call does not qualify
+int dwconv_fast(const rcot_dw_params& p, int planes, cudaStream_t st);
+int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w, float* din,
+                    int64_t din_bs, float* dw, int B, int Cn, int H, int W, cudaStream_t st);
+}  // namespace rcot
+
 using namespace rcot;
 
 extern "C" int rcot_ln_stats(const float* x, int64_t x_bs, int B, int C, int HW, float* stats, rcot_stream_t st) {
@@ -551,6 +557,7 @@ extern "C" int rcot_dwconv3x3(const rcot_dw_params* pp, rcot_stream_t st) {
     if (p.mode == 2) RCOT_REQUIRE(p.dg != nullptr, "dwconv3x3: gate backward needs dg");
     planes = p.hid;
   }
+  if (dwconv_fast(p, planes, (cudaStream_t)st)) return check_launch("dwconv3x3");
   if (p.W % 4 != 0 || p.H % 2 != 0) {
     RCOT_REQUIRE(p.mode != 2, "dwconv3x3: gate backward needs width %% 4 == 0 and even height, got %dx%d", p.H, p.W);
     const long tot = (long)p.B * planes * p.H * p.W;
@@ -585,6 +592,8 @@ extern "C" int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* d
                "dwconv3x3_bwd: bad arguments");
   RCOT_REQUIRE(W % 4 == 0 && H % 2 == 0 && in_bs % 4 == 0 && dout_bs % 4 == 0 && din_bs % 4 == 0,
                "dwconv3x3_bwd: width/strides must be multiples of 4 and height even");
+  if (dwconv_bwd_fast(in, in_bs, dout, dout_bs, w, din, din_bs, dw, B, Cn, H, W, (cudaStream_t)st))
+    return check_launch("dwconv3x3_bwd");
   long total = (long)B * H * W / 8;
   // enough CTAs per channel to fill the machine, at least ~4 quads per thread
   long want = (148L * 8 + Cn - 1) / Cn;
