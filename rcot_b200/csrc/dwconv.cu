@@ -207,17 +207,27 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     dw_bwd2_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
                    const float* __restrict__ w, float* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
-                   const DwGeom g) {
+                   const DwGeom g, const int ppt) {
   constexpr int ROWS = 2;
-  const DwThread t = dw_map(g, ROWS);
+  DwThread t = dw_map(g, ROWS);
   const int HW = g.H * g.W;
   float acc[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) acc[i] = 0.f;
-  if (t.active) {
-    float wf[9];
+  float wf[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) wf[i] = __ldg(w + t.ch * 9 + 8 - i);   // flipped taps
+  for (int i = 0; i < 9; ++i) wf[i] = __ldg(w + t.ch * 9 + 8 - i);   // flipped taps
+  // large planes: a thread walks `ppt` patches (stride = patches covered by the grid) before the tap sums
+  // are reduced, so the 9 warp reductions are amortised
+  for (int it = 0; it < ppt; ++it) {
+    if (it > 0) {
+      const int patch = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+      t.active = patch < g.ppp;
+      const int py = (t.active ? patch : 0) / g.pw;
+      t.y = py * ROWS;
+      t.x0 = ((t.active ? patch : 0) - py * g.pw) * 4;
+    }
+    if (!t.active) continue;
     float d[ROWS][4];
     {
       Patch<ROWS> P;
@@ -264,7 +274,8 @@ __global__ void __launch_bounds__(256)
     for (int i = 0; i < 9; ++i) {
       float s = acc[i];
       for (int o = width >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if ((threadIdx.x & (width - 1)) == 0 && t.active) atomicAdd(dw + t.ch * 9 + i, s);
+      if ((threadIdx.x & (width - 1)) == 0 && t.ch < g.planes && (threadIdx.x >> g.pshift) < (256 >> g.pshift))
+        atomicAdd(dw + t.ch * 9 + i, s);
     }
   }
 }
@@ -325,7 +336,14 @@ int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t d
   DwGeom g;
   dim3 grid;
   if (!dw_geom(g, grid, B, Cn, H, W, 2)) return 0;
-  dw_bwd2_kernel<<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g);
+  int ppt = 1;
+  if (g.pshift < 0) {   // large planes: up to 4 patches per thread
+    ppt = g.ppp / 256;
+    if (ppt > 4) ppt = 4;
+    if (ppt < 1) ppt = 1;
+    grid.x = cdiv(g.ppp, 256 * ppt);
+  }
+  dw_bwd2_kernel<<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt);
   return 1;
 }
 
