@@ -57,6 +57,12 @@ __global__ void __launch_bounds__(256)
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   constexpr int R = NCH > 0 ? NCH : 1;
+  float ag[R], ab[R];   // per-thread partial channel sums over this CTA's pixel groups (register path)
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    ag[k] = 0.f;
+    ab[k] = 0.f;
+  }
   for (int gi = 0; gi < groups; ++gi) {
     const int p = (blockIdx.x * groups + gi) * 32 + lane;
     const bool valid = p < HW;
@@ -85,12 +91,8 @@ __global__ void __launch_bounds__(256)
         const float g = rd[k] * __ldg(gamma + c);
         sg += g;
         sgx = fmaf(g, xh, sgx);
-        const float wg = warp_sum(rd[k] * xh);
-        const float wb = warp_sum(rd[k]);
-        if (lane == 0) {
-          sacc[c] += wg;
-          sacc[C + c] += wb;
-        }
+        ag[k] = fmaf(rd[k], xh, ag[k]);   // reduced over the 32 pixels of the warp once, after the group loop
+        ab[k] += rd[k];
       }
     } else {
       for (int c = wy; c < C; c += 8) {
@@ -142,6 +144,18 @@ __global__ void __launch_bounds__(256)
           if (dyp) r += dyp[(size_t)c * HW];
           dxp[(size_t)c * HW] = r;
         }
+      }
+    }
+    __syncthreads();
+  }
+  if (NCH > 0) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float wg = warp_sum(ag[k]);
+      const float wb = warp_sum(ab[k]);
+      if (lane == 0) {          // channel wy + 8k belongs to this warp alone
+        sacc[wy + 8 * k] = wg;
+        sacc[C + wy + 8 * k] = wb;
       }
     }
     __syncthreads();
