@@ -160,6 +160,14 @@ int rcot_dwconv3x3_wgrad(const float* in, int64_t in_bs, const float* dout, int6
 int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w, float* din,
                        int64_t din_bs, float* dw, int B, int Cn, int H, int W, rcot_stream_t stream);
 
+/* GDFN middle backward in one pass (Net_Restormer.py:81-83 backward): with a = dw(u[j]),
+ * b = dw(u[j+hid]): da = dg*b*gelu'(a), db = dg*gelu(a); du = dw^T([da; db]); dw += corr(u, [da; db]);
+ * g_out[j] = gelu(a)*b (optional, may be NULL).  Same arithmetic as mode 2 followed by rcot_dwconv3x3_bwd, without
+ * the [da; db] round trip through HBM.  Requires W % 32 == 0 and 16-byte aligned u / du. */
+int rcot_gdfn_mid_bwd(const float* u, int64_t u_bs, const float* dg, int64_t dg_bs, const float* w, float* du,
+                      int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
+                      rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- MDTA small-matrix steps
  * Net_Restormer.py:39-49: normalize(q), normalize(k), softmax(q k^T * temperature), attn @ v,
  * project_out -- folded into the per-image matrix M = W_out * blockdiag(A). */

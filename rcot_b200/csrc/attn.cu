@@ -37,13 +37,19 @@ __device__ __forceinline__ void store_split8(uint8_t* base, int N, int K, int n,
   *reinterpret_cast<uint4*>(base + packed_offset(N, K, n, k0, 1)) = lo;
 }
 
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p) {
-  extern __shared__ float sm[];
+// Forward.  grid = (heads, B, nsplit): every CTA of a (head, image) recomputes the c x c softmax (cheap) and
+// produces `nco` rows of M = W_out * blockdiag(A); split 0 also writes A and the normalised Gram.
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p, const int nco) {
+  extern __shared__ __align__(16) float sm[];
   const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
   float* sA = sm;            // [c*c]
   float* snq = sm + c * c;   // [c]
   float* snk = snq + c;      // [c]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int co_begin = blockIdx.z * nco;
+  const int co_end = min(C, co_begin + nco);
+  if (co_begin >= co_end) return;
+  const bool first = blockIdx.z == 0;
   const float* Gb = p.G + ((size_t)b * p.heads + h) * c * c;
   const float* ss = p.sumsq + (size_t)b * 2 * C;
   for (int i = tid; i < c; i += blockDim.x) {
@@ -57,8 +63,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p)
   for (int i = warp; i < c; i += nwarp) {  // one warp per row
     float mx = -INFINITY;
     for (int j = lane; j < c; j += 32) {
-      const float gt = Gb[i * c + j] / (snq[i] * snk[j]);
-      Gtb[i * c + j] = gt;
+      const float gt = __ldg(Gb + i * c + j) / (snq[i] * snk[j]);
+      if (first) Gtb[i * c + j] = gt;
       const float l = gt * tau;
       sA[i * c + j] = l;
       mx = fmaxf(mx, l);
@@ -75,48 +81,62 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p)
     for (int j = lane; j < c; j += 32) {
       const float a = sA[i * c + j] * inv;
       sA[i * c + j] = a;
-      Ab[i * c + j] = a;
+      if (first) Ab[i * c + j] = a;
     }
   }
   __syncthreads();
-  // M[co, (h,j)] = sum_i W_out[co, (h,i)] * A[i,j]  -> shared memory, then 16-byte packed stores
-  float* sM = snk + c;       // [C * c]
-  for (int e = tid; e < C * c; e += blockDim.x) {
-    const int co = e / c, j = e - co * c;
-    const float* wrow = p.w_out + (size_t)co * C + h * c;
-    float acc = 0.f;
-    for (int i = 0; i < c; ++i) acc = fmaf(__ldg(wrow + i), sA[i * c + j], acc);
-    sM[e] = acc;
+  // M[co, (h,j)] = sum_i W_out[co, (h,i)] * A[i,j] for this split's rows -> shared memory (four j per thread:
+  // one float4 of A per W value), then 16-byte packed stores
+  float* sM = snk + c;       // [nco * c]
+  const int c4 = c >> 2, rows = co_end - co_begin;
+  for (int t = tid; t < rows * c4; t += blockDim.x) {
+    const int col = t / c4, j0 = (t - col * c4) * 4;
+    const float* wrow = p.w_out + (size_t)(co_begin + col) * C + h * c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < c; ++i) {
+      const float w = __ldg(wrow + i);
+      const float4 a = *reinterpret_cast<const float4*>(sA + i * c + j0);
+      acc.x = fmaf(w, a.x, acc.x);
+      acc.y = fmaf(w, a.y, acc.y);
+      acc.z = fmaf(w, a.z, acc.z);
+      acc.w = fmaf(w, a.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(sM + col * c + j0) = acc;
   }
   __syncthreads();
   uint8_t* Mp = reinterpret_cast<uint8_t*>(p.Mpack) + (size_t)b * p.pack_bs;
   uint8_t* MTp = p.MTpack ? reinterpret_cast<uint8_t*>(p.MTpack) + (size_t)b * p.pack_bs : nullptr;
   const int c8 = c >> 3;
-  for (int t = tid; t < C * c8; t += blockDim.x) {          // M: row n = co, 8 consecutive k = h*c + j
-    const int co = t / c8, j0 = (t - co * c8) * 8;
-    store_split8(Mp, C, C, co, h * c + j0, sM + co * c + j0);
+  for (int t = tid; t < rows * c8; t += blockDim.x) {       // M: row n = co, 8 consecutive k = h*c + j
+    const int col = t / c8, j0 = (t - col * c8) * 8;
+    store_split8(Mp, C, C, co_begin + col, h * c + j0, sM + col * c + j0);
   }
   if (MTp) {
-    const int C8 = C >> 3;
-    for (int t = tid; t < c * C8; t += blockDim.x) {        // M^T: row n = h*c + j, 8 consecutive k = co
-      const int co0 = (t / c) * 8, j = t - (t / c) * c;
+    const int r8 = rows >> 3;                               // rows is a multiple of 8 (launcher)
+    for (int t = tid; t < c * r8; t += blockDim.x) {        // M^T: row n = h*c + j, 8 consecutive k = co
+      const int col0 = (t / c) * 8, j = t - (t / c) * c;
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = sM[(co0 + i) * c + j];
-      store_split8(MTp, C, C, h * c + j, co0, v);
+      for (int i = 0; i < 8; ++i) v[i] = sM[(col0 + i) * c + j];
+      store_split8(MTp, C, C, h * c + j, co_begin + col0, v);
     }
   }
 }
 
-constexpr int AB_CH = 16;  // rows of W_out / P staged per step in attn_bwd
+constexpr int AB_CH = 32;  // rows of W_out / P staged per step in attn_bwd
+constexpr int AB_T = 6;    // largest register tile edge: ceil(96 / 16)
 
+// Backward.  One CTA per (head, image).  Phase 1 streams W_out / P through shared memory AB_CH rows at a time and
+// runs two register-tiled products:  dA[i,j] = sum_co W_out[co,(h,i)] P[co,(h,j)]  (T x T outputs per thread,
+// T = ceil(c/16)) and  dW_out[co,(h,i)] += sum_j P[co,(h,j)] A[i,j]  (2 x T outputs per thread, A^T in shared
+// memory).  Then softmax / normalisation backward on the c x c tile and the packed W12 stores.
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
-  const int ca = c + 1;         // padded row stride of sA: conflict-free when threads differ in the row
-  float* sA = sm;               // [c*ca] softmax probabilities
-  float* sG = sA + c * ca;      // [c*c] normalised Gram
-  float* sD = sG + c * c;       // [c*c] dA -> dGt
+  const int ca = c + 1;         // padded row stride of sA: the transposing copy below stays conflict-free
+  float* sA = sm;               // [c*ca] softmax probabilities A[i][j]
+  float* sX = sA + c * ca;      // [c*c] phase 1: A^T (sX[j*c+i]); afterwards: normalised Gram
+  float* sD = sX + c * c;       // [c*c] dA -> dGt
   float* sW = sD + c * c;       // [AB_CH*c] rows of W_out[:, head block]
   float* sP = sW + AB_CH * c;   // [AB_CH*c] rows of P[:, head block]
   float* snq = sP + AB_CH * c;  // [c]
@@ -130,8 +150,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
   const float* Pm = p.P + (size_t)b * C * C;  // [co, ci]
   for (int e = tid; e < c * c; e += blockDim.x) {
     const int i = e / c, j = e - i * c;
-    sA[i * ca + j] = p.A[hb + e];
-    sG[e] = p.Gt[hb + e];
+    sA[i * ca + j] = __ldg(p.A + hb + e);
   }
   for (int i = tid; i < c; i += blockDim.x) {
     snq[i] = sqrtf(ss[h * c + i]);
@@ -139,48 +158,97 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
     srk[i] = 0.f;
   }
   if (tid == 0) s_dtau = 0.f;
-  // dA[i,j] = sum_co W_out[co,(h,i)] * P[co,(h,j)]   and   dW_out[co,(h,i)] += sum_j P[co,(h,j)] * A[i,j],
-  // streaming W_out / P through shared memory AB_CH rows at a time (coalesced along the head block).
-  constexpr int MAXO = 36;  // ceil(96*96/256)
-  float acc[MAXO];
+  __syncthreads();
+  for (int e = tid; e < c * c; e += blockDim.x) {
+    const int j = e / c, i = e - j * c;
+    sX[e] = sA[i * ca + j];
+  }
+  const int T = (c + 15) >> 4;            // register tile edge (<= AB_T)
+  const int nt = (c + T - 1) / T;         // tiles per dimension (<= 16)
+  // dA role: thread (ti, tj) owns rows ti*T.., columns tj*T.. of dA
+  const int ti = tid / nt, tj = tid - ti * nt;
+  const bool da_on = ti < nt;
+  int ia[AB_T], ja[AB_T];
 #pragma unroll
-  for (int o = 0; o < MAXO; ++o) acc[o] = 0.f;
-  const int nout = (c * c + 255) / 256;
+  for (int q = 0; q < AB_T; ++q) {
+    ia[q] = min(ti * T + q, c - 1);       // clamped: duplicates are never stored
+    ja[q] = min(tj * T + q, c - 1);
+  }
+  // dW_out role: thread (rg, ig) owns staged rows 2rg, 2rg+1 and head columns ig*T..
+  const int rg = tid >> 4, ig = tid & 15;
+  int iw[AB_T];
+#pragma unroll
+  for (int q = 0; q < AB_T; ++q) iw[q] = min(ig * T + q, c - 1);
+  float acc[AB_T][AB_T];
+#pragma unroll
+  for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+    for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
   for (int co0 = 0; co0 < C; co0 += AB_CH) {
     __syncthreads();
     for (int e = tid; e < AB_CH * c; e += blockDim.x) {
       const int r = e / c, i = e - r * c;
-      sW[e] = __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i);
-      sP[e] = __ldg(Pm + (size_t)(co0 + r) * C + h * c + i);
+      const bool in = co0 + r < C;        // a partial last chunk is zero-filled
+      sW[e] = in ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;
+      sP[e] = in ? __ldg(Pm + (size_t)(co0 + r) * C + h * c + i) : 0.f;
     }
     __syncthreads();
+    if (da_on) {
+#pragma unroll 4
+      for (int r = 0; r < AB_CH; ++r) {
+        float wv[AB_T], pv[AB_T];
 #pragma unroll
-    for (int o = 0; o < MAXO; ++o) {
-      if (o < nout) {
-        const int e = tid + o * 256;
-        if (e < c * c) {
-          const int i = e / c, j = e - i * c;
-          float a = acc[o];
-#pragma unroll 8
-          for (int r = 0; r < AB_CH; ++r) a = fmaf(sW[r * c + i], sP[r * c + j], a);
-          acc[o] = a;
+        for (int q = 0; q < AB_T; ++q)
+          if (q < T) {
+            wv[q] = sW[r * c + ia[q]];
+            pv[q] = sP[r * c + ja[q]];
+          }
+#pragma unroll
+        for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+          for (int y = 0; y < AB_T; ++y)
+            if (x < T && y < T) acc[x][y] = fmaf(wv[x], pv[y], acc[x][y]);
+      }
+    }
+    {
+      float aw[2][AB_T];
+#pragma unroll
+      for (int q = 0; q < AB_T; ++q) aw[0][q] = aw[1][q] = 0.f;
+      const float* p0 = sP + (2 * rg) * c;
+      const float* p1 = p0 + c;
+#pragma unroll 4
+      for (int j = 0; j < c; ++j) {
+        const float x0 = p0[j], x1 = p1[j];
+        const float* at = sX + j * c;
+#pragma unroll
+        for (int q = 0; q < AB_T; ++q)
+          if (q < T) {
+            const float a = at[iw[q]];
+            aw[0][q] = fmaf(x0, a, aw[0][q]);
+            aw[1][q] = fmaf(x1, a, aw[1][q]);
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int co = co0 + 2 * rg + k;
+        if (co < C) {
+#pragma unroll
+          for (int q = 0; q < AB_T; ++q)
+            if (q < T && ig * T + q < c) atomicAdd(p.dw_out + (size_t)co * C + h * c + ig * T + q, aw[k][q]);
         }
       }
     }
-    for (int e = tid; e < AB_CH * c; e += blockDim.x) {
-      const int r = e / c, i = e - r * c;
-      const float* prow = sP + r * c;
-      const float* arow = sA + i * ca;
-      float a = 0.f;
-      for (int j = 0; j < c; ++j) a = fmaf(prow[j], arow[j], a);
-      atomicAdd(p.dw_out + (size_t)(co0 + r) * C + h * c + i, a);
-    }
   }
+  __syncthreads();                          // phase 1 done with sX (A^T) and the staged rows
+  if (da_on) {
 #pragma unroll
-  for (int o = 0; o < MAXO; ++o) {
-    const int e = tid + o * 256;
-    if (o < nout && e < c * c) sD[e] = acc[o];
+    for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+      for (int y = 0; y < AB_T; ++y)
+        if (x < T && y < T && ti * T + x < c && tj * T + y < c) sD[(ti * T + x) * c + tj * T + y] = acc[x][y];
   }
+  float* sG = sX;
+  for (int e = tid; e < c * c; e += blockDim.x) sG[e] = __ldg(p.Gt + hb + e);
   __syncthreads();
   const float tau = __ldg(p.temperature + h);
   float dtau = 0.f;
@@ -257,8 +325,14 @@ extern "C" int rcot_attn_fwd(const rcot_attn_params* pp, rcot_stream_t st) {
   if (rc) return rc;
   RCOT_REQUIRE(p.G && p.Mpack, "attn_fwd: null pointer");
   const int c = p.C / p.heads;
-  const size_t smem = ((size_t)c * c + 2 * c + (size_t)p.C * c) * sizeof(float);
   RCOT_REQUIRE(c % 8 == 0 && p.C % 8 == 0, "attn_fwd: channels per head must be a multiple of 8");
+  // rows of M per CTA: enough CTAs to cover the 148 SMs, a multiple of 8 rows each (packed 16-byte stores)
+  int nsplit = cdiv(148, (long)p.heads * p.B);
+  if (nsplit > p.C / 8) nsplit = p.C / 8;
+  if (nsplit < 1) nsplit = 1;
+  const int nco = round_up(cdiv(p.C, nsplit), 8);
+  nsplit = cdiv(p.C, nco);
+  const size_t smem = ((size_t)c * c + 2 * c + (size_t)nco * c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -268,8 +342,8 @@ extern "C" int rcot_attn_fwd(const rcot_attn_params* pp, rcot_stream_t st) {
     }
     attr_set = true;
   }
-  dim3 grid(p.heads, p.B);
-  attn_fwd_kernel<<<grid, 256, smem, (cudaStream_t)st>>>(p);
+  dim3 grid(p.heads, p.B, nsplit);
+  attn_fwd_kernel<<<grid, 256, smem, (cudaStream_t)st>>>(p, nco);
   return check_launch("attn_fwd");
 }
 
@@ -280,8 +354,8 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
   if (rc) return rc;
   RCOT_REQUIRE(p.P && p.dw_out && p.dtemperature && p.W12pack, "attn_bwd: null pointer");
   const int c = p.C / p.heads;
-  RCOT_REQUIRE(p.C % AB_CH == 0, "attn_bwd: C must be a multiple of %d", AB_CH);
-  const size_t smem = ((size_t)c * (c + 1) + 2 * c * c + 2 * AB_CH * c + 4 * c) * sizeof(float);
+  RCOT_REQUIRE(c % 8 == 0, "attn_bwd: channels per head must be a multiple of 8");
+  const size_t smem = ((size_t)3 * c * c + c + 2 * AB_CH * c + 4 * c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

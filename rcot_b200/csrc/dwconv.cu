@@ -280,6 +280,159 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------ GDFN middle backward, fused
+// Everything between the two 1x1 GEMMs of GDFN's backward in ONE pass over the hidden tensor:
+//     a = dw(u_j), b = dw(u_{j+hid});  da = dg*b*gelu'(a), db = dg*gelu(a);
+//     du_j = dw^T(da), du_{j+hid} = dw^T(db);  dW_dw += corr(u, [da; db]);  optionally g = gelu(a)*b.
+// The two-kernel form (dw_gate<2> then dw_bwd2) writes [da; db] to HBM and reads it and u again; here a CTA owns a
+// 32-row band of one channel pair of one image and walks it in 32x32 tiles: u with a 2-pixel halo goes to shared
+// memory once (both channels), [da; db] is produced on the tile plus a 1-pixel halo into shared memory, and the
+// transposed stencil and the 9-tap weight-gradient sums read both from there.  HBM traffic: u and dg in, du out.
+constexpr int GF_T = 32;            // tile edge
+constexpr int GF_UW = GF_T + 8;     // u region row stride: image columns x0-4 .. x0+35 (float4 aligned)
+constexpr int GF_UH = GF_T + 4;     // u region rows y0-2 .. y0+33
+constexpr int GF_DC = GF_T + 2;     // [da; db] region columns x0-1 .. x0+32
+constexpr int GF_DW = GF_T + 4;     // its row stride (16-byte aligned rows)
+constexpr int GF_DH = GF_T + 2;     // its rows y0-1 .. y0+32
+
+__global__ void __launch_bounds__(256, 4)
+    gdfn_mid_bwd_kernel(const float* __restrict__ u, int64_t u_bs, const float* __restrict__ dg, int64_t dg_bs,
+                        const float* __restrict__ w, float* __restrict__ du, int64_t du_bs, float* __restrict__ dw,
+                        float* __restrict__ g_out, int64_t g_bs, int hid, int H, int W) {
+  __shared__ __align__(16) float su[2][GF_UH][GF_UW];
+  __shared__ __align__(16) float sd[2][GF_DH][GF_DW];
+  __shared__ float red[18][8];
+  const int tid = threadIdx.x;
+  const int ch = blockIdx.y, b = blockIdx.z;
+  const int y0 = blockIdx.x * GF_T;
+  const int th = min(GF_T, H - y0);
+  const int HW = H * W;
+  const float* ua = u + (size_t)b * u_bs + (size_t)ch * HW;
+  const float* ub = ua + (size_t)hid * HW;
+  const float* dgp = dg + (size_t)b * dg_bs + (size_t)ch * HW;
+  float* dua = du + (size_t)b * du_bs + (size_t)ch * HW;
+  float* dub = dua + (size_t)hid * HW;
+  float* gp = g_out ? g_out + (size_t)b * g_bs + (size_t)ch * HW : nullptr;
+  float wk[2][9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    wk[0][i] = __ldg(w + ch * 9 + i);
+    wk[1][i] = __ldg(w + (ch + hid) * 9 + i);
+  }
+  float acc[2][9];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[c][i] = 0.f;
+  const int ty = tid >> 3, k4 = (tid & 7) * 4;   // stencil role: row ty, columns k4 .. k4+3 of the tile
+  const int nrow_u = th + 4, npos = (th + 2) * GF_DC;
+  for (int x0 = 0; x0 < W; x0 += GF_T) {
+    __syncthreads();                             // previous tile fully consumed
+    // ---- 1: u (both channels) with a 2-pixel halo, zero outside the image
+    for (int e = tid; e < nrow_u * (GF_UW / 4); e += 256) {
+      const int r = e / (GF_UW / 4), q = e - r * (GF_UW / 4);
+      const int y = y0 - 2 + r, x = x0 - 4 + 4 * q;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+        va = __ldg(reinterpret_cast<const float4*>(ua + y * W + x));
+        vb = __ldg(reinterpret_cast<const float4*>(ub + y * W + x));
+      }
+      *reinterpret_cast<float4*>(&su[0][r][4 * q]) = va;
+      *reinterpret_cast<float4*>(&su[1][r][4 * q]) = vb;
+    }
+    __syncthreads();
+    // ---- 2: [da; db] on the tile plus a 1-pixel halo (zero outside the image), one position per thread
+    for (int idx = tid; idx < npos; idx += 256) {
+      const int r = idx / GF_DC, cx = idx - r * GF_DC;
+      const int y = y0 - 1 + r, x = x0 - 1 + cx;
+      float da = 0.f, db = 0.f;
+      if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+        float a = 0.f, bb = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            a = fmaf(su[0][r + ky][cx + 2 + kx], wk[0][ky * 3 + kx], a);
+            bb = fmaf(su[1][r + ky][cx + 2 + kx], wk[1][ky * 3 + kx], bb);
+          }
+        const float d = __ldg(dgp + y * W + x);
+        const float ga = gelu_erf_d(a);
+        da = d * bb * gelu_erf_grad_d(a);
+        db = d * ga;
+        if (gp && r >= 1 && r <= th && cx >= 1 && cx <= GF_T) gp[y * W + x] = ga * bb;
+      }
+      sd[0][r][cx] = da;
+      sd[1][r][cx] = db;
+    }
+    __syncthreads();
+    // ---- 3: du = dw^T([da; db]) and the tap sums of dW, a 4-pixel strip per thread and channel
+    if (ty < th && x0 + k4 < W) {
+      const int y = y0 + ty;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float D[3][6];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float4 m = *reinterpret_cast<const float4*>(&sd[c][ty + ky][k4]);
+          const float2 e2 = *reinterpret_cast<const float2*>(&sd[c][ty + ky][k4 + 4]);
+          D[ky][0] = m.x; D[ky][1] = m.y; D[ky][2] = m.z; D[ky][3] = m.w; D[ky][4] = e2.x; D[ky][5] = e2.y;
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float s = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) s = fmaf(D[ky][j + kx], wk[c][8 - (ky * 3 + kx)], s);
+          o[j] = s;
+        }
+        *reinterpret_cast<float4*>((c == 0 ? dua : dub) + y * W + x0 + k4) = make_float4(o[0], o[1], o[2], o[3]);
+        float Q[3][6];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float* row = &su[c][ty + 1 + ky][k4 + 3];
+          const float4 m = *reinterpret_cast<const float4*>(row + 1);
+          Q[ky][0] = row[0]; Q[ky][1] = m.x; Q[ky][2] = m.y; Q[ky][3] = m.z; Q[ky][4] = m.w; Q[ky][5] = row[5];
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[c][ky * 3 + kx] = fmaf(D[1][j + 1], Q[ky][j + kx], acc[c][ky * 3 + kx]);
+      }
+    }
+  }
+  // ---- 18 tap sums of the band: warp shuffles, then one atomicAdd per tap
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float s = warp_sum_dw(acc[c][i]);
+      if (lane == 0) red[c * 9 + i][wid] = s;
+    }
+  __syncthreads();
+  if (tid < 18) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[tid][k];
+    atomicAdd(dw + (tid < 9 ? ch * 9 + tid : (ch + hid) * 9 + tid - 9), s);
+  }
+}
+
+// Returns 1 if the fused kernel handled the call, 0 if the geometry does not qualify.
+int gdfn_mid_bwd_fast(const float* u, int64_t u_bs, const float* dg, int64_t dg_bs, const float* w, float* du,
+                      int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
+                      cudaStream_t st) {
+  if (W % GF_T != 0 || B > 65535 || hid > 65535) return 0;
+  if (u_bs % 4 != 0 || du_bs % 4 != 0 || ((uintptr_t)u % 16 != 0) || ((uintptr_t)du % 16 != 0)) return 0;
+  dim3 grid(cdiv(H, GF_T), hid, B);
+  gdfn_mid_bwd_kernel<<<grid, 256, 0, st>>>(u, u_bs, dg, dg_bs, w, du, du_bs, dw, g_out, g_bs, hid, H, W);
+  return 1;
+}
+
 // ------------------------------------------------------------------ launch geometry
 static bool dw_geom(DwGeom& g, dim3& grid, int B, int planes, int H, int W, int rows) {
   if (W % 4 != 0 || H % rows != 0 || B > 65535) return false;

@@ -520,6 +520,9 @@ __global__ void __launch_bounds__(256)
 
 namespace rcot {   // dwconv.cu: lean kernels for aligned feature maps; return 0 when a call does not qualify
 int dwconv_fast(const rcot_dw_params& p, int planes, cudaStream_t st);
+int gdfn_mid_bwd_fast(const float* u, int64_t u_bs, const float* dg, int64_t dg_bs, const float* w, float* du,
+                      int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
+                      cudaStream_t st);
 int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w, float* din,
                     int64_t din_bs, float* dw, int B, int Cn, int H, int W, cudaStream_t st);
 }  // namespace rcot
@@ -617,6 +620,18 @@ extern "C" int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* d
   dim3 grid(chunks, Cn);
   dw_bwd_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, B, H, W);
   return check_launch("dwconv3x3_bwd");
+}
+
+extern "C" int rcot_gdfn_mid_bwd(const float* u, int64_t u_bs, const float* dg, int64_t dg_bs, const float* w, float* du,
+                                 int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
+                                 rcot_stream_t st) {
+  RCOT_REQUIRE(u && dg && w && du && dw && B > 0 && hid > 0 && H > 0 && W > 0, "gdfn_mid_bwd: bad arguments");
+  RCOT_REQUIRE(W % 32 == 0 && B <= 65535 && hid <= 65535, "gdfn_mid_bwd: needs width %% 32 == 0 (got %dx%d)", H, W);
+  RCOT_REQUIRE(u_bs % 4 == 0 && du_bs % 4 == 0 && ((uintptr_t)u % 16 == 0) && ((uintptr_t)du % 16 == 0),
+               "gdfn_mid_bwd: u and du must be 16-byte aligned");
+  RCOT_REQUIRE(gdfn_mid_bwd_fast(u, u_bs, dg, dg_bs, w, du, du_bs, dw, g_out, g_bs, B, hid, H, W, (cudaStream_t)st) == 1,
+               "gdfn_mid_bwd: geometry not supported");
+  return check_launch("gdfn_mid_bwd");
 }
 
 extern "C" int rcot_pixel_shuffle(const float* in, int64_t in_bs, float* out, int64_t out_bs, int B, int C, int H,

@@ -12,9 +12,15 @@ T_net.forward :328-434.  Algebra: SURVEY.md Appendix A.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
+
+# RCOT_FUSED_GDFN_MID=0 selects the two-kernel form of GDFN's middle backward (kept for A/B timing and as the
+# path for feature maps whose width is not a multiple of 32).
+FUSED_GDFN_MID = os.environ.get("RCOT_FUSED_GDFN_MID", "1") != "0"
 
 
 # ---------------------------------------------------------------------------------- parameters
@@ -278,12 +284,19 @@ def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual, kept=None):
         u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
     dg = ops.pm_gemm(dy, ps.pack(f + "project_out.weight", "dgrad"), hid)
     g = g_kept if g_kept is not None else torch.empty_like(dg)
-    dab = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=2, dg=dg, g_out=None if g_kept is not None else g,
-                     out=torch.empty_like(u))
-    ops.pk_gemm(dy, g, ps.g[f + "project_out.weight"], ldo=hid)
-    del g, dg
-    du = ops.dwconv_bwd(u, dab, ps.p[f + "dwconv.weight"], ps.g[f + "dwconv.weight"])
-    del dab, u
+    if FUSED_GDFN_MID and ops.gdfn_mid_ok(u):
+        # gate backward + transposed depthwise conv + its weight gradient in one pass over u (no [da; db] in HBM)
+        du = ops.gdfn_mid_bwd(u, dg, ps.p[f + "dwconv.weight"], ps.g[f + "dwconv.weight"],
+                              g_out=None if g_kept is not None else g)
+        ops.pk_gemm(dy, g, ps.g[f + "project_out.weight"], ldo=hid)
+        del g, dg, u
+    else:
+        dab = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=2, dg=dg, g_out=None if g_kept is not None else g,
+                         out=torch.empty_like(u))
+        ops.pk_gemm(dy, g, ps.g[f + "project_out.weight"], ldo=hid)
+        del g, dg
+        du = ops.dwconv_bwd(u, dab, ps.p[f + "dwconv.weight"], ps.g[f + "dwconv.weight"])
+        del dab, u
     ops.pk_gemm(du, x, ps.g[f + "project_in.weight"], ldo=C, ln=ln)
     dz = ops.pm_gemm(du, ps.pack(f + "project_in.weight", "dgrad"), C,
                      residual=None if norm_name or not residual else dy)

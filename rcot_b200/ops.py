@@ -316,6 +316,23 @@ def dwconv_bwd(x, dout, w, dw):
     return din
 
 
+def gdfn_mid_ok(u):
+    """Geometry the fused GDFN middle backward accepts (every level of a training patch whose width is a multiple of 32)."""
+    return u.shape[3] % 32 == 0 and u.data_ptr() % 16 == 0 and _img_view(u, "u") % 4 == 0
+
+
+def gdfn_mid_bwd(u, dg, w, dw, g_out=None):
+    """du = dw^T(gate'(dw(u)) * dg), dw += corr(u, .), optionally g_out = gelu(a)*b: one pass (csrc/dwconv.cu)."""
+    B, Cn, H, W = u.shape
+    hid = Cn // 2
+    du = torch.empty_like(u)
+    _lib.check(L().rcot_gdfn_mid_bwd(_ptr(u), C.c_int64(_img_view(u, "u")), _ptr(dg), C.c_int64(_img_view(dg, "dg")),
+                                     _ptr(_f32(w)), _ptr(du), C.c_int64(_img_view(du, "du")), _ptr(_f32(dw)),
+                                     _ptr(g_out), C.c_int64(_img_view(g_out, "g_out") if g_out is not None else 0),
+                                     B, hid, H, W, _stream()), "gdfn_mid_bwd")
+    return du
+
+
 # ------------------------------------------------------------------ MDTA small-matrix steps
 def attn_fwd(G, sumsq, temperature, w_out, A, Gt, Mpack, MTpack, B, Cc, heads):
     p = AttnParams()
@@ -513,6 +530,7 @@ ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(
 dwconv = _instrument("dwconv", lambda a, k, r: _nb(a[0], r, k.get("dg"), k.get("g_out")))(dwconv)
 dwconv_wgrad = _instrument("dwconv_wgrad", lambda a, k, r: _nb(a[0], a[1]))(dwconv_wgrad)
 dwconv_bwd = _instrument("dwconv_bwd", lambda a, k, r: _nb(a[0], a[1], r))(dwconv_bwd)
+gdfn_mid_bwd = _instrument("gdfn_mid_bwd", lambda a, k, r: _nb(a[0], a[1], r, k.get("g_out")))(gdfn_mid_bwd)
 attn_fwd = _instrument("attn_fwd", lambda a, k, r: _nb(a[0], a[3]) * 2)(attn_fwd)
 attn_bwd = _instrument("attn_bwd", lambda a, k, r: _nb(a[0], a[3]) * 3)(attn_bwd)
 pixel_shuffle = _instrument("pixel_shuffle", lambda a, k, r: _nb(a[0], a[0]))(pixel_shuffle)

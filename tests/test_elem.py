@@ -177,3 +177,69 @@ def test_dwconv_odd_sizes(cuda_lib):
     _close("plain", ops.dwconv(u.cuda(), w.cuda(), sumsq=sumsq, nsq=6), full)
     _close("sumsq", sumsq, (full[:, :6] ** 2).sum((2, 3)))
     _close("gate", ops.dwconv(u.cuda(), w.cuda(), mode=1), F.gelu(a) * b)
+
+
+@pytest.mark.parametrize("B,K,O", [(64, 8192, 2048), (32, 2048, 64), (5, 64, 1), (70, 136, 37), (3, 50, 7)])
+def test_linear_kernels(cuda_lib, B, K, O):
+    """F_net's fully connected tail (Net_Restormer.py:496-498,512-520): tiled fp32 GEMM forward (bias, LeakyReLU,
+    mask; reduction split with atomics on the wide layer), data gradient and weight gradient vs fp64."""
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(B + K + O)
+    x = torch.randn(B, K, generator=g)
+    W = torch.randn(O, K, generator=g) / K ** 0.5
+    bias = torch.randn(O, generator=g)
+    dy = torch.randn(B, O, generator=g)
+    mo = torch.randn(B, O, generator=g)
+    mk = torch.randn(B, K, generator=g)
+    x64, W64, b64 = x.double(), W.double(), bias.double()
+    lin = x64 @ W64.t() + b64
+    xd, Wd, bd = x.cuda(), W.cuda(), bias.cuda()
+    _close("fwd bias", ops.linear_fwd(xd, Wd, bd), lin)
+    _close("fwd nobias", ops.linear_fwd(xd, Wd), x64 @ W64.t())
+    _close("fwd act", ops.linear_fwd(xd, Wd, bd, act=True), F.leaky_relu(lin, 0.2))
+    fac_o = torch.where(mo > 0, 1.0, 0.2).double()
+    _close("fwd mask", ops.linear_fwd(xd, Wd, mask=mo.cuda()), (x64 @ W64.t()) * fac_o)
+    fac_k = torch.where(mk > 0, 1.0, 0.2).double()
+    _close("dgrad", ops.linear_dgrad(dy.cuda(), Wd), dy.double() @ W64)
+    _close("dgrad mask", ops.linear_dgrad(dy.cuda(), Wd, mask=mk.cuda()), (dy.double() @ W64) * fac_k)
+    dW = torch.ones(O, K, device="cuda")
+    db = torch.ones(O, device="cuda")
+    ops.linear_wgrad(dy.cuda(), xd, dW, db)
+    _close("wgrad", dW, 1 + dy.double().t() @ x64)
+    _close("bgrad", db, 1 + dy.double().sum(0))
+
+
+@pytest.mark.parametrize("B,hid,H,W,with_g", [(2, 5, 32, 32, True), (2, 3, 48, 64, False), (1, 4, 8, 32, True),
+                                              (2, 2, 128, 128, True)])
+def test_gdfn_mid_bwd_fused(cuda_lib, B, hid, H, W, with_g):
+    """Gate backward + transposed depthwise conv + its weight gradient in one kernel vs autograd (fp64), and
+    against the two-kernel form it replaces (same taps in the same order)."""
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(H + W + hid)
+    Cn = 2 * hid
+    u = torch.randn(B, Cn, H, W, generator=g)
+    w = torch.randn(Cn, 1, 3, 3, generator=g) / 3
+    dgate = torch.randn(B, hid, H, W, generator=g)
+    u64, w64 = u.double().requires_grad_(True), w.double().requires_grad_(True)
+    a, b = F.conv2d(u64, w64, padding=1, groups=Cn).chunk(2, 1)
+    gate = F.gelu(a) * b
+    gate.backward(dgate.double())
+    ud, wd, dgd = u.cuda(), w.cuda(), dgate.cuda()
+    assert ops.gdfn_mid_ok(ud)
+    prev = torch.randn(Cn, 1, 3, 3, generator=g)
+    dw = prev.cuda().clone()
+    gout = torch.full((B, hid, H, W), float("nan"), device="cuda") if with_g else None
+    du = ops.gdfn_mid_bwd(ud, dgd, wd, dw, g_out=gout)
+    _close("du", du, u64.grad)
+    _close("dw", dw, prev.double() + w64.grad, rtol=2e-3)
+    if with_g:
+        _close("g_out", gout, gate.detach())
+    # the two-kernel form: same taps in the same order -> identical du and g
+    g2 = torch.empty(B, hid, H, W, device="cuda")
+    dab = ops.dwconv(ud, wd, mode=2, dg=dgd, g_out=g2, out=torch.empty_like(ud))
+    dw2 = prev.cuda().clone()
+    du2 = ops.dwconv_bwd(ud, dab, wd, dw2)
+    torch.testing.assert_close(du, du2, rtol=1e-5, atol=1e-6)
+    if with_g:
+        torch.testing.assert_close(gout, g2, rtol=1e-5, atol=1e-6)
+    _close("dw vs two-kernel", dw, dw2.cpu().double(), rtol=2e-3)
