@@ -286,21 +286,37 @@ __global__ void __launch_bounds__(256)
 //     du_j = dw^T(da), du_{j+hid} = dw^T(db);  dW_dw += corr(u, [da; db]);  optionally g = gelu(a)*b.
 // The two-kernel form (dw_gate<2> then dw_bwd2) writes [da; db] to HBM and reads it and u again; here a CTA owns a
 // 32-row band of one channel pair of one image and walks it in 32x32 tiles: u with a 2-pixel halo goes to shared
-// memory once (both channels), [da; db] is produced on the tile plus a 1-pixel halo into shared memory, and the
-// transposed stencil and the 9-tap weight-gradient sums read both from there.  HBM traffic: u and dg in, du out.
+// memory once (both channels), [da; db] is produced on the tile plus a 1-pixel halo into shared memory (4-pixel
+// strips per thread: float4 shared-memory reads, one float4 of dg), and the transposed stencil and the 9-tap
+// weight-gradient sums read both from there.  HBM traffic: u and dg in, du out.
 constexpr int GF_T = 32;            // tile edge
-constexpr int GF_UW = GF_T + 8;     // u region row stride: image columns x0-4 .. x0+35 (float4 aligned)
+constexpr int GF_LD = GF_T + 8;     // row stride of both regions: image columns x0-4 .. x0+35 (index = x - x0 + 4)
 constexpr int GF_UH = GF_T + 4;     // u region rows y0-2 .. y0+33
-constexpr int GF_DC = GF_T + 2;     // [da; db] region columns x0-1 .. x0+32
-constexpr int GF_DW = GF_T + 4;     // its row stride (16-byte aligned rows)
-constexpr int GF_DH = GF_T + 2;     // its rows y0-1 .. y0+32
+constexpr int GF_DH = GF_T + 2;     // [da; db] region rows y0-1 .. y0+32 (columns x0-1 .. x0+32 are used)
+
+// gelu(a) = a*Phi(a) and gelu'(a) = Phi(a) + a*phi(a) from ONE exponential: Phi through the Abramowitz-Stegun
+// 7.1.26 rational form of erfc (absolute error 1.5e-7 in erf, i.e. < 1e-7 in Phi -- fp32 rounding level), whose
+// exp(-a^2/2) factor is the same one phi needs.
+__device__ __forceinline__ void gelu_pair(float a, float& ge, float& dge) {
+  const float x = fabsf(a) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.f));
+  const float e = __expf(-x * x);
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float tail = 0.5f * q * t * e;            // Phi(-|a|)
+  const float Phi = a >= 0.f ? 1.f - tail : tail;
+  ge = a * Phi;
+  dge = fmaf(a * 0.39894228040143268f, e, Phi);
+}
 
 __global__ void __launch_bounds__(256, 4)
     gdfn_mid_bwd_kernel(const float* __restrict__ u, int64_t u_bs, const float* __restrict__ dg, int64_t dg_bs,
                         const float* __restrict__ w, float* __restrict__ du, int64_t du_bs, float* __restrict__ dw,
                         float* __restrict__ g_out, int64_t g_bs, int hid, int H, int W) {
-  __shared__ __align__(16) float su[2][GF_UH][GF_UW];
-  __shared__ __align__(16) float sd[2][GF_DH][GF_DW];
+  __shared__ __align__(16) float su[2][GF_UH][GF_LD];
+  __shared__ __align__(16) float sd[2][GF_DH][GF_LD];
   __shared__ float red[18][8];
   const int tid = threadIdx.x;
   const int ch = blockIdx.y, b = blockIdx.z;
@@ -325,12 +341,19 @@ __global__ void __launch_bounds__(256, 4)
 #pragma unroll
     for (int i = 0; i < 9; ++i) acc[c][i] = 0.f;
   const int ty = tid >> 3, k4 = (tid & 7) * 4;   // stencil role: row ty, columns k4 .. k4+3 of the tile
-  const int nrow_u = th + 4, npos = (th + 2) * GF_DC;
+  const int nrow_u = th + 4, nrow_d = th + 2;
+  const int n_strip = nrow_d * 8;                // step 2: eight 4-pixel strips per row ...
+  const int edge0 = (n_strip + 31) & ~31;        // ... then (warp aligned) one task per row for the two halo columns
+  // Six values around a 4-pixel strip (columns x-1 .. x+4) of one region row
+  auto row6 = [](const float* row, float (&v)[6]) {
+    const float4 m = *reinterpret_cast<const float4*>(row + 1);
+    v[0] = row[0]; v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w; v[5] = row[5];
+  };
   for (int x0 = 0; x0 < W; x0 += GF_T) {
     __syncthreads();                             // previous tile fully consumed
     // ---- 1: u (both channels) with a 2-pixel halo, zero outside the image
-    for (int e = tid; e < nrow_u * (GF_UW / 4); e += 256) {
-      const int r = e / (GF_UW / 4), q = e - r * (GF_UW / 4);
+    for (int e = tid; e < nrow_u * (GF_LD / 4); e += 256) {
+      const int r = e / (GF_LD / 4), q = e - r * (GF_LD / 4);
       const int y = y0 - 2 + r, x = x0 - 4 + 4 * q;
       float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
       if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
@@ -341,42 +364,82 @@ __global__ void __launch_bounds__(256, 4)
       *reinterpret_cast<float4*>(&su[1][r][4 * q]) = vb;
     }
     __syncthreads();
-    // ---- 2: [da; db] on the tile plus a 1-pixel halo (zero outside the image), one position per thread
-    for (int idx = tid; idx < npos; idx += 256) {
-      const int r = idx / GF_DC, cx = idx - r * GF_DC;
-      const int y = y0 - 1 + r, x = x0 - 1 + cx;
-      float da = 0.f, db = 0.f;
-      if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
-        float a = 0.f, bb = 0.f;
+    // ---- 2: [da; db] on the tile plus a 1-pixel halo (zero outside the image)
+    for (int t = tid; t < edge0 + nrow_d; t += 256) {
+      if (t < n_strip) {
+        const int r = t >> 3, sx = (t & 7) * 4;  // region row, tile column of the strip
+        const int y = y0 - 1 + r;
+        float4 da4 = make_float4(0.f, 0.f, 0.f, 0.f), db4 = da4;
+        if ((unsigned)y < (unsigned)H) {
+          float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+          for (int ky = 0; ky < 3; ++ky) {
+            float v0[6], v1[6];
+            row6(&su[0][r + ky][sx + 3], v0);
+            row6(&su[1][r + ky][sx + 3], v1);
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            a = fmaf(su[0][r + ky][cx + 2 + kx], wk[0][ky * 3 + kx], a);
-            bb = fmaf(su[1][r + ky][cx + 2 + kx], wk[1][ky * 3 + kx], bb);
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                a[j] = fmaf(v0[j + kx], wk[0][ky * 3 + kx], a[j]);
+                bb[j] = fmaf(v1[j + kx], wk[1][ky * 3 + kx], bb[j]);
+              }
           }
-        const float d = __ldg(dgp + y * W + x);
-        const float ga = gelu_erf_d(a);
-        da = d * bb * gelu_erf_grad_d(a);
-        db = d * ga;
-        if (gp && r >= 1 && r <= th && cx >= 1 && cx <= GF_T) gp[y * W + x] = ga * bb;
+          const float4 d4 = __ldg(reinterpret_cast<const float4*>(dgp + y * W + x0 + sx));
+          const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+          float da[4], db[4], gg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float ge, dge;
+            gelu_pair(a[j], ge, dge);
+            da[j] = d[j] * bb[j] * dge;
+            db[j] = d[j] * ge;
+            gg[j] = ge * bb[j];
+          }
+          da4 = make_float4(da[0], da[1], da[2], da[3]);
+          db4 = make_float4(db[0], db[1], db[2], db[3]);
+          if (gp && r >= 1 && r <= th)
+            *reinterpret_cast<float4*>(gp + y * W + x0 + sx) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+        }
+        *reinterpret_cast<float4*>(&sd[0][r][sx + 4]) = da4;
+        *reinterpret_cast<float4*>(&sd[1][r][sx + 4]) = db4;
+      } else if (t >= edge0) {
+        const int r = t - edge0;
+        const int y = y0 - 1 + r;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int ci = side == 0 ? 3 : GF_T + 4;        // region column index of x0-1 / x0+32
+          const int x = x0 - 4 + ci;
+          float da = 0.f, db = 0.f;
+          if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+            float a = 0.f, bb = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                a = fmaf(su[0][r + ky][ci - 1 + kx], wk[0][ky * 3 + kx], a);
+                bb = fmaf(su[1][r + ky][ci - 1 + kx], wk[1][ky * 3 + kx], bb);
+              }
+            const float d = __ldg(dgp + y * W + x);
+            float ge, dge;
+            gelu_pair(a, ge, dge);
+            da = d * bb * dge;
+            db = d * ge;
+          }
+          sd[0][r][ci] = da;
+          sd[1][r][ci] = db;
+        }
       }
-      sd[0][r][cx] = da;
-      sd[1][r][cx] = db;
     }
     __syncthreads();
     // ---- 3: du = dw^T([da; db]) and the tap sums of dW, a 4-pixel strip per thread and channel
-    if (ty < th && x0 + k4 < W) {
+    if (ty < th) {
       const int y = y0 + ty;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float D[3][6];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const float4 m = *reinterpret_cast<const float4*>(&sd[c][ty + ky][k4]);
-          const float2 e2 = *reinterpret_cast<const float2*>(&sd[c][ty + ky][k4 + 4]);
-          D[ky][0] = m.x; D[ky][1] = m.y; D[ky][2] = m.z; D[ky][3] = m.w; D[ky][4] = e2.x; D[ky][5] = e2.y;
-        }
+        for (int ky = 0; ky < 3; ++ky) row6(&sd[c][ty + ky][k4 + 3], D[ky]);
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -388,19 +451,15 @@ __global__ void __launch_bounds__(256, 4)
           o[j] = s;
         }
         *reinterpret_cast<float4*>((c == 0 ? dua : dub) + y * W + x0 + k4) = make_float4(o[0], o[1], o[2], o[3]);
-        float Q[3][6];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const float* row = &su[c][ty + 1 + ky][k4 + 3];
-          const float4 m = *reinterpret_cast<const float4*>(row + 1);
-          Q[ky][0] = row[0]; Q[ky][1] = m.x; Q[ky][2] = m.y; Q[ky][3] = m.z; Q[ky][4] = m.w; Q[ky][5] = row[5];
-        }
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+          float Q[6];
+          row6(&su[c][ty + 1 + ky][k4 + 3], Q);
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[c][ky * 3 + kx] = fmaf(D[1][j + 1], Q[ky][j + kx], acc[c][ky * 3 + kx]);
+            for (int j = 0; j < 4; ++j) acc[c][ky * 3 + kx] = fmaf(D[1][j + 1], Q[j + kx], acc[c][ky * 3 + kx]);
+        }
       }
     }
   }
@@ -427,7 +486,9 @@ int gdfn_mid_bwd_fast(const float* u, int64_t u_bs, const float* dg, int64_t dg_
                       int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
                       cudaStream_t st) {
   if (W % GF_T != 0 || B > 65535 || hid > 65535) return 0;
-  if (u_bs % 4 != 0 || du_bs % 4 != 0 || ((uintptr_t)u % 16 != 0) || ((uintptr_t)du % 16 != 0)) return 0;
+  if (u_bs % 4 != 0 || du_bs % 4 != 0 || dg_bs % 4 != 0 || ((uintptr_t)u % 16 != 0) || ((uintptr_t)du % 16 != 0) ||
+      ((uintptr_t)dg % 16 != 0) || (g_out && (g_bs % 4 != 0 || (uintptr_t)g_out % 16 != 0)))
+    return 0;
   dim3 grid(cdiv(H, GF_T), hid, B);
   gdfn_mid_bwd_kernel<<<grid, 256, 0, st>>>(u, u_bs, dg, dg_bs, w, du, du_bs, dw, g_out, g_bs, hid, H, W);
   return 1;

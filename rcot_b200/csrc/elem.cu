@@ -627,8 +627,10 @@ extern "C" int rcot_gdfn_mid_bwd(const float* u, int64_t u_bs, const float* dg, 
                                  rcot_stream_t st) {
   RCOT_REQUIRE(u && dg && w && du && dw && B > 0 && hid > 0 && H > 0 && W > 0, "gdfn_mid_bwd: bad arguments");
   RCOT_REQUIRE(W % 32 == 0 && B <= 65535 && hid <= 65535, "gdfn_mid_bwd: needs width %% 32 == 0 (got %dx%d)", H, W);
-  RCOT_REQUIRE(u_bs % 4 == 0 && du_bs % 4 == 0 && ((uintptr_t)u % 16 == 0) && ((uintptr_t)du % 16 == 0),
-               "gdfn_mid_bwd: u and du must be 16-byte aligned");
+  RCOT_REQUIRE(u_bs % 4 == 0 && du_bs % 4 == 0 && dg_bs % 4 == 0 && ((uintptr_t)u % 16 == 0) &&
+                   ((uintptr_t)du % 16 == 0) && ((uintptr_t)dg % 16 == 0) &&
+                   (!g_out || (g_bs % 4 == 0 && (uintptr_t)g_out % 16 == 0)),
+               "gdfn_mid_bwd: u, dg, du and g_out must be 16-byte aligned");
   RCOT_REQUIRE(gdfn_mid_bwd_fast(u, u_bs, dg, dg_bs, w, du, du_bs, dw, g_out, g_bs, B, hid, H, W, (cudaStream_t)st) == 1,
                "gdfn_mid_bwd: geometry not supported");
   return check_launch("gdfn_mid_bwd");

@@ -10,6 +10,7 @@
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace rcot {
 
@@ -17,7 +18,8 @@ constexpr int PK_PROD_WARPS = 16;
 constexpr int PK_PROD_THREADS = PK_PROD_WARPS * 32;
 constexpr int PK_THREADS = PK_PROD_THREADS + 32;   // + one MMA-issuing warp
 constexpr int PK_MAX_STAGES = 4;
-constexpr int PK_BT = 2;                           // B-operand row tasks per producer thread (BN <= 256)
+// NBT (template): B-operand row tasks per producer thread, 1 for BN <= 128 and 2 for BN <= 256, so that narrow
+// B operands (the common C = 48 / 96 cases) carry no dead second task through the conversion code.
 
 // Producer thread t (16 warps) owns k8 = t & 3 (8 consecutive pixels of the 32-pixel chunk), A row t >> 2
 // and B rows (t >> 2) + 128*j: four neighbouring lanes read 128 contiguous bytes of one channel row
@@ -26,7 +28,7 @@ constexpr int PK_BT = 2;                           // B-operand row tasks per pr
 // and stored, so global latency overlaps the conversion; one MMA warp issues tcgen05.mma and hands
 // stages back through mbarriers; after the K loop the producer warps drain the TMEM accumulator
 // with fp32 atomics (split-K).
-template <int TERMS, bool GENERAL, bool LN>
+template <int TERMS, bool GENERAL, bool LN, int NBT>
 __global__ void __launch_bounds__(PK_THREADS, 1)
     pk_gemm_kernel(const rcot_pk_params p, const int BN, const int nt, const int cpi, const int per_cta,
                    const int total_chunks, const int stages, const uint32_t tmem_cols) {
@@ -67,22 +69,22 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
 
   if (warp < PK_PROD_WARPS) {
     const int k8 = tid & 3, r0 = tid >> 2;   // 4 neighbouring lanes read 128 contiguous bytes of one row
-    const int nbt = (BN + 127) >> 7;          // B row tasks actually used (uniform)
+    constexpr int nbt = NBT;                  // B row tasks (the launcher picks NBT = ceil(BN / 128))
     struct Regs {
       float a[8];
-      float b[PK_BT][8];
+      float b[NBT][8];
       float2 st;                              // LayerNorm (mean, rstd) of pixel q0 + lane
     };
     // ---- everything that does not depend on the chunk is hoisted out of the K loop
     const bool a_ok = (m0 + r0) < p.CA;
     const float* a_row = p.a + (size_t)(g * p.CA + (a_ok ? m0 + r0 : 0)) * HWa + k8 * 8;
-    bool b_ok[PK_BT];
-    const float* b_row[PK_BT];
-    int64_t b_bstride[PK_BT];
-    float ga[PK_BT], be[PK_BT];
-    int b_cb[PK_BT], b_ky[PK_BT], b_kx[PK_BT];
+    bool b_ok[NBT];
+    const float* b_row[NBT];
+    int64_t b_bstride[NBT];
+    float ga[NBT], be[NBT];
+    int b_cb[NBT], b_ky[NBT], b_kx[NBT];
 #pragma unroll
-    for (int j = 0; j < PK_BT; ++j) {
+    for (int j = 0; j < NBT; ++j) {
       const int r = r0 + 128 * j, n = n0 + r;
       b_ok[j] = (j < nbt) && (r < BN) && (n < Ntot);
       const int cb = b_ok[j] ? n / KK : 0, rr = b_ok[j] ? n - cb * KK : 0;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         }
         if (LN) R.st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWb + q0 + lane);
 #pragma unroll
-        for (int j = 0; j < PK_BT; ++j) {
+        for (int j = 0; j < NBT; ++j) {
           if (b_ok[j]) ld8(R.b[j], b_row[j] + (size_t)b * (LN ? p.b_bs : b_bstride[j]) + q);
           else {
 #pragma unroll
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
                         : make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < PK_BT; ++j) {
+      for (int j = 0; j < NBT; ++j) {
         const float* sp = b_row[j] + (size_t)b * b_bstride[j];
         if (!b_ok[j]) {
 #pragma unroll
@@ -185,12 +187,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
           const float rv = __shfl_sync(0xffffffffu, cur.st.y, k8 * 8 + i);
           const bool in = all_full || q + i < HWa;
 #pragma unroll
-          for (int j = 0; j < PK_BT; ++j)
+          for (int j = 0; j < NBT; ++j)
             cur.b[j][i] = (in && b_ok[j]) ? (cur.b[j][i] - mu) * rv * ga[j] + be[j] : 0.f;
         }
       }
 #pragma unroll
-      for (int j = 0; j < PK_BT; ++j) {
+      for (int j = 0; j < NBT; ++j) {
         if (j >= nbt) break;
         const int r = r0 + 128 * j;
         if (r < BN) op_store8<TERMS>(b_hi, b_lo, r, k8, cur.b[j]);
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         ph ^= 1;
       }
     };
-    if (LN) {
-      // (the LayerNorm variant is register-bound at 544 threads: one prefetch set + a copy is the cheaper shape)
+    if (LN && NBT > 1) {
+      // (the wide LayerNorm variant is register-bound at 544 threads: one prefetch set + a copy is the cheaper shape)
       Regs nxt;
       int qn = nq0;
       if (nchunks > 0) {
@@ -296,8 +298,258 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
-template <int TERMS, bool GENERAL, bool LN>
-static int launch_pk(const rcot_pk_params& p, cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-M variant for the blocks' 1x1 weight gradients with LayerNorm (dW_in = du z^T, dW_qkv = dpre z^T): CA is
+// 2.6..5.3 x CB there, so a CTA that owns ONE 128-row tile of A re-reads and re-normalises the same B chunk for
+// every tile.  Here a CTA owns MT (2 or 4) A tiles = MT accumulators in TMEM (MT*BN <= 512 columns): the B operand
+// (x, normalised on the fly) is converted once per 32-pixel chunk for all of them.  One register set per thread:
+// each operand row is stored and immediately refilled with the next chunk's loads, so global latency hides behind
+// the rest of the chunk.  Rows beyond CA / columns beyond N are simply never written or read back (an accumulator
+// element depends on one A row and one B row only).
+template <int TERMS, int MT, int NBT>
+__global__ void __launch_bounds__(PK_THREADS, 1)
+    pk_mm_kernel(const rcot_pk_params p, const int BN, const int nt, const int cpi, const int per_cta,
+                 const int total_chunks, const int stages, const uint32_t tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full_bar[PK_MAX_STAGES], empty_bar[PK_MAX_STAGES], done_bar;
+  __shared__ uint32_t tmem_base_s;
+  constexpr int TA = (TERMS > 1) ? 2 : 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mg = blockIdx.x / nt, nt_i = blockIdx.x - mg * nt;
+  const int m0 = mg * (MT * 128), n0 = nt_i * BN;
+  const int HW = p.Ha * p.Wa;
+  const int Ntot = p.CB1;
+  const uint32_t a_tile = op_tile_bytes(128), b_tile = op_tile_bytes(BN);
+  const uint32_t stage_bytes = TA * (MT * a_tile + b_tile);
+  int mt_valid = (p.CA - m0 + 127) >> 7;      // A tiles of this CTA that hold at least one row
+  if (mt_valid > MT) mt_valid = MT;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], PK_PROD_WARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  const int c_begin = blockIdx.y * per_cta;
+  int c_end = c_begin + per_cta;
+  if (c_end > total_chunks) c_end = total_chunks;
+  const int nchunks = c_end - c_begin;
+
+  if (warp < PK_PROD_WARPS) {
+    const int k8 = tid & 3, r0 = tid >> 2;   // 4 neighbouring lanes read 128 contiguous bytes of one row
+    const float* a_base = p.a + (size_t)(m0 + r0) * HW + k8 * 8;
+    const size_t a_mstride = (size_t)128 * HW;
+    bool a_ok[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) a_ok[m] = (m0 + m * 128 + r0) < p.CA;
+    bool b_ok[NBT];
+    const float* b_ptr[NBT];
+    float ga[NBT], be[NBT];
+#pragma unroll
+    for (int j = 0; j < NBT; ++j) {
+      const int r = r0 + 128 * j, n = n0 + r;
+      b_ok[j] = (r < BN) && (n < Ntot);
+      b_ptr[j] = p.b + (size_t)(b_ok[j] ? n : 0) * HW + k8 * 8;
+      ga[j] = b_ok[j] ? __ldg(p.ln_gamma + n) : 0.f;
+      be[j] = b_ok[j] ? __ldg(p.ln_beta + n) : 0.f;
+    }
+    const float2* stats = reinterpret_cast<const float2*>(p.ln_stats);
+    auto ld8 = [&](float* v, const float* src) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+      v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    };
+    float ra[MT][8], rb[NBT][8];
+    float2 st = make_float2(0.f, 0.f);
+    // (image, first pixel) of the chunk whose loads are issued next
+    int nb = c_begin / cpi;
+    int nq0 = (c_begin - nb * cpi) * KC;
+    if (nchunks > 0) {
+      const size_t ao = (size_t)nb * p.a_bs + nq0, bo = (size_t)nb * p.b_bs + nq0;
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        if (a_ok[m]) ld8(ra[m], a_base + m * a_mstride + ao);
+      st = __ldg(stats + (size_t)nb * HW + nq0 + lane);
+#pragma unroll
+      for (int j = 0; j < NBT; ++j)
+        if (b_ok[j]) ld8(rb[j], b_ptr[j] + bo);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      const bool more = it + 1 < nchunks;
+      nq0 += KC;                                  // walker -> the chunk after this one
+      if (nq0 >= HW) {
+        nq0 = 0;
+        ++nb;
+      }
+      const size_t ao = (size_t)nb * p.a_bs + nq0, bo = (size_t)nb * p.b_bs + nq0;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* stg = smem + (size_t)s * stage_bytes;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (a_ok[m]) {
+          op_store8<TERMS>(stg + m * a_tile, stg + (MT + m) * a_tile, r0, k8, ra[m]);
+          if (more) ld8(ra[m], a_base + m * a_mstride + ao);
+        }
+      }
+      const float2 stc = st;                      // statistics of pixel q0 + lane of THIS chunk
+      if (more) st = __ldg(stats + (size_t)nb * HW + nq0 + lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {               // this thread's 8 pixels are held by lanes k8*8+i (all lanes shuffle)
+        const float mu = __shfl_sync(0xffffffffu, stc.x, k8 * 8 + i);
+        const float rv = __shfl_sync(0xffffffffu, stc.y, k8 * 8 + i);
+#pragma unroll
+        for (int j = 0; j < NBT; ++j) rb[j][i] = fmaf((rb[j][i] - mu) * rv, ga[j], be[j]);
+      }
+      uint8_t* b_hi = stg + TA * MT * a_tile;
+#pragma unroll
+      for (int j = 0; j < NBT; ++j) {
+        if (b_ok[j]) {
+          op_store8<TERMS>(b_hi, b_hi + b_tile, r0 + 128 * j, k8, rb[j]);
+          if (more) ld8(rb[j], b_ptr[j] + bo);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    // ---- MMA issuer warp: MT accumulators share the B stage
+    const uint32_t idesc = make_idesc_bf16(128, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t stg = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_hi = stg + TA * MT * a_tile;
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          if (m < mt_valid)
+            issue_stage<TERMS>(tmem + m * BN, stg + m * a_tile, stg + (MT + m) * a_tile, b_hi, b_hi + b_tile, idesc,
+                               it == 0);
+        tc_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+    if (lane == 0 && nchunks > 0) tc_commit(&done_bar);
+  }
+  if (warp < PK_PROD_WARPS && nchunks > 0) {
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    // ---- epilogue: thread = row (TMEM lane), the four warp groups split the columns; 16-byte vector reductions
+    // (red.global.add.v4.f32) when the output rows are 16-byte aligned, scalar atomics otherwise
+    const uint32_t lane_base = tmem_lane_base(tmem);
+    const int part = warp >> 2;
+    const int ncols8 = BN / 8;
+    const int c8_begin = (ncols8 * part) / 4, c8_end = (ncols8 * (part + 1)) / 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.ldo % 4 == 0) && (n0 % 4 == 0);
+    for (int m = 0; m < mt_valid; ++m) {
+      const int row = m0 + m * 128 + (warp & 3) * 32 + lane;
+      for (int c8 = c8_begin; c8 < c8_end; ++c8) {
+        if (n0 + c8 * 8 >= Ntot) break;
+        float v[8];
+        tmem_ld8(lane_base + m * BN + c8 * 8, v);
+        if (row < p.CA) {
+          float* dst = p.out + (size_t)row * p.ldo + n0 + c8 * 8;
+          if (vec && n0 + c8 * 8 + 8 <= Ntot) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                         "f"(v[3])
+                         : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]),
+                         "f"(v[6]), "f"(v[7])
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (n0 + c8 * 8 + i < Ntot) atomicAdd(dst + i, v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <int TERMS, int MT, int NBT>
+static int launch_pk_mm(const rcot_pk_params& p, int BN, cudaStream_t stream) {
+  const int Ntot = p.CB1;
+  const int HW = p.Ha * p.Wa;
+  const int nt = cdiv(Ntot, BN), mgroups = cdiv(p.CA, 128 * MT);
+  const int cpi = HW / KC;
+  const int total_chunks = cpi * p.B;
+  const long tiles = (long)mgroups * nt;
+  int S = (int)((148 + tiles - 1) / tiles);     // one CTA per SM: every split adds CA x N atomics to the epilogue
+  int maxS = total_chunks / 4;
+  if (maxS < 1) maxS = 1;
+  if (S > maxS) S = maxS;
+  if (S < 1) S = 1;
+  int per_cta = cdiv(total_chunks, S);
+  S = cdiv(total_chunks, per_cta);
+  constexpr int TA = (TERMS > 1) ? 2 : 1;
+  const size_t stage_bytes = (size_t)TA * (MT * (size_t)op_tile_bytes(128) + (size_t)op_tile_bytes(BN));
+  int stages = (int)((196 * 1024) / stage_bytes);
+  if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
+  RCOT_REQUIRE(stages >= 2, "pk_gemm(mm): stage of %zu bytes does not fit twice", stage_bytes);
+  const size_t smem = stages * stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pk_mm_kernel<TERMS, MT, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         196 * 1024);
+    if (e != cudaSuccess) {
+      set_error("pk_gemm(mm): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return RCOT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  RCOT_REQUIRE(S <= 65535, "pk_gemm(mm): grid too large");
+  dim3 grid(mgroups * nt, S, 1);
+  pk_mm_kernel<TERMS, MT, NBT><<<grid, PK_THREADS, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks, stages,
+                                                                  tmem_cols_pow2(MT * BN));
+  return check_launch("pk_gemm(mm)");
+}
+
+// Picks (MT, NBT) for the multi-M kernel; returns -100 when the call does not qualify.
+template <int TERMS>
+static int try_pk_mm(const rcot_pk_params& p, cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("RCOT_PK_MM");       // RCOT_PK_MM=0: A/B switch back to the one-tile-per-CTA kernel
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int HW = p.Ha * p.Wa;
+  if (!enabled || p.CA <= 128 || HW % KC != 0 || p.per_image || p.groups > 1 || p.b2 != nullptr) return -100;
+  int BN = round_up(p.CB1, 16);
+  if (BN > 256) BN = 256;
+  if (BN <= 128) {
+    if (p.CA > 256) return launch_pk_mm<TERMS, 4, 1>(p, BN, stream);
+    return launch_pk_mm<TERMS, 2, 1>(p, BN, stream);
+  }
+  return launch_pk_mm<TERMS, 2, 2>(p, BN, stream);
+}
+
+template <int TERMS, bool GENERAL, bool LN, int NBT>
+static int launch_pk_n(const rcot_pk_params& p, cudaStream_t stream) {
   const int Ntot = (p.CB1 + p.CB2) * p.ks * p.ks;
   const int HWa = p.Ha * p.Wa;
   int BN = round_up(Ntot, 16);
@@ -321,7 +573,7 @@ static int launch_pk(const rcot_pk_params& p, cudaStream_t stream) {
   const size_t smem = stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pk_gemm_kernel<TERMS, GENERAL, LN>,
+    cudaError_t e = cudaFuncSetAttribute(pk_gemm_kernel<TERMS, GENERAL, LN, NBT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
     if (e != cudaSuccess) {
       set_error("pk_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -331,9 +583,15 @@ static int launch_pk(const rcot_pk_params& p, cudaStream_t stream) {
   }
   RCOT_REQUIRE(zdim <= 65535 && S <= 65535, "pk_gemm: grid too large");
   dim3 grid(mt * nt, S, zdim);
-  pk_gemm_kernel<TERMS, GENERAL, LN><<<grid, PK_THREADS, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks,
-                                                                        stages, tmem_cols_pow2(BN));
+  pk_gemm_kernel<TERMS, GENERAL, LN, NBT><<<grid, PK_THREADS, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks,
+                                                                             stages, tmem_cols_pow2(BN));
   return check_launch("pk_gemm");
+}
+
+template <int TERMS, bool GENERAL, bool LN>
+static int launch_pk(const rcot_pk_params& p, cudaStream_t stream) {
+  const int Ntot = (p.CB1 + p.CB2) * p.ks * p.ks;
+  return Ntot <= 128 ? launch_pk_n<TERMS, GENERAL, LN, 1>(p, stream) : launch_pk_n<TERMS, GENERAL, LN, 2>(p, stream);
 }
 
 }  // namespace rcot
@@ -359,6 +617,8 @@ extern "C" int rcot_pk_gemm(const rcot_pk_params* pp, rcot_stream_t stream_) {
   if (ln) {
     RCOT_REQUIRE(p.ks == 1 && p.ln_gamma && p.ln_beta && p.groups == 1, "pk_gemm: LayerNorm needs ks==1");
     RCOT_REQUIRE(!general, "pk_gemm: LayerNorm path needs HW %% 8 == 0 and 16-byte aligned tensors");
+    const int rc = p.terms == 3 ? try_pk_mm<3>(p, stream) : try_pk_mm<1>(p, stream);
+    if (rc != -100) return rc;
     return p.terms == 3 ? launch_pk<3, false, true>(p, stream) : launch_pk<1, false, true>(p, stream);
   }
   if (general) return p.terms == 3 ? launch_pk<3, true, false>(p, stream) : launch_pk<1, true, false>(p, stream);

@@ -35,14 +35,20 @@ class ParamSet:
         if used is not None:
             names = [n for n in names if n in used] + [n for n in names if n not in used]
         self.names = names
+        # every tensor starts on a 16-byte boundary of the flat buffers (vector reductions into .grad, float4
+        # optimizer passes); the padding elements stay zero in both buffers, so the optimizers leave them alone
         self.offsets = {}
         off = 0
+        self.n_used = None
         for n in names:
+            if used is not None and self.n_used is None and n not in used:
+                self.n_used = off
             self.offsets[n] = off
-            off += named_params[n].numel()
+            off += (named_params[n].numel() + 3) // 4 * 4
         self.numel = off
-        self.n_used = off if used is None else sum(named_params[n].numel() for n in names if n in used)
-        self.flat = torch.empty(off, device=device, dtype=torch.float32)
+        if self.n_used is None:
+            self.n_used = off
+        self.flat = torch.zeros(off, device=device, dtype=torch.float32)
         self.grad = torch.zeros(off, device=device, dtype=torch.float32)
         self.p, self.g = {}, {}
         for n in names:

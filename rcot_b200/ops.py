@@ -318,7 +318,7 @@ def dwconv_bwd(x, dout, w, dw):
 
 def gdfn_mid_ok(u):
     """Geometry the fused GDFN middle backward accepts (every level of a training patch whose width is a multiple of 32)."""
-    return u.shape[3] % 32 == 0 and u.data_ptr() % 16 == 0 and _img_view(u, "u") % 4 == 0
+    return u.shape[3] % 32 == 0 and u.data_ptr() % 16 == 0 and _img_view(u, "u") % 4 == 0 and u.shape[1] % 2 == 0
 
 
 def gdfn_mid_bwd(u, dg, w, dw, g_out=None):
