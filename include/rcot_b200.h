@@ -163,7 +163,7 @@ int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* dout, int64_
 /* GDFN middle backward in one pass (Net_Restormer.py:81-83 backward): with a = dw(u[j]),
  * b = dw(u[j+hid]): da = dg*b*gelu'(a), db = dg*gelu(a); du = dw^T([da; db]); dw += corr(u, [da; db]);
  * g_out[j] = gelu(a)*b (optional, may be NULL).  Same arithmetic as mode 2 followed by rcot_dwconv3x3_bwd, without
- * the [da; db] round trip through HBM.  Requires W % 32 == 0 and 16-byte aligned u / du. */
+ * the [da; db] round trip through HBM.  Requires W % 32 == 0, H % 4 == 0 and 16-byte aligned u / dg / du / g_out. */
 int rcot_gdfn_mid_bwd(const float* u, int64_t u_bs, const float* dg, int64_t dg_bs, const float* w, float* du,
                       int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
                       rcot_stream_t stream);
@@ -187,6 +187,8 @@ typedef struct {
   float* dtemperature;       /* [heads] +=                                 (bwd out)       */
   void* W12pack;             /* per-image packed [2C x 2C], zero-initialised by the caller */
   int64_t pack12_bs;         /* = rcot_packed_bytes(2C, 2C)                                */
+  float* dA;                 /* [B, heads, c, c] scratch, ZEROED by the caller before rcot_attn_bwd (its first
+                                kernel accumulates W_out^T P there in row chunks, its second consumes it) */
 } rcot_attn_params;
 int rcot_attn_fwd(const rcot_attn_params* p, rcot_stream_t stream);
 int rcot_attn_bwd(const rcot_attn_params* p, rcot_stream_t stream);

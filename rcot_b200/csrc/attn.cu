@@ -123,77 +123,61 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p,
   }
 }
 
-constexpr int AB_CH = 32;  // rows of W_out / P staged per step in attn_bwd
+constexpr int AB_CH = 32;  // rows of W_out / P per phase-1 CTA
 constexpr int AB_T = 6;    // largest register tile edge: ceil(96 / 16)
 
-// Backward.  One CTA per (head, image).  Phase 1 streams W_out / P through shared memory AB_CH rows at a time and
-// runs two register-tiled products:  dA[i,j] = sum_co W_out[co,(h,i)] P[co,(h,j)]  (T x T outputs per thread,
-// T = ceil(c/16)) and  dW_out[co,(h,i)] += sum_j P[co,(h,j)] A[i,j]  (2 x T outputs per thread, A^T in shared
-// memory).  Then softmax / normalisation backward on the c x c tile and the packed W12 stores.
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p) {
+// Backward, phase 1.  grid = (heads, B, ceil(C / AB_CH)): a CTA stages AB_CH rows of W_out / P (head block) and runs
+// two register-tiled products:  dA[i,j] += sum_co W_out[co,(h,i)] P[co,(h,j)]  (T x T outputs per thread,
+// T = ceil(c/16); partial over this CTA's rows -> atomics into the zeroed scratch dA) and
+// dW_out[co,(h,i)] += sum_j P[co,(h,j)] A[i,j]  (2 x T outputs per thread, complete for these rows).
+// One CTA per (head, image) for all of it ran at < 1 IPC on 32 SMs; split by rows it fills the machine.
+__global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params p) {
   extern __shared__ __align__(16) float sm[];
   const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
-  const int ca = c + 1;         // padded row stride of sA: the transposing copy below stays conflict-free
+  const int co0 = blockIdx.z * AB_CH;
+  const int ca = c + 1;         // padded row stride of sA: threads that differ in the row hit different banks
   float* sA = sm;               // [c*ca] softmax probabilities A[i][j]
-  float* sX = sA + c * ca;      // [c*c] phase 1: A^T (sX[j*c+i]); afterwards: normalised Gram
-  float* sD = sX + c * c;       // [c*c] dA -> dGt
-  float* sW = sD + c * c;       // [AB_CH*c] rows of W_out[:, head block]
+  float* sW = sA + c * ca;      // [AB_CH*c] rows of W_out[:, head block]
   float* sP = sW + AB_CH * c;   // [AB_CH*c] rows of P[:, head block]
-  float* snq = sP + AB_CH * c;  // [c]
-  float* snk = snq + c;
-  float* srq = snk + c;
-  float* srk = srq + c;
-  __shared__ float s_dtau;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int tid = threadIdx.x;
   const size_t hb = ((size_t)b * p.heads + h) * c * c;
-  const float* ss = p.sumsq + (size_t)b * 2 * C;
   const float* Pm = p.P + (size_t)b * C * C;  // [co, ci]
-  for (int e = tid; e < c * c; e += blockDim.x) {
-    const int i = e / c, j = e - i * c;
-    sA[i * ca + j] = __ldg(p.A + hb + e);
+  for (int i = tid / c, j = tid - (tid / c) * c; i < c;) {   // (i, j) walk without a division per element
+    sA[i * ca + j] = __ldg(p.A + hb + i * c + j);
+    j += 256;
+    while (j >= c) {
+      j -= c;
+      ++i;
+    }
   }
-  for (int i = tid; i < c; i += blockDim.x) {
-    snq[i] = sqrtf(ss[h * c + i]);
-    snk[i] = sqrtf(ss[C + h * c + i]);
-    srk[i] = 0.f;
+  for (int r = tid / c, i = tid - (tid / c) * c; r < AB_CH;) {
+    const bool in = co0 + r < C;              // a partial last chunk is zero-filled
+    sW[r * c + i] = in ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;
+    sP[r * c + i] = in ? __ldg(Pm + (size_t)(co0 + r) * C + h * c + i) : 0.f;
+    i += 256;
+    while (i >= c) {
+      i -= c;
+      ++r;
+    }
   }
-  if (tid == 0) s_dtau = 0.f;
   __syncthreads();
-  for (int e = tid; e < c * c; e += blockDim.x) {
-    const int j = e / c, i = e - j * c;
-    sX[e] = sA[i * ca + j];
-  }
   const int T = (c + 15) >> 4;            // register tile edge (<= AB_T)
   const int nt = (c + T - 1) / T;         // tiles per dimension (<= 16)
-  // dA role: thread (ti, tj) owns rows ti*T.., columns tj*T.. of dA
-  const int ti = tid / nt, tj = tid - ti * nt;
-  const bool da_on = ti < nt;
-  int ia[AB_T], ja[AB_T];
+  {
+    // dA role: thread (ti, tj) owns rows ti*T.., columns tj*T.. of dA
+    const int ti = tid / nt, tj = tid - ti * nt;
+    if (ti < nt) {
+      int ia[AB_T], ja[AB_T];
 #pragma unroll
-  for (int q = 0; q < AB_T; ++q) {
-    ia[q] = min(ti * T + q, c - 1);       // clamped: duplicates are never stored
-    ja[q] = min(tj * T + q, c - 1);
-  }
-  // dW_out role: thread (rg, ig) owns staged rows 2rg, 2rg+1 and head columns ig*T..
-  const int rg = tid >> 4, ig = tid & 15;
-  int iw[AB_T];
+      for (int q = 0; q < AB_T; ++q) {
+        ia[q] = min(ti * T + q, c - 1);       // clamped: duplicates are never stored
+        ja[q] = min(tj * T + q, c - 1);
+      }
+      float acc[AB_T][AB_T];
 #pragma unroll
-  for (int q = 0; q < AB_T; ++q) iw[q] = min(ig * T + q, c - 1);
-  float acc[AB_T][AB_T];
+      for (int x = 0; x < AB_T; ++x)
 #pragma unroll
-  for (int x = 0; x < AB_T; ++x)
-#pragma unroll
-    for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
-  for (int co0 = 0; co0 < C; co0 += AB_CH) {
-    __syncthreads();
-    for (int e = tid; e < AB_CH * c; e += blockDim.x) {
-      const int r = e / c, i = e - r * c;
-      const bool in = co0 + r < C;        // a partial last chunk is zero-filled
-      sW[e] = in ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;
-      sP[e] = in ? __ldg(Pm + (size_t)(co0 + r) * C + h * c + i) : 0.f;
-    }
-    __syncthreads();
-    if (da_on) {
+        for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
 #pragma unroll 4
       for (int r = 0; r < AB_CH; ++r) {
         float wv[AB_T], pv[AB_T];
@@ -209,62 +193,88 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
           for (int y = 0; y < AB_T; ++y)
             if (x < T && y < T) acc[x][y] = fmaf(wv[x], pv[y], acc[x][y]);
       }
-    }
-    {
-      float aw[2][AB_T];
+      float* dA = p.dA + hb;
 #pragma unroll
-      for (int q = 0; q < AB_T; ++q) aw[0][q] = aw[1][q] = 0.f;
-      const float* p0 = sP + (2 * rg) * c;
-      const float* p1 = p0 + c;
+      for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+        for (int y = 0; y < AB_T; ++y)
+          if (x < T && y < T && ti * T + x < c && tj * T + y < c) atomicAdd(dA + (ti * T + x) * c + tj * T + y, acc[x][y]);
+    }
+  }
+  {
+    // dW_out role: thread (rg, ig) owns staged rows 2rg, 2rg+1 and head columns ig*T..
+    const int rg = tid >> 4, ig = tid & 15;
+    int iw[AB_T];
+#pragma unroll
+    for (int q = 0; q < AB_T; ++q) iw[q] = min(ig * T + q, c - 1) * ca;
+    float aw[2][AB_T];
+#pragma unroll
+    for (int q = 0; q < AB_T; ++q) aw[0][q] = aw[1][q] = 0.f;
+    const float* p0 = sP + (2 * rg) * c;
+    const float* p1 = p0 + c;
 #pragma unroll 4
-      for (int j = 0; j < c; ++j) {
-        const float x0 = p0[j], x1 = p1[j];
-        const float* at = sX + j * c;
+    for (int j = 0; j < c; ++j) {
+      const float x0 = p0[j], x1 = p1[j];
+#pragma unroll
+      for (int q = 0; q < AB_T; ++q)
+        if (q < T) {
+          const float a = sA[iw[q] + j];
+          aw[0][q] = fmaf(x0, a, aw[0][q]);
+          aw[1][q] = fmaf(x1, a, aw[1][q]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int co = co0 + 2 * rg + k;
+      if (co < C) {
 #pragma unroll
         for (int q = 0; q < AB_T; ++q)
-          if (q < T) {
-            const float a = at[iw[q]];
-            aw[0][q] = fmaf(x0, a, aw[0][q]);
-            aw[1][q] = fmaf(x1, a, aw[1][q]);
-          }
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int co = co0 + 2 * rg + k;
-        if (co < C) {
-#pragma unroll
-          for (int q = 0; q < AB_T; ++q)
-            if (q < T && ig * T + q < c) atomicAdd(p.dw_out + (size_t)co * C + h * c + ig * T + q, aw[k][q]);
-        }
+          if (q < T && ig * T + q < c) atomicAdd(p.dw_out + (size_t)co * C + h * c + ig * T + q, aw[k][q]);
       }
     }
   }
-  __syncthreads();                          // phase 1 done with sX (A^T) and the staged rows
-  if (da_on) {
-#pragma unroll
-    for (int x = 0; x < AB_T; ++x)
-#pragma unroll
-      for (int y = 0; y < AB_T; ++y)
-        if (x < T && y < T && ti * T + x < c && tj * T + y < c) sD[(ti * T + x) * c + tj * T + y] = acc[x][y];
+}
+
+// Backward, phase 2.  One CTA per (head, image): softmax / normalisation backward on the c x c tile (dA complete in
+// global memory) and the packed W12 stores.
+__global__ void __launch_bounds__(256) attn_bwd_p2_kernel(const rcot_attn_params p) {
+  extern __shared__ __align__(16) float sm[];
+  const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
+  float* sA = sm;               // [c*c] softmax probabilities
+  float* sG = sA + c * c;       // [c*c] normalised Gram
+  float* sD = sG + c * c;       // [c*c] dA -> dGt -> B_q
+  float* snq = sD + c * c;      // [c]
+  float* snk = snq + c;
+  float* srq = snk + c;
+  float* srk = srq + c;
+  __shared__ float s_dtau;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const size_t hb = ((size_t)b * p.heads + h) * c * c;
+  const float* ss = p.sumsq + (size_t)b * 2 * C;
+  for (int e = tid; e < c * c; e += blockDim.x) {
+    sA[e] = __ldg(p.A + hb + e);
+    sG[e] = __ldg(p.Gt + hb + e);
+    sD[e] = p.dA[hb + e];
   }
-  float* sG = sX;
-  for (int e = tid; e < c * c; e += blockDim.x) sG[e] = __ldg(p.Gt + hb + e);
+  for (int i = tid; i < c; i += blockDim.x) {
+    snq[i] = sqrtf(ss[h * c + i]);
+    snk[i] = sqrtf(ss[C + h * c + i]);
+  }
+  if (tid == 0) s_dtau = 0.f;
   __syncthreads();
   const float tau = __ldg(p.temperature + h);
   float dtau = 0.f;
   for (int i = warp; i < c; i += nwarp) {
     float rd = 0.f;
-    for (int j = lane; j < c; j += 32) rd = fmaf(sD[i * c + j], sA[i * ca + j], rd);
+    for (int j = lane; j < c; j += 32) rd = fmaf(sD[i * c + j], sA[i * c + j], rd);
     rd = warp_sum_a(rd);
     float rq = 0.f;
     for (int j = lane; j < c; j += 32) {
-      const float dS = sA[i * ca + j] * (sD[i * c + j] - rd);
+      const float dS = sA[i * c + j] * (sD[i * c + j] - rd);
       dtau = fmaf(dS, sG[i * c + j], dtau);
       const float dG = dS * tau;
       sD[i * c + j] = dG;
-      const float t = dG * sG[i * c + j];
-      rq += t;
-      atomicAdd(&srk[j], t);
+      rq = fmaf(dG, sG[i * c + j], rq);
     }
     rq = warp_sum_a(rq);
     if (lane == 0) srq[i] = rq;
@@ -273,14 +283,20 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const rcot_attn_params p)
   if (lane == 0) atomicAdd(&s_dtau, dtau);
   __syncthreads();
   if (tid == 0) atomicAdd(p.dtemperature + h, s_dtau);
+  for (int j = tid; j < c; j += blockDim.x) {               // column sums r_k[j] = sum_i dGt[i,j] * Gt[i,j]
+    float t = 0.f;
+    for (int i = 0; i < c; ++i) t = fmaf(sD[i * c + j], sG[i * c + j], t);
+    srk[j] = t;
+  }
+  __syncthreads();
   // packed W12: rows [0,C) produce dq, rows [C,2C) produce dk; K runs over [q channels ; k channels].
   // Only the head-diagonal blocks are ever written: the caller keeps one zero-initialised pack
   // buffer per (C, heads) configuration, so every other entry stays zero.
   uint8_t* Wp = reinterpret_cast<uint8_t*>(p.W12pack) + (size_t)b * p.pack12_bs;
   const int N2 = 2 * C;
-  for (int e = tid; e < c * c; e += blockDim.x) {            // B_q = dGt / (|q_i| |k_j|), in place
-    const int i = e / c, j = e - i * c;
-    sD[e] = sD[e] / (fmaxf(snq[i], 1e-12f) * fmaxf(snk[j], 1e-12f));
+  for (int i = warp; i < c; i += nwarp) {                   // B_q = dGt / (|q_i| |k_j|), in place
+    const float qi = fmaxf(snq[i], 1e-12f);
+    for (int j = lane; j < c; j += 32) sD[i * c + j] = sD[i * c + j] / (qi * fmaxf(snk[j], 1e-12f));
   }
   __syncthreads();
   const int c8 = c >> 3;
@@ -352,20 +368,27 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
   const rcot_attn_params& p = *pp;
   int rc = attn_check(p);
   if (rc) return rc;
-  RCOT_REQUIRE(p.P && p.dw_out && p.dtemperature && p.W12pack, "attn_bwd: null pointer");
+  RCOT_REQUIRE(p.P && p.dw_out && p.dtemperature && p.W12pack && p.dA, "attn_bwd: null pointer");
   const int c = p.C / p.heads;
   RCOT_REQUIRE(c % 8 == 0, "attn_bwd: channels per head must be a multiple of 8");
-  const size_t smem = ((size_t)3 * c * c + c + 2 * AB_CH * c + 4 * c) * sizeof(float);
+  const size_t smem1 = ((size_t)c * (c + 1) + 2 * AB_CH * c) * sizeof(float);
+  const size_t smem2 = ((size_t)3 * c * c + 4 * c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     if (e != cudaSuccess) {
       set_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return RCOT_ERR_CUDA;
     }
     attr_set = true;
   }
-  dim3 grid(p.heads, p.B);
-  attn_bwd_kernel<<<grid, 256, smem, (cudaStream_t)st>>>(p);
-  return check_launch("attn_bwd");
+  dim3 grid1(p.heads, p.B, cdiv(p.C, AB_CH));
+  attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p);
+  rc = check_launch("attn_bwd(p1)");
+  if (rc) return rc;
+  dim3 grid2(p.heads, p.B);
+  attn_bwd_p2_kernel<<<grid2, 256, smem2, (cudaStream_t)st>>>(p);
+  return check_launch("attn_bwd(p2)");
 }

@@ -344,10 +344,18 @@ __global__ void __launch_bounds__(256, 4)
   const int nrow_u = th + 4, nrow_d = th + 2;
   const int n_strip = nrow_d * 8;                // step 2: eight 4-pixel strips per row ...
   const int edge0 = (n_strip + 31) & ~31;        // ... then (warp aligned) one task per row for the two halo columns
-  // Six values around a 4-pixel strip (columns x-1 .. x+4) of one region row
-  auto row6 = [](const float* row, float (&v)[6]) {
-    const float4 m = *reinterpret_cast<const float4*>(row + 1);
-    v[0] = row[0]; v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w; v[5] = row[5];
+  // Six values (columns x-1 .. x+4) around this lane's 4-pixel strip of one region row.  The eight lanes of a row
+  // hold neighbouring strips, so the two edge values come from the neighbours' float4 by warp shuffle (a scalar
+  // shared-memory read at stride 4 words is a 4-way bank conflict); only strips 0 and 7 read their outer edge.
+  // Must be called by all 32 lanes.
+  const int ls = tid & 7;
+  auto row6 = [&](const float* row, int sx, float (&v)[6]) {
+    const float4 m = *reinterpret_cast<const float4*>(row + sx + 4);
+    float l = __shfl_up_sync(0xffffffffu, m.w, 1);
+    float r = __shfl_down_sync(0xffffffffu, m.x, 1);
+    if (ls == 0) l = row[3];
+    if (ls == 7) r = row[GF_T + 4];
+    v[0] = l; v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w; v[5] = r;
   };
   for (int x0 = 0; x0 < W; x0 += GF_T) {
     __syncthreads();                             // previous tile fully consumed
@@ -366,25 +374,27 @@ __global__ void __launch_bounds__(256, 4)
     __syncthreads();
     // ---- 2: [da; db] on the tile plus a 1-pixel halo (zero outside the image)
     for (int t = tid; t < edge0 + nrow_d; t += 256) {
-      if (t < n_strip) {
-        const int r = t >> 3, sx = (t & 7) * 4;  // region row, tile column of the strip
+      if ((t & ~31) < n_strip) {                 // warp-uniform: whole warps run the strip code (shuffles inside)
+        const bool mine = t < n_strip;
+        const int r = mine ? (t >> 3) : nrow_d - 1, sx = ls * 4;   // region row, tile column of the strip
         const int y = y0 - 1 + r;
+        const bool in = mine && (unsigned)y < (unsigned)H;
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          float v0[6], v1[6];
+          row6(&su[0][r + ky][0], sx, v0);
+          row6(&su[1][r + ky][0], sx, v1);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              a[j] = fmaf(v0[j + kx], wk[0][ky * 3 + kx], a[j]);
+              bb[j] = fmaf(v1[j + kx], wk[1][ky * 3 + kx], bb[j]);
+            }
+        }
         float4 da4 = make_float4(0.f, 0.f, 0.f, 0.f), db4 = da4;
-        if ((unsigned)y < (unsigned)H) {
-          float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            float v0[6], v1[6];
-            row6(&su[0][r + ky][sx + 3], v0);
-            row6(&su[1][r + ky][sx + 3], v1);
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                a[j] = fmaf(v0[j + kx], wk[0][ky * 3 + kx], a[j]);
-                bb[j] = fmaf(v1[j + kx], wk[1][ky * 3 + kx], bb[j]);
-              }
-          }
+        if (in) {
           const float4 d4 = __ldg(reinterpret_cast<const float4*>(dgp + y * W + x0 + sx));
           const float d[4] = {d4.x, d4.y, d4.z, d4.w};
           float da[4], db[4], gg[4];
@@ -401,8 +411,10 @@ __global__ void __launch_bounds__(256, 4)
           if (gp && r >= 1 && r <= th)
             *reinterpret_cast<float4*>(gp + y * W + x0 + sx) = make_float4(gg[0], gg[1], gg[2], gg[3]);
         }
-        *reinterpret_cast<float4*>(&sd[0][r][sx + 4]) = da4;
-        *reinterpret_cast<float4*>(&sd[1][r][sx + 4]) = db4;
+        if (mine) {
+          *reinterpret_cast<float4*>(&sd[0][r][sx + 4]) = da4;
+          *reinterpret_cast<float4*>(&sd[1][r][sx + 4]) = db4;
+        }
       } else if (t >= edge0) {
         const int r = t - edge0;
         const int y = y0 - 1 + r;
@@ -433,13 +445,14 @@ __global__ void __launch_bounds__(256, 4)
     }
     __syncthreads();
     // ---- 3: du = dw^T([da; db]) and the tap sums of dW, a 4-pixel strip per thread and channel
+    // (th % 4 == 0 is checked by the launcher, so the four rows of a warp are all inside or all outside)
     if (ty < th) {
       const int y = y0 + ty;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float D[3][6];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) row6(&sd[c][ty + ky][k4 + 3], D[ky]);
+        for (int ky = 0; ky < 3; ++ky) row6(&sd[c][ty + ky][0], k4, D[ky]);
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -454,7 +467,7 @@ __global__ void __launch_bounds__(256, 4)
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           float Q[6];
-          row6(&su[c][ty + 1 + ky][k4 + 3], Q);
+          row6(&su[c][ty + 1 + ky][0], k4, Q);
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -485,7 +498,7 @@ __global__ void __launch_bounds__(256, 4)
 int gdfn_mid_bwd_fast(const float* u, int64_t u_bs, const float* dg, int64_t dg_bs, const float* w, float* du,
                       int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
                       cudaStream_t st) {
-  if (W % GF_T != 0 || B > 65535 || hid > 65535) return 0;
+  if (W % GF_T != 0 || H % 4 != 0 || B > 65535 || hid > 65535) return 0;
   if (u_bs % 4 != 0 || du_bs % 4 != 0 || dg_bs % 4 != 0 || ((uintptr_t)u % 16 != 0) || ((uintptr_t)du % 16 != 0) ||
       ((uintptr_t)dg % 16 != 0) || (g_out && (g_bs % 4 != 0 || (uintptr_t)g_out % 16 != 0)))
     return 0;

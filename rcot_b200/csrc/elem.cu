@@ -626,7 +626,8 @@ extern "C" int rcot_gdfn_mid_bwd(const float* u, int64_t u_bs, const float* dg, 
                                  int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
                                  rcot_stream_t st) {
   RCOT_REQUIRE(u && dg && w && du && dw && B > 0 && hid > 0 && H > 0 && W > 0, "gdfn_mid_bwd: bad arguments");
-  RCOT_REQUIRE(W % 32 == 0 && B <= 65535 && hid <= 65535, "gdfn_mid_bwd: needs width %% 32 == 0 (got %dx%d)", H, W);
+  RCOT_REQUIRE(W % 32 == 0 && H % 4 == 0 && B <= 65535 && hid <= 65535,
+               "gdfn_mid_bwd: needs width %% 32 == 0 and height %% 4 == 0 (got %dx%d)", H, W);
   RCOT_REQUIRE(u_bs % 4 == 0 && du_bs % 4 == 0 && dg_bs % 4 == 0 && ((uintptr_t)u % 16 == 0) &&
                    ((uintptr_t)du % 16 == 0) && ((uintptr_t)dg % 16 == 0) &&
                    (!g_out || (g_bs % 4 == 0 && (uintptr_t)g_out % 16 == 0)),

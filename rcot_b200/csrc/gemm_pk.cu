@@ -345,11 +345,17 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
 
   if (warp < PK_PROD_WARPS) {
     const int k8 = tid & 3, r0 = tid >> 2;   // 4 neighbouring lanes read 128 contiguous bytes of one row
-    const float* a_base = p.a + (size_t)(m0 + r0) * HW + k8 * 8;
-    const size_t a_mstride = (size_t)128 * HW;
+    // Loads are unconditional (rows beyond CA / N are clamped to the last valid row and the walker stops at the
+    // CTA's last chunk): a load whose result is merged under a predicate makes the compiler wait for it right
+    // away, which exposes the full global latency every chunk (measured: 80 % long-scoreboard stalls).
+    const float* a_ptr[MT];
     bool a_ok[MT];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) a_ok[m] = (m0 + m * 128 + r0) < p.CA;
+    for (int m = 0; m < MT; ++m) {
+      const int row = m0 + m * 128 + r0;
+      a_ok[m] = row < p.CA;
+      a_ptr[m] = p.a + (size_t)(a_ok[m] ? row : p.CA - 1) * HW + k8 * 8;
+    }
     bool b_ok[NBT];
     const float* b_ptr[NBT];
     float ga[NBT], be[NBT];
@@ -357,9 +363,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
     for (int j = 0; j < NBT; ++j) {
       const int r = r0 + 128 * j, n = n0 + r;
       b_ok[j] = (r < BN) && (n < Ntot);
-      b_ptr[j] = p.b + (size_t)(b_ok[j] ? n : 0) * HW + k8 * 8;
-      ga[j] = b_ok[j] ? __ldg(p.ln_gamma + n) : 0.f;
-      be[j] = b_ok[j] ? __ldg(p.ln_beta + n) : 0.f;
+      const int nc = b_ok[j] ? n : Ntot - 1;
+      b_ptr[j] = p.b + (size_t)nc * HW + k8 * 8;
+      ga[j] = __ldg(p.ln_gamma + nc);
+      be[j] = __ldg(p.ln_beta + nc);
     }
     const float2* stats = reinterpret_cast<const float2*>(p.ln_stats);
     auto ld8 = [&](float* v, const float* src) {
@@ -368,41 +375,37 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
     };
     float ra[MT][8], rb[NBT][8];
-    float2 st = make_float2(0.f, 0.f);
     // (image, first pixel) of the chunk whose loads are issued next
     int nb = c_begin / cpi;
     int nq0 = (c_begin - nb * cpi) * KC;
-    if (nchunks > 0) {
+    {
       const size_t ao = (size_t)nb * p.a_bs + nq0, bo = (size_t)nb * p.b_bs + nq0;
 #pragma unroll
-      for (int m = 0; m < MT; ++m)
-        if (a_ok[m]) ld8(ra[m], a_base + m * a_mstride + ao);
-      st = __ldg(stats + (size_t)nb * HW + nq0 + lane);
+      for (int m = 0; m < MT; ++m) ld8(ra[m], a_ptr[m] + ao);
 #pragma unroll
-      for (int j = 0; j < NBT; ++j)
-        if (b_ok[j]) ld8(rb[j], b_ptr[j] + bo);
+      for (int j = 0; j < NBT; ++j) ld8(rb[j], b_ptr[j] + bo);
     }
+    float2 st = __ldg(stats + (size_t)nb * HW + nq0 + lane);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nchunks; ++it) {
-      const bool more = it + 1 < nchunks;
-      nq0 += KC;                                  // walker -> the chunk after this one
-      if (nq0 >= HW) {
-        nq0 = 0;
-        ++nb;
+      if (it + 1 < nchunks) {                     // walker -> the chunk after this one (stays on the last chunk)
+        nq0 += KC;
+        if (nq0 >= HW) {
+          nq0 = 0;
+          ++nb;
+        }
       }
       const size_t ao = (size_t)nb * p.a_bs + nq0, bo = (size_t)nb * p.b_bs + nq0;
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* stg = smem + (size_t)s * stage_bytes;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        if (a_ok[m]) {
-          op_store8<TERMS>(stg + m * a_tile, stg + (MT + m) * a_tile, r0, k8, ra[m]);
-          if (more) ld8(ra[m], a_base + m * a_mstride + ao);
-        }
+        if (a_ok[m]) op_store8<TERMS>(stg + m * a_tile, stg + (MT + m) * a_tile, r0, k8, ra[m]);
+        ld8(ra[m], a_ptr[m] + ao);
       }
       const float2 stc = st;                      // statistics of pixel q0 + lane of THIS chunk
-      if (more) st = __ldg(stats + (size_t)nb * HW + nq0 + lane);
+      st = __ldg(stats + (size_t)nb * HW + nq0 + lane);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {               // this thread's 8 pixels are held by lanes k8*8+i (all lanes shuffle)
         const float mu = __shfl_sync(0xffffffffu, stc.x, k8 * 8 + i);
@@ -413,10 +416,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       uint8_t* b_hi = stg + TA * MT * a_tile;
 #pragma unroll
       for (int j = 0; j < NBT; ++j) {
-        if (b_ok[j]) {
-          op_store8<TERMS>(b_hi, b_hi + b_tile, r0 + 128 * j, k8, rb[j]);
-          if (more) ld8(rb[j], b_ptr[j] + bo);
-        }
+        if (b_ok[j]) op_store8<TERMS>(b_hi, b_hi + b_tile, r0 + 128 * j, k8, rb[j]);
+        ld8(rb[j], b_ptr[j] + bo);
       }
       fence_async_smem();
       __syncwarp();

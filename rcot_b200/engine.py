@@ -150,11 +150,14 @@ class AttnScratch:
         c = C // heads
         self.pb = ops.packed_bytes(C, C)
         self.pb12 = ops.packed_bytes(2 * C, 2 * C)
-        # one allocation for everything that must be zeroed per call: [sumsq | G | P]
-        self.zbuf = torch.zeros(B * (2 * C + heads * c * c + C * C), device=device)
-        self.sumsq = self.zbuf[:B * 2 * C].view(B, 2 * C)
-        self.G = self.zbuf[B * 2 * C:B * (2 * C + heads * c * c)].view(B, heads, c, c)
-        self.P = self.zbuf[B * (2 * C + heads * c * c):].view(B, C, C)
+        # one allocation for everything that must be zeroed per call: [sumsq | G | P | dA]
+        n0, n1, n2 = B * 2 * C, B * (2 * C + heads * c * c), B * (2 * C + heads * c * c + C * C)
+        self.zbuf = torch.zeros(n2 + B * heads * c * c, device=device)
+        self.sumsq = self.zbuf[:n0].view(B, 2 * C)
+        self.G = self.zbuf[n0:n1].view(B, heads, c, c)
+        self.P = self.zbuf[n1:n2].view(B, C, C)
+        self.dA = self.zbuf[n2:].view(B, heads, c, c)     # backward scratch: W_out^T P per head
+        self.bwd_z = self.zbuf[n1:]                       # what a backward without its own forward must zero
         self.A = torch.empty(B, heads, c, c, device=device)
         self.Gt = torch.empty(B, heads, c, c, device=device)
         self.Mpack = torch.zeros(B * self.pb, dtype=torch.uint8, device=device)
@@ -244,10 +247,10 @@ def mdta_bwd(bs: BlockSpec, x, dy, norm_name, residual, ctx):
     B, _, H, W = x.shape
     stats, pre, qkv, sc, st = ctx
     if st is not sc:
-        ops.zero_(sc.P)          # the forward that zeroed the shared scratch may be long gone
+        ops.zero_(sc.bwd_z)      # [P | dA]: the forward that zeroed the shared scratch may be long gone
     ops.pk_gemm(dy, qkv[:, 2 * C:], sc.P, ldo=C, per_image=True)
     ops.attn_bwd(sc.P, st.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], st.A, st.Gt,
-                 ps.g[a + "project_out.weight"], ps.g[a + "temperature"], sc.w12(), B, C, h)
+                 ps.g[a + "project_out.weight"], ps.g[a + "temperature"], sc.w12(), B, C, h, sc.dA)
     dqkv = torch.empty_like(qkv)
     ops.pm_gemm(qkv[:, :2 * C], sc.w12().data_ptr(), 2 * C, wpack_bs=sc.pb12, out=dqkv, out_coff=0)
     ops.pm_gemm(dy, st.MTpack.data_ptr(), C, wpack_bs=sc.pb, out=dqkv, out_coff=2 * C)

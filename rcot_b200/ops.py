@@ -64,7 +64,7 @@ class AttnParams(C.Structure):
         ("G", C.c_void_p), ("sumsq", C.c_void_p), ("temperature", C.c_void_p), ("w_out", C.c_void_p),
         ("A", C.c_void_p), ("Gt", C.c_void_p), ("Mpack", C.c_void_p), ("MTpack", C.c_void_p),
         ("pack_bs", C.c_int64), ("P", C.c_void_p), ("dw_out", C.c_void_p), ("dtemperature", C.c_void_p),
-        ("W12pack", C.c_void_p), ("pack12_bs", C.c_int64),
+        ("W12pack", C.c_void_p), ("pack12_bs", C.c_int64), ("dA", C.c_void_p),
     ]
 
 
@@ -318,7 +318,7 @@ def dwconv_bwd(x, dout, w, dw):
 
 def gdfn_mid_ok(u):
     """Geometry the fused GDFN middle backward accepts (every level of a training patch whose width is a multiple of 32)."""
-    return u.shape[3] % 32 == 0 and u.data_ptr() % 16 == 0 and _img_view(u, "u") % 4 == 0 and u.shape[1] % 2 == 0
+    return u.shape[3] % 32 == 0 and u.shape[2] % 4 == 0 and u.data_ptr() % 16 == 0 and _img_view(u, "u") % 4 == 0 and u.shape[1] % 2 == 0
 
 
 def gdfn_mid_bwd(u, dg, w, dw, g_out=None):
@@ -344,8 +344,10 @@ def attn_fwd(G, sumsq, temperature, w_out, A, Gt, Mpack, MTpack, B, Cc, heads):
     _lib.check(L().rcot_attn_fwd(C.byref(p), _stream()), "attn_fwd")
 
 
-def attn_bwd(P, sumsq, temperature, w_out, A, Gt, dw_out, dtemp, W12pack, B, Cc, heads):
+def attn_bwd(P, sumsq, temperature, w_out, A, Gt, dw_out, dtemp, W12pack, B, Cc, heads, dA):
+    """``dA``: zeroed [B, heads, c, c] scratch (phase 1 accumulates W_out^T P into it, phase 2 consumes it)."""
     p = AttnParams()
+    p.dA = dA.data_ptr()
     p.B, p.C, p.heads = B, Cc, heads
     p.sumsq, p.temperature, p.w_out = sumsq.data_ptr(), temperature.data_ptr(), w_out.data_ptr()
     p.A, p.Gt, p.P = A.data_ptr(), Gt.data_ptr(), P.data_ptr()

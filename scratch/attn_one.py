@@ -15,8 +15,9 @@ Mp = torch.zeros(B * pb, dtype=torch.uint8, device=dev); MTp = torch.zeros_like(
 W12 = torch.zeros(B * pb12, dtype=torch.uint8, device=dev)
 P = torch.randn(B, C, C, device=dev)
 dw = torch.zeros(C, C, device=dev); dt = torch.zeros(h, 1, 1, device=dev)
+dA = torch.zeros(B, h, c, c, device=dev)
 def fwd(): ops.attn_fwd(G, sumsq, temp, w_out, A, Gt, Mp, MTp, B, C, h)
-def bwd(): ops.attn_bwd(P, sumsq, temp, w_out, A, Gt, dw, dt, W12, B, C, h)
+def bwd(): ops.zero_(dA); ops.attn_bwd(P, sumsq, temp, w_out, A, Gt, dw, dt, W12, B, C, h, dA)
 for fn in (fwd, bwd):
     for _ in range(3): fn()
     torch.cuda.synchronize()
