@@ -31,7 +31,7 @@ constexpr int PK_MAX_STAGES = 4;
 template <int TERMS, bool GENERAL, bool LN, int NBT>
 __global__ void __launch_bounds__(PK_THREADS, 1)
     pk_gemm_kernel(const rcot_pk_params p, const int BN, const int nt, const int cpi, const int per_cta,
-                   const int total_chunks, const int stages, const uint32_t tmem_cols) {
+                   const int total_chunks, const int stages, const uint32_t tmem_cols, const int tr) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full_bar[PK_MAX_STAGES], empty_bar[PK_MAX_STAGES], done_bar;
   __shared__ uint32_t tmem_base_s;
@@ -273,22 +273,42 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
   if (warp < PK_PROD_WARPS && nchunks > 0) {
     mbar_wait(&done_bar, 0);
     tc_fence_after();
-    // ---- epilogue: thread = row m (TMEM lane), the two warp groups split the columns
+    // ---- epilogue: thread = row m (TMEM lane), the four warp groups split the columns.
+    // tr = 1: the launcher swapped the operands (see rcot_pk_gemm), so kernel row m is the caller's COLUMN: the
+    // 32 lanes of a warp then add to consecutive addresses (coalesced reductions).  Otherwise 16-byte vector
+    // reductions when the output rows are 16-byte aligned, scalar atomics as the last resort.
     const uint32_t lane_base = tmem_lane_base(tmem);
     const int m = m0 + (warp & 3) * 32 + lane;
     const int part = warp >> 2;               // 4 column parts
     const int ncols8 = BN / 8;
     const int c8_begin = (ncols8 * part) / 4, c8_end = (ncols8 * (part + 1)) / 4;
     float* ob = p.out + (size_t)g * p.out_gs + (p.per_image ? (size_t)bz * p.out_bs : 0);
+    const bool vec = !tr && ((reinterpret_cast<uintptr_t>(ob) & 15) == 0) && (p.ldo % 4 == 0);
     for (int c8 = c8_begin; c8 < c8_end; ++c8) {
       if (n0 + c8 * 8 >= Ntot) break;
       float v[8];
       tmem_ld8(lane_base + c8 * 8, v);
       if (m < p.CA) {
+        if (tr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = n0 + c8 * 8 + i;
-          if (n < Ntot) atomicAdd(ob + (size_t)m * p.ldo + n, v[i]);
+          for (int i = 0; i < 8; ++i) {
+            const int n = n0 + c8 * 8 + i;
+            if (n < Ntot) atomicAdd(ob + (size_t)n * p.ldo + m, v[i]);
+          }
+        } else if (vec && n0 + c8 * 8 + 8 <= Ntot) {
+          float* dst = ob + (size_t)m * p.ldo + n0 + c8 * 8;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                       "f"(v[3])
+                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                       "f"(v[7])
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = n0 + c8 * 8 + i;
+            if (n < Ntot) atomicAdd(ob + (size_t)m * p.ldo + n, v[i]);
+          }
         }
       }
     }
@@ -550,7 +570,7 @@ static int try_pk_mm(const rcot_pk_params& p, cudaStream_t stream) {
 }
 
 template <int TERMS, bool GENERAL, bool LN, int NBT>
-static int launch_pk_n(const rcot_pk_params& p, cudaStream_t stream) {
+static int launch_pk_n(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   const int Ntot = (p.CB1 + p.CB2) * p.ks * p.ks;
   const int HWa = p.Ha * p.Wa;
   int BN = round_up(Ntot, 16);
@@ -585,14 +605,15 @@ static int launch_pk_n(const rcot_pk_params& p, cudaStream_t stream) {
   RCOT_REQUIRE(zdim <= 65535 && S <= 65535, "pk_gemm: grid too large");
   dim3 grid(mt * nt, S, zdim);
   pk_gemm_kernel<TERMS, GENERAL, LN, NBT><<<grid, PK_THREADS, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks,
-                                                                             stages, tmem_cols_pow2(BN));
+                                                                             stages, tmem_cols_pow2(BN), tr);
   return check_launch("pk_gemm");
 }
 
 template <int TERMS, bool GENERAL, bool LN>
-static int launch_pk(const rcot_pk_params& p, cudaStream_t stream) {
+static int launch_pk(const rcot_pk_params& p, cudaStream_t stream, int tr = 0) {
   const int Ntot = (p.CB1 + p.CB2) * p.ks * p.ks;
-  return Ntot <= 128 ? launch_pk_n<TERMS, GENERAL, LN, 1>(p, stream) : launch_pk_n<TERMS, GENERAL, LN, 2>(p, stream);
+  return Ntot <= 128 ? launch_pk_n<TERMS, GENERAL, LN, 1>(p, stream, tr)
+                     : launch_pk_n<TERMS, GENERAL, LN, 2>(p, stream, tr);
 }
 
 }  // namespace rcot
@@ -623,5 +644,20 @@ extern "C" int rcot_pk_gemm(const rcot_pk_params* pp, rcot_stream_t stream_) {
     return p.terms == 3 ? launch_pk<3, false, true>(p, stream) : launch_pk<1, false, true>(p, stream);
   }
   if (general) return p.terms == 3 ? launch_pk<3, true, false>(p, stream) : launch_pk<1, true, false>(p, stream);
-  return p.terms == 3 ? launch_pk<3, false, false>(p, stream) : launch_pk<1, false, false>(p, stream);
+  int tr = 0;
+  if (p.b2 == nullptr && (p.ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0)) {
+    // The output rows are not 16-byte aligned (e.g. dW of GDFN's project_out: ldo = hid = 255): the two operands
+    // of a 1x1 product are interchangeable, so swap them and let the epilogue write the transpose -- TMEM lanes
+    // (consecutive threads) then map to consecutive output addresses and the reductions coalesce.
+    rcot_pk_params q = p;
+    q.a = p.b;
+    q.a_bs = p.b_bs;
+    q.CA = p.CB1;
+    q.b = p.a;
+    q.b_bs = p.a_bs;
+    q.CB1 = p.CA;
+    p = q;
+    tr = 1;
+  }
+  return p.terms == 3 ? launch_pk<3, false, false>(p, stream, tr) : launch_pk<1, false, false>(p, stream, tr);
 }

@@ -19,7 +19,10 @@ def _close(name, got, ref, rtol=1e-3, atol=1e-4):
 @pytest.mark.parametrize("Cin,Cout,k,s,p,H,W", [(48, 24, 3, 1, 1, 16, 16), (3, 64, 5, 1, 2, 16, 16),
                                                 (64, 64, 4, 2, 1, 16, 16), (256, 512, 3, 1, 1, 8, 8),
                                                 (512, 512, 4, 2, 1, 4, 4), (512, 512, 4, 2, 1, 2, 2),
-                                                (96, 3, 3, 1, 1, 10, 14), (96, 300, 1, 1, 0, 8, 8)])
+                                                (96, 3, 3, 1, 1, 10, 14), (96, 300, 1, 1, 0, 8, 8),
+                                                # ldo % 4 != 0: operands swapped, transposed (coalesced) reductions
+                                                (127, 48, 1, 1, 0, 16, 16), (255, 96, 1, 1, 0, 8, 16),
+                                                (510, 192, 1, 1, 0, 8, 8)])
 def test_conv_wgrad(cuda_lib, Cin, Cout, k, s, p, H, W):
     from rcot_b200 import ops
     g = torch.Generator().manual_seed(Cin + Cout + k)
@@ -243,3 +246,26 @@ def test_gdfn_mid_bwd_fused(cuda_lib, B, hid, H, W, with_g):
     if with_g:
         torch.testing.assert_close(gout, g2, rtol=1e-5, atol=1e-6)
     _close("dw vs two-kernel", dw, dw2.cpu().double(), rtol=2e-3)
+
+
+@pytest.mark.parametrize("B,CA,CB,H,W,off", [(3, 254, 48, 8, 8, 0), (2, 1020, 192, 8, 8, 0), (2, 300, 384, 4, 8, 0),
+                                             (3, 288, 96, 8, 16, 1), (1, 144, 48, 16, 16, 0)])
+def test_wgrad_ln_multi_m(cuda_lib, B, CA, CB, H, W, off):
+    """The multi-M pixel-as-K kernel (MT = 2 / 4 accumulators per CTA, NBT = 1 / 2, two N tiles, chunk walker across
+    images, vector and scalar reductions) against fp64: dW = dOut LN(x)^T as in the blocks' 1x1 weight gradients."""
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(CA + CB + off)
+    x = torch.randn(B, CB, H, W, generator=g) + 0.5
+    du = torch.randn(B, CA, H, W, generator=g)
+    gamma, beta = torch.randn(CB, generator=g), torch.randn(CB, generator=g)
+    xd = x.double()
+    mu = xd.mean(1, keepdim=True)
+    rstd = 1 / torch.sqrt(((xd - mu) ** 2).mean(1, keepdim=True) + 1e-5)
+    z = (xd - mu) * rstd * gamma.double().view(1, -1, 1, 1) + beta.double().view(1, -1, 1, 1)
+    ref = torch.einsum("bnhw,bchw->nc", du.double(), z)
+    stats = ops.ln_stats(x.cuda())
+    prev = torch.randn(CA * CB + off, generator=g)
+    buf = prev.cuda().clone()
+    out = buf[off:].view(CA, CB)          # off = 1: rows not 16-byte aligned -> scalar reductions
+    ops.pk_gemm(du.cuda(), x.cuda(), out, ldo=CB, ln=(stats, gamma.cuda(), beta.cuda()))
+    _close("dW_ln_mm", out, prev[off:].view(CA, CB).double() + ref)
