@@ -88,8 +88,8 @@ typedef struct {
   float* stats_out;     /* optional [B, Hr*Wr, 2]: LayerNorm (mean, rstd) over the N output channels of every pixel,
                            computed in the epilogue (needs N <= 256, i.e. one pass) for the LN that consumes `out` */
   int32_t debug;        /* unused (bring-up knobs) */
-  int32_t tap_major;    /* ks > 1: K is ordered (ky, kx, channel); needs C1 % 32 == 0 and no concat: a K-chunk
-                           is 32 channels at ONE tap, so the gather is a strided read like the 1x1 case */
+  int32_t tap_major;    /* ks > 1: K is ordered (ky, kx, channel); needs C1 % 16 == 0 and no concat: a producer
+                           thread's 16 K indices are 16 channels at ONE tap: a strided read like the 1x1 case */
 } rcot_pm_params;
 
 int rcot_pm_gemm(const rcot_pm_params* p, rcot_stream_t stream);

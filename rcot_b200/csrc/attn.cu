@@ -131,10 +131,9 @@ constexpr int AB_T = 6;    // largest register tile edge: ceil(96 / 16)
 // T = ceil(c/16); partial over this CTA's rows -> atomics into the zeroed scratch dA) and
 // dW_out[co,(h,i)] += sum_j P[co,(h,j)] A[i,j]  (2 x T outputs per thread, complete for these rows).
 // One CTA per (head, image) for all of it ran at < 1 IPC on 32 SMs; split by rows it fills the machine.
-__global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params p) {
+__global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params p, const int nsub) {
   extern __shared__ __align__(16) float sm[];
   const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
-  const int co0 = blockIdx.z * AB_CH;
   const int ca = c + 1;         // padded row stride of sA: threads that differ in the row hit different banks
   float* sA = sm;               // [c*ca] softmax probabilities A[i][j]
   float* sW = sA + c * ca;      // [AB_CH*c] rows of W_out[:, head block]
@@ -150,34 +149,44 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
       ++i;
     }
   }
-  for (int r = tid / c, i = tid - (tid / c) * c; r < AB_CH;) {
-    const bool in = co0 + r < C;              // a partial last chunk is zero-filled
-    sW[r * c + i] = in ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;
-    sP[r * c + i] = in ? __ldg(Pm + (size_t)(co0 + r) * C + h * c + i) : 0.f;
-    i += 256;
-    while (i >= c) {
-      i -= c;
-      ++r;
-    }
-  }
-  __syncthreads();
   const int T = (c + 15) >> 4;            // register tile edge (<= AB_T)
   const int nt = (c + T - 1) / T;         // tiles per dimension (<= 16)
-  {
-    // dA role: thread (ti, tj) owns rows ti*T.., columns tj*T.. of dA
-    const int ti = tid / nt, tj = tid - ti * nt;
-    if (ti < nt) {
-      int ia[AB_T], ja[AB_T];
+  // dA role: thread (ti, tj) owns rows ti*T.., columns tj*T.. of dA
+  const int ti = tid / nt, tj = tid - ti * nt;
+  const bool da_on = ti < nt;
+  int ia[AB_T], ja[AB_T];
 #pragma unroll
-      for (int q = 0; q < AB_T; ++q) {
-        ia[q] = min(ti * T + q, c - 1);       // clamped: duplicates are never stored
-        ja[q] = min(tj * T + q, c - 1);
+  for (int q = 0; q < AB_T; ++q) {
+    ia[q] = min(ti * T + q, c - 1);       // clamped: duplicates are never stored
+    ja[q] = min(tj * T + q, c - 1);
+  }
+  float acc[AB_T][AB_T];
+#pragma unroll
+  for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+    for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
+  // dW_out role: thread (rg, ig) owns staged rows 2rg, 2rg+1 and head columns ig*T..
+  const int rg = tid >> 4, ig = tid & 15;
+  int iw[AB_T];
+#pragma unroll
+  for (int q = 0; q < AB_T; ++q) iw[q] = min(ig * T + q, c - 1) * ca;
+  // a CTA walks nsub sub-chunks of AB_CH rows (wide layers: fewer, longer CTAs -> fewer dA atomics)
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int co0 = (blockIdx.z * nsub + sub) * AB_CH;
+    if (co0 >= C) break;
+    __syncthreads();                          // sA filled (first pass) / previous sub-chunk consumed
+    for (int r = tid / c, i = tid - (tid / c) * c; r < AB_CH;) {
+      const bool in = co0 + r < C;            // a partial last chunk is zero-filled
+      sW[r * c + i] = in ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;
+      sP[r * c + i] = in ? __ldg(Pm + (size_t)(co0 + r) * C + h * c + i) : 0.f;
+      i += 256;
+      while (i >= c) {
+        i -= c;
+        ++r;
       }
-      float acc[AB_T][AB_T];
-#pragma unroll
-      for (int x = 0; x < AB_T; ++x)
-#pragma unroll
-        for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
+    }
+    __syncthreads();
+    if (da_on) {
 #pragma unroll 4
       for (int r = 0; r < AB_CH; ++r) {
         float wv[AB_T], pv[AB_T];
@@ -193,20 +202,7 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
           for (int y = 0; y < AB_T; ++y)
             if (x < T && y < T) acc[x][y] = fmaf(wv[x], pv[y], acc[x][y]);
       }
-      float* dA = p.dA + hb;
-#pragma unroll
-      for (int x = 0; x < AB_T; ++x)
-#pragma unroll
-        for (int y = 0; y < AB_T; ++y)
-          if (x < T && y < T && ti * T + x < c && tj * T + y < c) atomicAdd(dA + (ti * T + x) * c + tj * T + y, acc[x][y]);
     }
-  }
-  {
-    // dW_out role: thread (rg, ig) owns staged rows 2rg, 2rg+1 and head columns ig*T..
-    const int rg = tid >> 4, ig = tid & 15;
-    int iw[AB_T];
-#pragma unroll
-    for (int q = 0; q < AB_T; ++q) iw[q] = min(ig * T + q, c - 1) * ca;
     float aw[2][AB_T];
 #pragma unroll
     for (int q = 0; q < AB_T; ++q) aw[0][q] = aw[1][q] = 0.f;
@@ -232,6 +228,14 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
           if (q < T && ig * T + q < c) atomicAdd(p.dw_out + (size_t)co * C + h * c + ig * T + q, aw[k][q]);
       }
     }
+  }
+  if (da_on) {
+    float* dA = p.dA + hb;
+#pragma unroll
+    for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+      for (int y = 0; y < AB_T; ++y)
+        if (x < T && y < T && ti * T + x < c && tj * T + y < c) atomicAdd(dA + (ti * T + x) * c + tj * T + y, acc[x][y]);
   }
 }
 
@@ -384,8 +388,11 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
     }
     attr_set = true;
   }
-  dim3 grid1(p.heads, p.B, cdiv(p.C, AB_CH));
-  attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p);
+  int nsub = p.C / 96;                         // 1 for C <= 191, 2 for C = 192, 4 for C = 384
+  if (nsub < 1) nsub = 1;
+  if (nsub > 4) nsub = 4;
+  dim3 grid1(p.heads, p.B, cdiv(p.C, AB_CH * nsub));
+  attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p, nsub);
   rc = check_launch("attn_bwd(p1)");
   if (rc) return rc;
   dim3 grid2(p.heads, p.B);

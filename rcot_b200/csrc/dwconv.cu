@@ -13,9 +13,27 @@
 
 namespace rcot {
 
-__device__ __forceinline__ float gelu_erf_d(float a) { return 0.5f * a * (1.f + erff(a * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad_d(float a) {
-  return 0.5f * (1.f + erff(a * 0.70710678118654752f)) + a * 0.39894228040143268f * __expf(-0.5f * a * a);
+// gelu(a) = a*Phi(a) and gelu'(a) = Phi(a) + a*phi(a) from ONE exponential: Phi through the Abramowitz-Stegun
+// 7.1.26 rational form of erfc (absolute error 1.5e-7 in erf, i.e. < 1e-7 in Phi -- fp32 rounding level), whose
+// exp(-a^2/2) factor is the same one phi needs.
+__device__ __forceinline__ void gelu_pair(float a, float& ge, float& dge) {
+  const float x = fabsf(a) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.f));
+  const float e = __expf(-x * x);
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float tail = 0.5f * q * t * e;            // Phi(-|a|)
+  const float Phi = a >= 0.f ? 1.f - tail : tail;
+  ge = a * Phi;
+  dge = fmaf(a * 0.39894228040143268f, e, Phi);
+}
+
+__device__ __forceinline__ float gelu_fast(float a) {
+  float ge, dge;
+  gelu_pair(a, ge, dge);   // the derivative is dead code here
+  return ge;
 }
 
 template <int ROWS>
@@ -180,16 +198,17 @@ __global__ void __launch_bounds__(256)
     const int pr = pix + r * g.W;
     if (MODE == 1) {
       *reinterpret_cast<float4*>(out + (size_t)t.b * out_bs + (size_t)t.ch * HW + pr) =
-          make_float4(gelu_erf_d(a[r][0]) * gt[r][0], gelu_erf_d(a[r][1]) * gt[r][1], gelu_erf_d(a[r][2]) * gt[r][2],
-                      gelu_erf_d(a[r][3]) * gt[r][3]);
+          make_float4(gelu_fast(a[r][0]) * gt[r][0], gelu_fast(a[r][1]) * gt[r][1], gelu_fast(a[r][2]) * gt[r][2],
+                      gelu_fast(a[r][3]) * gt[r][3]);
     } else {
       const float4 d4 = __ldg(reinterpret_cast<const float4*>(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pr));
       const float d[4] = {d4.x, d4.y, d4.z, d4.w};
       float da[4], db[4], gg[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float ga = gelu_erf_d(a[r][j]);
-        da[j] = d[j] * gt[r][j] * gelu_erf_grad_d(a[r][j]);
+        float ga, dga;
+        gelu_pair(a[r][j], ga, dga);
+        da[j] = d[j] * gt[r][j] * dga;
         db[j] = d[j] * ga;
         gg[j] = ga * gt[r][j];
       }
@@ -293,23 +312,6 @@ constexpr int GF_T = 32;            // tile edge
 constexpr int GF_LD = GF_T + 8;     // row stride of both regions: image columns x0-4 .. x0+35 (index = x - x0 + 4)
 constexpr int GF_UH = GF_T + 4;     // u region rows y0-2 .. y0+33
 constexpr int GF_DH = GF_T + 2;     // [da; db] region rows y0-1 .. y0+32 (columns x0-1 .. x0+32 are used)
-
-// gelu(a) = a*Phi(a) and gelu'(a) = Phi(a) + a*phi(a) from ONE exponential: Phi through the Abramowitz-Stegun
-// 7.1.26 rational form of erfc (absolute error 1.5e-7 in erf, i.e. < 1e-7 in Phi -- fp32 rounding level), whose
-// exp(-a^2/2) factor is the same one phi needs.
-__device__ __forceinline__ void gelu_pair(float a, float& ge, float& dge) {
-  const float x = fabsf(a) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.f));
-  const float e = __expf(-x * x);
-  float q = fmaf(1.061405429f, t, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  const float tail = 0.5f * q * t * e;            // Phi(-|a|)
-  const float Phi = a >= 0.f ? 1.f - tail : tail;
-  ge = a * Phi;
-  dge = fmaf(a * 0.39894228040143268f, e, Phi);
-}
 
 __global__ void __launch_bounds__(256, 4)
     gdfn_mid_bwd_kernel(const float* __restrict__ u, int64_t u_bs, const float* __restrict__ dg, int64_t dg_bs,

@@ -137,13 +137,14 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         return;
       }
       if (p.tap_major) {
-        // K = (ky, kx, channel): this chunk is 32 channels at one tap -> one bounds test, strided reads
-        const int cpt = p.C1 >> 5;                    // chunks per tap
-        const int tap = c / cpt;
-        const int ch0 = (c - tap * cpt) * KC + khalf * 16;
+        // K = (ky, kx, channel), C1 % 16 == 0: this thread's 16 consecutive K indices are 16 channels at ONE tap
+        // -> one bounds test, strided reads (the K padding of the last chunk maps to tap >= KS*KS: zeros)
+        const int k0 = c * KC + khalf * 16;
+        const int tap = k0 / p.C1;
+        const int ch0 = k0 - tap * p.C1;
         const int ky = tap / KS, kx = tap - ky * KS;
         int sy, sx;
-        bool ok = x.valid;
+        bool ok = x.valid && tap < KS * KS;
         if (MODE == 0) {
           sy = x.ry + ky;
           sx = x.rx + kx;
@@ -500,7 +501,7 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
     RCOT_REQUIRE(p.N <= 256 && !p.bias && !p.act && !p.mask_y && !p.accumulate && p.out_coff == 0,
                  "pm_gemm: stats_out needs N <= 256 and the plain / residual epilogue");
   if (p.tap_major)
-    RCOT_REQUIRE(p.ks > 1 && p.C2 == 0 && p.C1 % 32 == 0, "pm_gemm: tap_major needs ks > 1, no concat, C1 %% 32 == 0");
+    RCOT_REQUIRE(p.ks > 1 && p.C2 == 0 && p.C1 % 16 == 0, "pm_gemm: tap_major needs ks > 1, no concat, C1 %% 16 == 0");
 #define PM_DISPATCH(KS, MODE, LN)                                           \
   return (p.terms == 3) ? launch_pm<KS, MODE, 3, LN>(p, stream) : launch_pm<KS, MODE, 1, LN>(p, stream)
   switch (p.ks) {

@@ -129,7 +129,7 @@ def conv_pack_kind(w: torch.Tensor, dgrad: bool, concat: bool = False) -> str:
     """Tap-major K order whenever the gathered tensor's channel count allows the fast producer path."""
     Cout, Cin, kh, kw = w.shape
     gathered = Cout if dgrad else Cin
-    tap = kh * kw > 1 and gathered % 32 == 0 and not concat
+    tap = kh * kw > 1 and gathered % 16 == 0 and not concat
     return ("dgrad" if dgrad else "fwd") + ("_tap" if tap else "")
 
 
