@@ -388,9 +388,7 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
     }
     attr_set = true;
   }
-  int nsub = p.C / 96;                         // 1 for C <= 191, 2 for C = 192, 4 for C = 384
-  if (nsub < 1) nsub = 1;
-  if (nsub > 4) nsub = 4;
+  const int nsub = 1;   // sub-chunks per CTA: longer CTAs (2, 4) measured slower at C = 192 / 384, so one chunk each
   dim3 grid1(p.heads, p.B, cdiv(p.C, AB_CH * nsub));
   attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p, nsub);
   rc = check_launch("attn_bwd(p1)");

@@ -10,6 +10,7 @@
 // The generic kernels in elem.cu remain the fallback for odd sizes (whole-image inference).
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace rcot {
 
@@ -165,12 +166,11 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------ GELU gate: forward / backward
 // mode 1: out[j] = gelu(dw(in[j])) * dw(in[j+hid])
 // mode 2: a = dw(in[j]), b = dw(in[j+hid]); out[j] = dg*b*gelu'(a); out[j+hid] = dg*gelu(a); g_out[j] = gelu(a)*b
-template <int MODE>
+template <int MODE, int ROWS>
 __global__ void __launch_bounds__(256)
     dw_gate_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ w, float* __restrict__ out,
                    int64_t out_bs, int hid, const float* __restrict__ dg, int64_t dg_bs, float* __restrict__ g_out,
                    int64_t g_bs, const DwGeom g) {
-  constexpr int ROWS = 2;
   const DwThread t = dw_map(g, ROWS);
   if (!t.active) return;
   const int HW = g.H * g.W;
@@ -223,11 +223,11 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------ fused backward: din and dW
+template <int ROWS>
 __global__ void __launch_bounds__(256)
     dw_bwd2_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
                    const float* __restrict__ w, float* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
                    const DwGeom g, const int ppt) {
-  constexpr int ROWS = 2;
   DwThread t = dw_map(g, ROWS);
   const int HW = g.H * g.W;
   float acc[9];
@@ -510,6 +510,15 @@ int gdfn_mid_bwd_fast(const float* u, int64_t u_bs, const float* dg, int64_t dg_
 }
 
 // ------------------------------------------------------------------ launch geometry
+static int dw_rows_pref() {
+  static int pref = 0;
+  if (pref == 0) {
+    const char* e = getenv("RCOT_DW_ROWS");
+    pref = (e && e[0] == '2') ? 2 : 4;
+  }
+  return pref;
+}
+
 static bool dw_geom(DwGeom& g, dim3& grid, int B, int planes, int H, int W, int rows) {
   if (W % 4 != 0 || H % rows != 0 || B > 65535) return false;
   g.H = H;
@@ -550,12 +559,23 @@ int dwconv_fast(const rcot_dw_params& p, int planes, cudaStream_t st) {
     }
     return 0;
   }
-  if (!dw_geom(g, grid, p.B, planes, p.H, p.W, 2)) return 0;
+  // gate kernels: 4x4 output patches when the plane allows (halo rows re-read 1.5x instead of 2x), RCOT_DW_ROWS=2
+  // forces the 4x2 patches (A/B switch)
+  const int rows = (dw_rows_pref() == 4 && p.H % 4 == 0 && dw_geom(g, grid, p.B, planes, p.H, p.W, 4)) ? 4 : 2;
+  if (rows == 2 && !dw_geom(g, grid, p.B, planes, p.H, p.W, 2)) return 0;
   if (p.mode == 1) {
-    dw_gate_kernel<1><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
+    if (rows == 4)
+      dw_gate_kernel<1, 4><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
+    else
+      dw_gate_kernel<1, 2><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
   } else {
     if (p.dg_bs % 4 != 0 || (p.g_out && p.g_bs % 4 != 0)) return 0;
-    dw_gate_kernel<2><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, p.dg, p.dg_bs, p.g_out, p.g_bs, g);
+    if (rows == 4)
+      dw_gate_kernel<2, 4><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, p.dg, p.dg_bs, p.g_out,
+                                                 p.g_bs, g);
+    else
+      dw_gate_kernel<2, 2><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, p.dg, p.dg_bs, p.g_out,
+                                                 p.g_bs, g);
   }
   return 1;
 }
@@ -564,7 +584,8 @@ int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t d
                     int64_t din_bs, float* dw, int B, int Cn, int H, int W, cudaStream_t st) {
   DwGeom g;
   dim3 grid;
-  if (!dw_geom(g, grid, B, Cn, H, W, 2)) return 0;
+  const int rows = (dw_rows_pref() == 4 && H % 4 == 0 && dw_geom(g, grid, B, Cn, H, W, 4)) ? 4 : 2;
+  if (rows == 2 && !dw_geom(g, grid, B, Cn, H, W, 2)) return 0;
   int ppt = 1;
   if (g.pshift < 0) {   // large planes: up to 4 patches per thread
     ppt = g.ppp / 256;
@@ -572,7 +593,10 @@ int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t d
     if (ppt < 1) ppt = 1;
     grid.x = cdiv(g.ppp, 256 * ppt);
   }
-  dw_bwd2_kernel<<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt);
+  if (rows == 4)
+    dw_bwd2_kernel<4><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt);
+  else
+    dw_bwd2_kernel<2><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt);
   return 1;
 }
 

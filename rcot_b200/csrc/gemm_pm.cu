@@ -26,6 +26,10 @@ constexpr int PM_THREADS = (PM_PROD_WARPS + 1 + 4) * 32;  // producers, MMA warp
 
 struct PmGeom {
   int Ktot, nk, BN, passes, stages, tiles_m, tiles_per_img, flat, c1_aligned;
+  // parity classes of a stride-2 transposed conv (dgrad of the 4x4 stride-2 convs): an output pixel only sees the
+  // taps with ky = (y + pad) mod 2 (+2), kx likewise -- 4 of 16 -- so tiles hold pixels of ONE (y&1, x&1) class and
+  // the K loop runs over that class's 4 taps only (nk = 4 * C1/32 chunks) instead of multiplying 75 % zeros.
+  int cls, tpc, nk_full; // cls: enabled; tpc: tiles per class; nk_full: K chunks of the packed weights (nk = the loop's)
   long rows_total;
   uint32_t tmem_cols;
 };
@@ -80,13 +84,25 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       const uint8_t* wsrc;
       float mu, rstd;
       int ry, rx;
+      int cls;                // parity class (y&1)*2 + (x&1) of the tile's pixels (g.cls only)
       bool valid;
     };
     auto setup = [&](int t) {
       TileCtx x;
       const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
       int b, pix;
-      if (g.flat) {
+      x.cls = 0;
+      if (g.cls) {
+        const int cl = mt / g.tpc;
+        const long r = (long)(mt - cl * g.tpc) * 128 + row;
+        const int q = HWr >> 2, hw2 = p.Wr >> 1;          // pixels per class and image, class-grid width
+        x.valid = r < (long)q * p.B;
+        b = x.valid ? (int)(r / q) : 0;
+        const int rem = x.valid ? (int)(r - (long)b * q) : 0;
+        const int yy = rem / hw2, xx = rem - yy * hw2;
+        pix = (2 * yy + (cl >> 1)) * p.Wr + 2 * xx + (cl & 1);
+        x.cls = cl;
+      } else if (g.flat) {
         const long r = (long)mt * 128 + row;
         x.valid = r < g.rows_total;
         b = x.valid ? (int)(r / HWr) : 0;
@@ -113,7 +129,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         x.rstd = st.y;
       }
       x.wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
-               (size_t)pass * nk * (2 * b_tile);
+               (size_t)pass * g.nk_full * (2 * b_tile);
       return x;
     };
     auto load16 = [&](float* v, const TileCtx& x, int c) {
@@ -140,8 +156,13 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         // K = (ky, kx, channel), C1 % 16 == 0: this thread's 16 consecutive K indices are 16 channels at ONE tap
         // -> one bounds test, strided reads (the K padding of the last chunk maps to tap >= KS*KS: zeros)
         const int k0 = c * KC + khalf * 16;
-        const int tap = k0 / p.C1;
+        int tap = k0 / p.C1;
         const int ch0 = k0 - tap * p.C1;
+        if (MODE == 1 && g.cls) {
+          // c runs over this class's 4 taps: (ky, kx) = (ky0 + 2*(tap>>1), kx0 + 2*(tap&1))
+          const int ky0 = ((x.cls >> 1) + p.pad) & 1, kx0 = ((x.cls & 1) + p.pad) & 1;
+          tap = (ky0 + 2 * (tap >> 1)) * KS + kx0 + 2 * (tap & 1);
+        }
         const int ky = tap / KS, kx = tap - ky * KS;
         int sy, sx;
         bool ok = x.valid && tap < KS * KS;
@@ -252,7 +273,13 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       uint8_t* st = smem + (size_t)s * stage_bytes;
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
-        bulk_g2s(st + TA * a_tile, S.x.wsrc + (size_t)S.c * (2 * b_tile), TA * b_tile, &full_bar[s]);
+        int wc = S.c;               // chunk of the packed weights (tap-major: chunk = tap * C1/32 + channel chunk)
+        if (MODE == 1 && g.cls) {
+          const int cpt = p.C1 >> 5, te = S.c / cpt;
+          const int ky0 = ((S.x.cls >> 1) + p.pad) & 1, kx0 = ((S.x.cls & 1) + p.pad) & 1;
+          wc = ((ky0 + 2 * (te >> 1)) * KS + kx0 + 2 * (te & 1)) * cpt + (S.c - te * cpt);
+        }
+        bulk_g2s(st + TA * a_tile, S.x.wsrc + (size_t)wc * (2 * b_tile), TA * b_tile, &full_bar[s]);
       }
       if (LN) {
         const float* gb = ln_gb + (S.c * KC + khalf * 16) * 2;   // interleaved (gamma, beta), zero beyond Ktot
@@ -324,7 +351,16 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
       int b, pix;
       bool valid;
-      if (g.flat) {
+      if (g.cls) {
+        const int cl = mt / g.tpc;
+        const long r = (long)(mt - cl * g.tpc) * 128 + row;
+        const int q = HWr >> 2, hw2 = p.Wr >> 1;
+        valid = r < (long)q * p.B;
+        b = valid ? (int)(r / q) : 0;
+        const int rem = valid ? (int)(r - (long)b * q) : 0;
+        const int yy = rem / hw2, xx = rem - yy * hw2;
+        pix = (2 * yy + (cl >> 1)) * p.Wr + 2 * xx + (cl & 1);
+      } else if (g.flat) {
         const long r = (long)mt * 128 + row;
         valid = r < g.rows_total;
         b = valid ? (int)(r / HWr) : 0;
@@ -455,6 +491,16 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   g.tiles_per_img = cdiv(HWr, 128);
   g.tiles_m = g.flat ? cdiv(g.rows_total, 128) : g.tiles_per_img * p.B;
   g.tmem_cols = tmem_cols_pow2(2 * pl.BN);
+  g.nk_full = g.nk;
+  g.cls = 0;
+  g.tpc = 0;
+  if (MODE == 1 && KS == 4 && p.stride == 2 && p.tap_major && p.C1 % 32 == 0 && g.flat && p.Hr % 2 == 0 &&
+      p.Wr % 2 == 0) {
+    g.cls = 1;
+    g.tpc = cdiv(HWr / 4 * p.B, 128);
+    g.tiles_m = 4 * g.tpc;
+    g.nk = 4 * (p.C1 / 32);
+  }
   const size_t smem = stages * stage_bytes + ln_bytes;
   static bool attr_set = false;
   if (!attr_set) {
