@@ -344,8 +344,11 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
     // =========================================================== epilogue (warp % 4 = TMEM lane quarter)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const bool epi_other = p.bias || p.act || p.mask_y || p.accumulate;
-    const bool epi_plain = !epi_other && !p.residual, epi_res = !epi_other && p.residual;
+    // fast epilogues (operand of the fused op prefetched one 16-channel group ahead of the stores): plain, residual
+    // add, and the LeakyReLU-derivative mask of F_net's data gradients; everything else takes the generic path
+    const bool epi_mask = p.mask_y && !p.bias && !p.act && !p.accumulate && !p.residual;
+    const bool epi_other = (p.bias || p.act || p.mask_y || p.accumulate) && !epi_mask;
+    const bool epi_plain = !epi_other && !epi_mask && !p.residual, epi_res = !epi_other && !epi_mask && p.residual;
     uint32_t tcount = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
       const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
@@ -384,9 +387,10 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       float qa[16], qb[16];                              // residual values, fetched one group ahead
       float ln_s0 = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;       // shifted sums for the optional LayerNorm statistics
       const bool want_stats = p.stats_out != nullptr;
+      const float* pre = epi_mask ? mk : rs;   // tensor whose values are fetched ahead (same indexing as out)
       auto ldres = [&](float (&q)[16], int gi) {
         const int nrem = ncols - gi * 16;
-        const float* r0 = rs + (size_t)(gi * 16) * HWr;
+        const float* r0 = pre + (size_t)(gi * 16) * HWr;
 #pragma unroll
         for (int i = 0; i < 16; ++i) q[i] = (st_ok && i < nrem) ? __ldg(r0 + (size_t)i * HWr) : 0.f;
       };
@@ -394,10 +398,15 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         const int nrem = ncols - gi * 16;
         if (!st_ok) return;
         float* og = o + (size_t)(gi * 16) * HWr;
-        if (epi_plain || epi_res) {
+        if (epi_plain || epi_res || epi_mask) {
           float y[16];
+          if (epi_mask) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(cur[i]) + (epi_res ? q[i] : 0.f);
+            for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(cur[i]) * (q[i] > 0.f ? 1.f : p.slope);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(cur[i]) + (epi_res ? q[i] : 0.f);
+          }
           if (nrem >= 16) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) og[(size_t)i * HWr] = y[i];
@@ -433,20 +442,21 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         }
       };
       const uint32_t tbase = lane_base + buf * BN;
+      const bool pref = epi_res || epi_mask;
       tmem_ld16_nowait(tbase, ra);
-      if (epi_res) ldres(qa, 0);
+      if (pref) ldres(qa, 0);
       for (int gi = 0; gi < ngroups; gi += 2) {   // TMEM + residual loads run one group ahead of the stores
         tmem_ld_wait();
         if (gi + 1 < ngroups) {
           tmem_ld16_nowait(tbase + (gi + 1) * 16, rb);
-          if (epi_res) ldres(qb, gi + 1);
+          if (pref) ldres(qb, gi + 1);
         }
         emit(ra, qa, gi);
         if (gi + 1 < ngroups) {
           tmem_ld_wait();
           if (gi + 2 < ngroups) {
             tmem_ld16_nowait(tbase + (gi + 2) * 16, ra);
-            if (epi_res) ldres(qa, gi + 2);
+            if (pref) ldres(qa, gi + 2);
           }
           emit(rb, qb, gi + 1);
         }

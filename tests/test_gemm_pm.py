@@ -106,6 +106,12 @@ def test_conv_fwd_dgrad(cuda_lib, Cin, Cout, k, s, p, H, W, bias, act):
     ops.pm_gemm(dy.cuda(), pkT.ptr(0), Cin, ks=k, stride=s, pad=p, mode=1, out_hw=(H, W), out=acc,
                 mask_y=mask.cuda(), accumulate=True)
     _close(acc, prev.double() + refdx * torch.where(mask > 0, 1.0, 0.2).double())
+    # mask alone: the prefetching epilogue of F_net's data gradients (and the parity-class tiles when k=4, s=2)
+    for tap in ([False, True] if Cout % 16 == 0 else [False]):
+        pkm = ops.pack_single(wd, "dgrad_tap" if tap else "dgrad")
+        only = ops.pm_gemm(dy.cuda(), pkm.ptr(0), Cin, ks=k, stride=s, pad=p, mode=1, out_hw=(H, W), mask_y=mask.cuda(),
+                           tap_major=tap)
+        _close(only, refdx * torch.where(mask > 0, 1.0, 0.2).double())
 
 
 def test_bf16_single_term(cuda_lib):
