@@ -22,19 +22,39 @@ __device__ __forceinline__ float warp_max_a(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ void store_split(uint8_t* base, int N, int K, int n, int k, float w) {
+// Packed-operand geometry of an [N x K] matrix (tc.cuh packed_offset), with the divisions by runtime values done
+// once per kernel instead of once per store: passes of BN columns, nk K-chunks, `tile` bytes per (pass, chunk, term).
+struct PackGeom {
+  int BN, nk;
+  uint32_t tile;
+  __device__ PackGeom(int N, int K) {
+    const int nst = (N + 255) / 256;
+    BN = ((N + nst - 1) / nst + 15) / 16 * 16;
+    nk = (K + KC - 1) / KC;
+    tile = op_tile_bytes(BN);
+  }
+  // byte offset of element (n, k) in the hi image; the lo image follows at +tile.  N <= 768 here: at most 3 passes.
+  __device__ __forceinline__ size_t hi(int n, int k) const {
+    const int pass = (n >= 2 * BN) ? 2 : (n >= BN ? 1 : 0);
+    const int np = n - pass * BN, kc = k >> 5, kp = k & 31;
+    return ((size_t)(pass * nk + kc) * 2) * tile + op_offset(np, kp);
+  }
+};
+__device__ __forceinline__ void store_split(uint8_t* base, const PackGeom& pg, int n, int k, float w) {
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-  *reinterpret_cast<__nv_bfloat16*>(base + packed_offset(N, K, n, k, 0)) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(base + packed_offset(N, K, n, k, 1)) = lo;
+  const size_t o = pg.hi(n, k);
+  *reinterpret_cast<__nv_bfloat16*>(base + o) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(base + o + pg.tile) = lo;
 }
 
 // 8 consecutive k (k0 % 8 == 0) of row n: one 16-byte core-matrix row in the hi image and one in the lo image.
-__device__ __forceinline__ void store_split8(uint8_t* base, int N, int K, int n, int k0, const float* v) {
+__device__ __forceinline__ void store_split8(uint8_t* base, const PackGeom& pg, int n, int k0, const float* v) {
   uint4 hi, lo;
   split8(v, hi, lo);
-  *reinterpret_cast<uint4*>(base + packed_offset(N, K, n, k0, 0)) = hi;
-  *reinterpret_cast<uint4*>(base + packed_offset(N, K, n, k0, 1)) = lo;
+  const size_t o = pg.hi(n, k0);
+  *reinterpret_cast<uint4*>(base + o) = hi;
+  *reinterpret_cast<uint4*>(base + o + pg.tile) = lo;
 }
 
 // Forward.  grid = (heads, B, nsplit): every CTA of a (head, image) recomputes the c x c softmax (cheap) and
@@ -107,9 +127,10 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p,
   uint8_t* Mp = reinterpret_cast<uint8_t*>(p.Mpack) + (size_t)b * p.pack_bs;
   uint8_t* MTp = p.MTpack ? reinterpret_cast<uint8_t*>(p.MTpack) + (size_t)b * p.pack_bs : nullptr;
   const int c8 = c >> 3;
+  const PackGeom pgM(C, C);
   for (int t = tid; t < rows * c8; t += blockDim.x) {       // M: row n = co, 8 consecutive k = h*c + j
     const int col = t / c8, j0 = (t - col * c8) * 8;
-    store_split8(Mp, C, C, co_begin + col, h * c + j0, sM + col * c + j0);
+    store_split8(Mp, pgM, co_begin + col, h * c + j0, sM + col * c + j0);
   }
   if (MTp) {
     const int r8 = rows >> 3;                               // rows is a multiple of 8 (launcher)
@@ -118,7 +139,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p,
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = sM[(col0 + i) * c + j];
-      store_split8(MTp, C, C, h * c + j, co_begin + col0, v);
+      store_split8(MTp, pgM, h * c + j, co_begin + col0, v);
     }
   }
 }
@@ -297,7 +318,7 @@ __global__ void __launch_bounds__(256) attn_bwd_p2_kernel(const rcot_attn_params
   // Only the head-diagonal blocks are ever written: the caller keeps one zero-initialised pack
   // buffer per (C, heads) configuration, so every other entry stays zero.
   uint8_t* Wp = reinterpret_cast<uint8_t*>(p.W12pack) + (size_t)b * p.pack12_bs;
-  const int N2 = 2 * C;
+  const PackGeom pgW(2 * C, 2 * C);
   for (int i = warp; i < c; i += nwarp) {                   // B_q = dGt / (|q_i| |k_j|), in place
     const float qi = fmaxf(snq[i], 1e-12f);
     for (int j = lane; j < c; j += 32) sD[i * c + j] = sD[i * c + j] / (qi * fmaxf(snk[j], 1e-12f));
@@ -307,14 +328,14 @@ __global__ void __launch_bounds__(256) attn_bwd_p2_kernel(const rcot_attn_params
   for (int t = tid; t < c * c8; t += blockDim.x) {
     {   // dq rows: n = h*c + i, 8 consecutive k = C + h*c + j
       const int i = t / c8, j0 = (t - i * c8) * 8;
-      store_split8(Wp, N2, N2, h * c + i, C + h * c + j0, sD + i * c + j0);
+      store_split8(Wp, pgW, h * c + i, C + h * c + j0, sD + i * c + j0);
     }
     {   // dk rows: n = C + h*c + j, 8 consecutive k = h*c + i
       const int j = t % c, i0 = (t / c) * 8;
       float v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = sD[(i0 + q) * c + j];
-      store_split8(Wp, N2, N2, C + h * c + j, h * c + i0, v);
+      store_split8(Wp, pgW, C + h * c + j, h * c + i0, v);
     }
   }
   // (the diagonal entries below live in the q->dq and k->dk blocks, which nothing above writes)
@@ -322,8 +343,8 @@ __global__ void __launch_bounds__(256) attn_bwd_p2_kernel(const rcot_attn_params
     // d/dq of q/max(|q|,eps): the projection term vanishes when the clamp is active
     const float cq = snq[i] >= 1e-12f ? -srq[i] / (snq[i] * snq[i]) : 0.f;
     const float ck = snk[i] >= 1e-12f ? -srk[i] / (snk[i] * snk[i]) : 0.f;
-    store_split(Wp, N2, N2, h * c + i, h * c + i, cq);
-    store_split(Wp, N2, N2, C + h * c + i, C + h * c + i, ck);
+    store_split(Wp, pgW, h * c + i, h * c + i, cq);
+    store_split(Wp, pgW, C + h * c + i, C + h * c + i, ck);
   }
 }
 
@@ -334,6 +355,7 @@ using namespace rcot;
 static int attn_check(const rcot_attn_params& p) {
   RCOT_REQUIRE(p.B > 0 && p.B <= 65535 && p.C > 0 && p.heads > 0 && p.C % p.heads == 0, "attn: bad sizes");
   RCOT_REQUIRE(p.C / p.heads <= 96, "attn: per-head channels must be <= 96 (got %d)", p.C / p.heads);
+  RCOT_REQUIRE(p.C <= 384, "attn: at most 384 channels (packed [2C x 2C] operand of <= 3 passes), got %d", p.C);
   RCOT_REQUIRE(p.sumsq && p.temperature && p.w_out && p.A && p.Gt, "attn: null pointer");
   return RCOT_OK;
 }

@@ -30,6 +30,10 @@ struct PmGeom {
   // taps with ky = (y + pad) mod 2 (+2), kx likewise -- 4 of 16 -- so tiles hold pixels of ONE (y&1, x&1) class and
   // the K loop runs over that class's 4 taps only (nk = 4 * C1/32 chunks) instead of multiplying 75 % zeros.
   int cls, tpc, nk_full; // cls: enabled; tpc: tiles per class; nk_full: K chunks of the packed weights (nk = the loop's)
+  // N slices: when tiles_m * passes cannot fill the SMs (F_net's deep convs: a few hundred pixels, K up to 8192) a
+  // pass of BNf packed columns is split into nslice work items of BN = BNf / nslice columns each (their own MMA N,
+  // TMEM buffers and weight rows), so 2-4x more CTAs stream the long K loop.  `passes` counts items along N.
+  int BNf, nslice;
   long rows_total;
   uint32_t tmem_cols;
 };
@@ -45,7 +49,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
   const int HWr = p.Hr * p.Wr, HWs = p.Hs * p.Ws;
   const int BN = g.BN, nk = g.nk, stages = g.stages;
   const uint32_t a_tile = op_tile_bytes(128);
-  const uint32_t b_tile = op_tile_bytes(BN);
+  const uint32_t b_tile = op_tile_bytes(BN);          // this item's columns (a slice of the packed pass)
+  const uint32_t b_tile_f = op_tile_bytes(g.BNf);     // the packed pass: [chunk][term][BNf x 32]
   const uint32_t stage_bytes = TA * (a_tile + b_tile);
   const int total_tiles = g.tiles_m * g.passes;
 
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
         x.rstd = st.y;
       }
       x.wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
-               (size_t)pass * g.nk_full * (2 * b_tile);
+               (size_t)(pass / g.nslice) * g.nk_full * (2 * b_tile_f) + (size_t)(pass % g.nslice) * b_tile;
       return x;
     };
     auto load16 = [&](float* v, const TileCtx& x, int c) {
@@ -279,7 +284,13 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
           const int ky0 = ((S.x.cls >> 1) + p.pad) & 1, kx0 = ((S.x.cls & 1) + p.pad) & 1;
           wc = ((ky0 + 2 * (te >> 1)) * KS + kx0 + 2 * (te & 1)) * cpt + (S.c - te * cpt);
         }
-        bulk_g2s(st + TA * a_tile, S.x.wsrc + (size_t)wc * (2 * b_tile), TA * b_tile, &full_bar[s]);
+        const uint8_t* wsrc = S.x.wsrc + (size_t)wc * (2 * b_tile_f);
+        if (g.nslice == 1) {
+          bulk_g2s(st + TA * a_tile, wsrc, TA * b_tile, &full_bar[s]);          // hi and lo images are adjacent
+        } else {
+          bulk_g2s(st + TA * a_tile, wsrc, b_tile, &full_bar[s]);
+          if (TA > 1) bulk_g2s(st + TA * a_tile + b_tile, wsrc + b_tile_f, b_tile, &full_bar[s]);
+        }
       }
       if (LN) {
         const float* gb = ln_gb + (S.c * KC + khalf * 16) * 2;   // interleaved (gamma, beta), zero beyond Ktot
@@ -376,12 +387,12 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
-      const int nbase = pass * BN;
+      const int nbase = (pass / g.nslice) * g.BNf + (pass % g.nslice) * BN;
       float* o = p.out + (size_t)b * p.out_bs + (size_t)(p.out_coff + nbase) * HWr + pix;
       const float* mk = p.mask_y ? p.mask_y + (size_t)b * p.mask_bs + (size_t)nbase * HWr + pix : nullptr;
       const float* rs = p.residual ? p.residual + (size_t)b * p.res_bs + (size_t)nbase * HWr + pix : nullptr;
       const bool st_ok = valid;
-      const int ncols = min(BN, p.N - nbase);            // valid columns of this pass
+      const int ncols = max(0, min(BN, p.N - nbase));    // valid columns of this item
       const int ngroups = (ncols + 15) >> 4;             // 16-column groups
       uint32_t ra[16], rb[16];
       float qa[16], qb[16];                              // residual values, fetched one group ahead
@@ -486,9 +497,23 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   g.nk = cdiv(g.Ktot, KC);
   NPlan pl = make_nplan(p.N);
   g.BN = pl.BN;
+  g.BNf = pl.BN;
+  g.nslice = 1;
   g.passes = pl.passes;
+  {
+    // few M tiles and a long K loop (conv with K >= 1024): slice the N pass while that still fills idle SMs
+    const long HW0 = (long)p.Hr * p.Wr;
+    const long tm = (p.wpack_bs == 0) ? cdiv(HW0 * p.B, 128) : (long)cdiv(HW0, 128) * p.B;
+    const int ktot = (p.C1 + p.C2) * KS * KS;
+    while (KS > 1 && ktot >= 1024 && !p.stats_out && g.nslice < 4 && tm * pl.passes * g.nslice * 2 <= 148 &&
+           (g.BN / 2) % 16 == 0) {
+      g.nslice *= 2;
+      g.BN /= 2;
+    }
+    g.passes = pl.passes * g.nslice;
+  }
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(pl.BN));
+  const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(g.BN));
   const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
   g.c1_aligned = (p.C2 == 0 || p.C1 % 16 == 0) ? 1 : 0;
   int stages = (int)((196 * 1024) / stage_bytes);
@@ -500,7 +525,7 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   g.rows_total = HWr * p.B;
   g.tiles_per_img = cdiv(HWr, 128);
   g.tiles_m = g.flat ? cdiv(g.rows_total, 128) : g.tiles_per_img * p.B;
-  g.tmem_cols = tmem_cols_pow2(2 * pl.BN);
+  g.tmem_cols = tmem_cols_pow2(2 * g.BN);
   g.nk_full = g.nk;
   g.cls = 0;
   g.tpc = 0;
