@@ -16,6 +16,7 @@
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace rcot {
 
@@ -23,6 +24,12 @@ constexpr int PM_MAX_STAGES = 6;
 constexpr int PM_PROD_WARPS = 8;
 constexpr int PM_PROD_THREADS = PM_PROD_WARPS * 32;
 constexpr int PM_THREADS = (PM_PROD_WARPS + 1 + 4) * 32;  // producers, MMA warp, 4 epilogue warps
+// TMA-staged variant (1x1 convs on feature maps with H*W % 128 == 0): one more warp issues, per K chunk, 32 bulk
+// copies (cp.async.bulk, one 512-byte pixel row per channel) of the raw fp32 tile into a ring of PM_RAW shared-memory
+// slots; the producers read their 16 values from there.  The ring holds 64 KB in flight per SM -- with register
+// prefetch the producers could keep 32 KB in flight, which caps a 1 us-latency stream at ~60 % of the HBM rate.
+constexpr int PM_RAW = 4;
+constexpr uint32_t PM_RAW_BYTES = KC * 128 * sizeof(float);   // 16 KB: 32 channels x 128 pixels
 
 struct PmGeom {
   int Ktot, nk, BN, passes, stages, tiles_m, tiles_per_img, flat, c1_aligned;
@@ -38,10 +45,12 @@ struct PmGeom {
   uint32_t tmem_cols;
 };
 
-template <int KS, int MODE, int TERMS, bool LN>
-__global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_params p, const PmGeom g) {
+template <int KS, int MODE, int TERMS, bool LN, bool TMA>
+__global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
+    pm_gemm_kernel(const rcot_pm_params p, const PmGeom g) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full_bar[PM_MAX_STAGES], empty_bar[PM_MAX_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t raw_full[PM_RAW], raw_empty[PM_RAW];
   __shared__ uint32_t tmem_base_s;
   constexpr int TA = (TERMS > 1) ? 2 : 1;
 
@@ -57,11 +66,12 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
   // LayerNorm affine parameters, interleaved (gamma, beta) and zero-padded to the chunk grid
   float* ln_gb = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);
   if (LN) {
-    for (int k = tid; k < nk * KC; k += PM_THREADS) {
+    for (int k = tid; k < nk * KC; k += blockDim.x) {
       ln_gb[2 * k] = k < g.Ktot ? __ldg(p.ln_gamma + k) : 0.f;
       ln_gb[2 * k + 1] = k < g.Ktot ? __ldg(p.ln_beta + k) : 0.f;
     }
   }
+  uint8_t* raw_ring = smem + (size_t)stages * stage_bytes + (LN ? (size_t)nk * KC * 2 * sizeof(float) : 0);
   if (warp == 0) tmem_alloc(&tmem_base_s, g.tmem_cols);
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -72,6 +82,12 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);                  // one arrival per epilogue warp
     }
+    if (TMA) {
+      for (int i = 0; i < PM_RAW; ++i) {
+        mbar_init(&raw_full[i], 1);                 // the loader's expect_tx arrival (+ the copies' bytes)
+        mbar_init(&raw_empty[i], PM_PROD_WARPS);    // one arrival per producer warp
+      }
+    }
     fence_barrier_init();
   }
   tc_fence_before();
@@ -79,7 +95,107 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < PM_PROD_WARPS) {
+  if (TMA && warp == PM_PROD_WARPS + 5) {
+    // =========================================================== loader (TMA variant): raw fp32 tiles by bulk copy
+    int rs = 0;
+    uint32_t rph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
+      int b, pix0;
+      if (g.flat) {
+        const long r = (long)mt * 128;
+        b = (int)(r / HWr);
+        pix0 = (int)(r - (long)b * HWr);
+      } else {
+        b = mt / g.tiles_per_img;
+        pix0 = (mt - b * g.tiles_per_img) * 128;
+      }
+      const float* b1 = p.in + (size_t)b * p.in_bs + pix0;
+      const float* b2 = p.in2 ? p.in2 + (size_t)b * p.in2_bs + pix0 : nullptr;
+      for (int c = 0; c < nk; ++c) {
+        mbar_wait(&raw_empty[rs], rph ^ 1);
+        const int k = c * KC + lane;
+        const int nvalid = min(KC, g.Ktot - c * KC);
+        if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)nvalid * 512u);
+        __syncwarp();
+        if (lane < nvalid) {
+          const float* src = (k < p.C1) ? b1 + (size_t)k * HWs : b2 + (size_t)(k - p.C1) * HWs;
+          bulk_g2s(raw_ring + (size_t)rs * PM_RAW_BYTES + lane * 512, src, 512, &raw_full[rs]);
+        }
+        if (++rs == PM_RAW) {
+          rs = 0;
+          rph ^= 1;
+        }
+      }
+    }
+  } else if (TMA && warp < PM_PROD_WARPS) {
+    // =========================================================== producers (TMA variant)
+    // raw slot -> registers -> (LayerNorm) -> bf16 hi/lo operand stage.  No global loads except the per-tile
+    // LayerNorm statistics; the weight stage is still one bulk copy issued by thread 0.
+    const int row = tid & 127, khalf = tid >> 7;
+    int rs = 0, ps_ = 0;
+    uint32_t rph = 0, pph_ = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
+      int b, pix;
+      if (g.flat) {
+        const long r = (long)mt * 128 + row;
+        b = (int)(r / HWr);
+        pix = (int)(r - (long)b * HWr);
+      } else {
+        b = mt / g.tiles_per_img;
+        pix = (mt - b * g.tiles_per_img) * 128 + row;
+      }
+      float mu = 0.f, rstd = 0.f;
+      if (LN) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWs + pix);
+        mu = st.x;
+        rstd = st.y;
+      }
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
+                            (size_t)(pass / g.nslice) * g.nk_full * (2 * b_tile_f) + (size_t)(pass % g.nslice) * b_tile;
+      for (int c = 0; c < nk; ++c) {
+        mbar_wait(&raw_full[rs], rph);
+        const float* raw = reinterpret_cast<const float*>(raw_ring + (size_t)rs * PM_RAW_BYTES) + (khalf * 16) * 128 + row;
+        const int k0 = c * KC + khalf * 16;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (k0 + i < g.Ktot) ? raw[i * 128] : 0.f;   // never-copied rows read as 0
+        const int s = ps_;
+        const uint32_t ph = pph_;
+        if (++ps_ == stages) {
+          ps_ = 0;
+          pph_ ^= 1;
+        }
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
+          bulk_g2s(st + TA * a_tile, wsrc + (size_t)c * (2 * b_tile_f), TA * b_tile, &full_bar[s]);
+        }
+        if (LN) {
+          const float* gb = ln_gb + k0 * 2;   // interleaved (gamma, beta), zero beyond Ktot
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 w2 = *reinterpret_cast<const float2*>(gb + 2 * i);
+            v[i] = (v[i] - mu) * rstd * w2.x + w2.y;
+          }
+        }
+        op_store8<TERMS>(st, st + a_tile, row, khalf * 2, v);
+        op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, v + 8);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&full_bar[s]);
+          mbar_arrive(&raw_empty[rs]);       // every lane's raw values have been consumed (stored) by now
+        }
+        if (++rs == PM_RAW) {
+          rs = 0;
+          rph ^= 1;
+        }
+      }
+    }
+  } else if (!TMA && warp < PM_PROD_WARPS) {
     // =========================================================== producers
     // Work items are (tile, K-chunk) pairs; the 16 loads of item j+1 are issued before item j is
     // converted, so global-load latency overlaps the conversion and the barrier waits.
@@ -351,7 +467,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
       if (lane == 0) tc_commit(&acc_full[buf]);
       __syncwarp();
     }
-  } else {
+  } else if (warp < PM_PROD_WARPS + 5) {
     // =========================================================== epilogue (warp % 4 = TMEM lane quarter)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -490,7 +606,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pm_gemm_kernel(const rcot_pm_pa
 
 static int g_num_sms = 0;
 
-template <int KS, int MODE, int TERMS, bool LN>
+template <int KS, int MODE, int TERMS, bool LN, bool TMA = false>
 static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   PmGeom g;
   g.Ktot = (p.C1 + p.C2) * KS * KS;
@@ -516,7 +632,8 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(g.BN));
   const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
   g.c1_aligned = (p.C2 == 0 || p.C1 % 16 == 0) ? 1 : 0;
-  int stages = (int)((196 * 1024) / stage_bytes);
+  const size_t raw_bytes = TMA ? (size_t)PM_RAW * PM_RAW_BYTES : 0;
+  int stages = (int)((196 * 1024 - raw_bytes - ln_bytes) / stage_bytes);
   if (stages > PM_MAX_STAGES) stages = PM_MAX_STAGES;
   if (stages < 2) stages = 2;
   g.stages = stages;
@@ -536,10 +653,11 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
     g.tiles_m = 4 * g.tpc;
     g.nk = 4 * (p.C1 / 32);
   }
-  const size_t smem = stages * stage_bytes + ln_bytes;
+  const size_t smem = stages * stage_bytes + ln_bytes + raw_bytes;
+  RCOT_REQUIRE(smem <= 208 * 1024, "pm_gemm: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN>,
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN, TMA>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) {
       set_error("pm_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -555,7 +673,7 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   }
   const long total = (long)g.tiles_m * g.passes;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  pm_gemm_kernel<KS, MODE, TERMS, LN><<<grid, PM_THREADS, smem, stream>>>(p, g);
+  pm_gemm_kernel<KS, MODE, TERMS, LN, TMA><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g);
   return check_launch("pm_gemm");
 }
 
@@ -586,9 +704,25 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
 #define PM_DISPATCH(KS, MODE, LN)                                           \
   return (p.terms == 3) ? launch_pm<KS, MODE, 3, LN>(p, stream) : launch_pm<KS, MODE, 1, LN>(p, stream)
   switch (p.ks) {
-    case 1:
+    case 1: {
+      // TMA-staged A operand: whole 128-pixel tiles inside one image, 16-byte aligned channel rows, K chunks that
+      // do not straddle the two concat sources.  RCOT_PM_TMA=0 switches back to the register-prefetch producers.
+      static int tma_on = -1;
+      if (tma_on < 0) {
+        const char* e = getenv("RCOT_PM_TMA");
+        tma_on = (e && e[0] == '0') ? 0 : 1;
+      }
+      const long HW = (long)p.Hr * p.Wr;
+      const bool tma = tma_on && HW % 128 == 0 && p.in_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 &&
+                       (p.in2 == nullptr || (p.C1 % 32 == 0 && p.in2_bs % 4 == 0 &&
+                                             (reinterpret_cast<uintptr_t>(p.in2) & 15) == 0));
+      if (tma) {
+        if (ln) return (p.terms == 3) ? launch_pm<1, 0, 3, true, true>(p, stream) : launch_pm<1, 0, 1, true, true>(p, stream);
+        return (p.terms == 3) ? launch_pm<1, 0, 3, false, true>(p, stream) : launch_pm<1, 0, 1, false, true>(p, stream);
+      }
       if (ln) { PM_DISPATCH(1, 0, true); }
       PM_DISPATCH(1, 0, false);
+    }
     case 3:
       if (p.mode == 0) { PM_DISPATCH(3, 0, false); }
       PM_DISPATCH(3, 1, false);

@@ -123,3 +123,36 @@ def test_bf16_single_term(cuda_lib):
     pk = ops.pack_single(w.cuda(), "fwd")
     out = ops.pm_gemm(x.cuda(), pk.ptr(0), 192, terms=1)
     _close(out, ref, rtol=2e-2, atol=2e-2)  # stated bf16-compute tolerance
+
+
+@pytest.mark.parametrize("C1,C2,N,H,W,ln", [(96, 0, 510, 16, 24, True), (64, 32, 192, 8, 16, False), (48, 0, 254, 16, 16, True),
+                                            (255, 0, 96, 16, 8, False), (127, 0, 48, 8, 32, False), (192, 0, 192, 16, 16, True)])
+def test_pointwise_tma_staged(cuda_lib, C1, C2, N, H, W, ln):
+    """1x1 GEMMs on feature maps with H*W % 128 == 0 take the TMA-staged producer path (bulk copies of the raw fp32
+    tile into a shared-memory ring): ragged K (48, 127, 255), concat, LayerNorm prologue, residual, several tiles per
+    image and several images per launch, against fp64."""
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(C1 + C2 + N)
+    B = 3
+    x1 = torch.randn(B, C1, H, W, generator=g) + 0.3
+    x2 = torch.randn(B, C2, H, W, generator=g) if C2 else None
+    w = torch.randn(N, C1 + C2, 1, 1, generator=g) / (C1 + C2) ** 0.5
+    res = torch.randn(B, N, H, W, generator=g)
+    xin = x1.double() if x2 is None else torch.cat([x1, x2], 1).double()
+    kw = {}
+    if ln:
+        gamma, beta = torch.randn(C1, generator=g), torch.randn(C1, generator=g)
+        mu = xin.mean(1, keepdim=True)
+        rstd = 1 / torch.sqrt(((xin - mu) ** 2).mean(1, keepdim=True) + 1e-5)
+        xin = (xin - mu) * rstd * gamma.double().view(1, -1, 1, 1) + beta.double().view(1, -1, 1, 1)
+        kw["ln"] = (ops.ln_stats(x1.cuda()), gamma.cuda(), beta.cuda())
+    ref = F.conv2d(xin, w.double()) + res.double()
+    pk = ops.pack_single(w.cuda(), "fwd")
+    out = ops.pm_gemm(x1.cuda(), pk.ptr(0), N, x2=None if x2 is None else x2.cuda(), residual=res.cuda(), **kw)
+    _close(out, ref)
+    # channel-slice input view (as MDTA's v = qkv[:, 2C:]): base pointer offset inside a wider tensor
+    wide = torch.randn(B, C1 + 16, H, W, generator=g).cuda()
+    sl = wide[:, 16:]
+    ws = torch.randn(N, C1, 1, 1, generator=g) / C1 ** 0.5
+    pk2 = ops.pack_single(ws.cuda(), "fwd")
+    _close(ops.pm_gemm(sl, pk2.ptr(0), N), F.conv2d(sl.cpu().double(), ws.double()))
