@@ -16,6 +16,7 @@
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
+#include <cuda.h>      // CUtensorMap + enums only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <stdlib.h>
 
 namespace rcot {
@@ -24,10 +25,12 @@ constexpr int PM_MAX_STAGES = 6;
 constexpr int PM_PROD_WARPS = 8;
 constexpr int PM_PROD_THREADS = PM_PROD_WARPS * 32;
 constexpr int PM_THREADS = (PM_PROD_WARPS + 1 + 4) * 32;  // producers, MMA warp, 4 epilogue warps
-// TMA-staged variant (1x1 convs on feature maps with H*W % 128 == 0): one more warp issues, per K chunk, 32 bulk
-// copies (cp.async.bulk, one 512-byte pixel row per channel) of the raw fp32 tile into a ring of PM_RAW shared-memory
-// slots; the producers read their 16 values from there.  The ring holds 64 KB in flight per SM -- with register
-// prefetch the producers could keep 32 KB in flight, which caps a 1 us-latency stream at ~60 % of the HBM rate.
+// TMA-staged variant (1x1 convs on feature maps with H*W % 128 == 0): one more warp issues, per K chunk, ONE tensor
+// copy (cp.async.bulk.tensor.3d: box = 128 pixels x 32 channels x 1 image of the fp32 NCHW activation, described by
+// a CUtensorMap built per launch) into a ring of PM_RAW shared-memory slots; the producers read their 16 values
+// from there.  The ring holds 64 KB in flight per SM -- with register prefetch the producers keep 32 KB in flight,
+// which caps a 1 us-latency stream at ~60 % of the HBM rate.  (32 separate 512-byte cp.async.bulk copies per chunk
+// were measured SLOWER than the register path: the copy engine is request-bound at that size.)
 constexpr int PM_RAW = 4;
 constexpr uint32_t PM_RAW_BYTES = KC * 128 * sizeof(float);   // 16 KB: 32 channels x 128 pixels
 
@@ -47,7 +50,8 @@ struct PmGeom {
 
 template <int KS, int MODE, int TERMS, bool LN, bool TMA>
 __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
-    pm_gemm_kernel(const rcot_pm_params p, const PmGeom g) {
+    pm_gemm_kernel(const rcot_pm_params p, const PmGeom g, const __grid_constant__ CUtensorMap tm1,
+                   const __grid_constant__ CUtensorMap tm2) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full_bar[PM_MAX_STAGES], empty_bar[PM_MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint64_t raw_full[PM_RAW], raw_empty[PM_RAW];
@@ -110,18 +114,23 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         b = mt / g.tiles_per_img;
         pix0 = (mt - b * g.tiles_per_img) * 128;
       }
-      const float* b1 = p.in + (size_t)b * p.in_bs + pix0;
-      const float* b2 = p.in2 ? p.in2 + (size_t)b * p.in2_bs + pix0 : nullptr;
       for (int c = 0; c < nk; ++c) {
         mbar_wait(&raw_empty[rs], rph ^ 1);
-        const int k = c * KC + lane;
-        const int nvalid = min(KC, g.Ktot - c * KC);
-        if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)nvalid * 512u);
-        __syncwarp();
-        if (lane < nvalid) {
-          const float* src = (k < p.C1) ? b1 + (size_t)k * HWs : b2 + (size_t)(k - p.C1) * HWs;
-          bulk_g2s(raw_ring + (size_t)rs * PM_RAW_BYTES + lane * 512, src, 512, &raw_full[rs]);
+        if (lane == 0) {
+          // channels beyond the tensor (ragged last chunk) are filled with zeros by the copy engine and still
+          // count towards the transaction bytes
+          mbar_arrive_expect_tx(&raw_full[rs], PM_RAW_BYTES);
+          const int k = c * KC;
+          const bool second = k >= p.C1;
+          const CUtensorMap* tm = second ? &tm2 : &tm1;
+          const int kc = second ? k - p.C1 : k;
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+              ::"r"(smem_u32(raw_ring + (size_t)rs * PM_RAW_BYTES)),
+              "l"(reinterpret_cast<uint64_t>(tm)), "r"(pix0), "r"(kc), "r"(b), "r"(smem_u32(&raw_full[rs]))
+              : "memory");
         }
+        __syncwarp();
         if (++rs == PM_RAW) {
           rs = 0;
           rph ^= 1;
@@ -606,6 +615,37 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
 
 static int g_num_sms = 0;
 
+// CUtensorMap of an fp32 activation [B, C, HW] (per-image block contiguous, batch stride bs elements) with a
+// 128-pixel x 32-channel x 1-image box, no swizzle: the box lands in shared memory as [channel][pixel].
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_act_map(CUtensorMap* tm, const float* base, int64_t bs, int C, long HW, int B) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("pm_gemm: cuTensorMapEncodeTiled is not available from this driver");
+      return RCOT_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)bs * sizeof(float)};
+  const cuuint32_t box[3] = {128, (cuuint32_t)KC, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("pm_gemm: cuTensorMapEncodeTiled failed (%d) for C=%d HW=%ld B=%d bs=%lld", (int)r, C, HW, B, (long long)bs);
+    return RCOT_ERR_CUDA;
+  }
+  return RCOT_OK;
+}
+
 template <int KS, int MODE, int TERMS, bool LN, bool TMA = false>
 static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   PmGeom g;
@@ -673,7 +713,15 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   }
   const long total = (long)g.tiles_m * g.passes;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  pm_gemm_kernel<KS, MODE, TERMS, LN, TMA><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g);
+  CUtensorMap tm1, tm2;
+  memset(&tm1, 0, sizeof(tm1));
+  memset(&tm2, 0, sizeof(tm2));
+  if (TMA) {
+    int rc = make_act_map(&tm1, p.in, p.in_bs, p.C1, HWr, p.B);
+    if (rc == RCOT_OK && p.in2) rc = make_act_map(&tm2, p.in2, p.in2_bs, p.C2, HWr, p.B);
+    if (rc != RCOT_OK) return rc;
+  }
+  pm_gemm_kernel<KS, MODE, TERMS, LN, TMA><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g, tm1, tm2);
   return check_launch("pm_gemm");
 }
 
