@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
   const uint32_t b_tile_f = op_tile_bytes(g.BNf);     // the packed pass: [chunk][term][BNf x 32]
   const uint32_t stage_bytes = TA * (a_tile + b_tile);
   const int total_tiles = g.tiles_m * g.passes;
+  // Features of the conv instantiations only, resolved at compile time so that the 1x1 kernels (the hot path: the
+  // epilogue of the write-heavy shapes lost 20 % when these were run-time branches) carry none of their code:
+  const bool use_cls = (MODE == 1 && KS == 4) && g.cls;      // parity-class tiles (stride-2 transposed conv)
+  const int nslice = (KS > 1) ? g.nslice : 1;                // N-sliced work items
 
   // LayerNorm affine parameters, interleaved (gamma, beta) and zero-padded to the chunk grid
   float* ln_gb = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         rstd = st.y;
       }
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
-                            (size_t)(pass / g.nslice) * g.nk_full * (2 * b_tile_f) + (size_t)(pass % g.nslice) * b_tile;
+                            (size_t)pass * g.nk_full * (2 * b_tile_f);
       for (int c = 0; c < nk; ++c) {
         mbar_wait(&raw_full[rs], rph);
         const float* raw = reinterpret_cast<const float*>(raw_ring + (size_t)rs * PM_RAW_BYTES) + (khalf * 16) * 128 + row;
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
       int b, pix;
       x.cls = 0;
-      if (g.cls) {
+      if (use_cls) {
         const int cl = mt / g.tpc;
         const long r = (long)(mt - cl * g.tpc) * 128 + row;
         const int q = HWr >> 2, hw2 = p.Wr >> 1;          // pixels per class and image, class-grid width
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         x.rstd = st.y;
       }
       x.wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
-               (size_t)(pass / g.nslice) * g.nk_full * (2 * b_tile_f) + (size_t)(pass % g.nslice) * b_tile;
+               (size_t)(pass / nslice) * g.nk_full * (2 * b_tile_f) + (size_t)(pass % nslice) * b_tile;
       return x;
     };
     auto load16 = [&](float* v, const TileCtx& x, int c) {
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         const int k0 = c * KC + khalf * 16;
         int tap = k0 / p.C1;
         const int ch0 = k0 - tap * p.C1;
-        if (MODE == 1 && g.cls) {
+        if (use_cls) {
           // c runs over this class's 4 taps: (ky, kx) = (ky0 + 2*(tap>>1), kx0 + 2*(tap&1))
           const int ky0 = ((x.cls >> 1) + p.pad) & 1, kx0 = ((x.cls & 1) + p.pad) & 1;
           tap = (ky0 + 2 * (tap >> 1)) * KS + kx0 + 2 * (tap & 1);
@@ -404,13 +408,13 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
         int wc = S.c;               // chunk of the packed weights (tap-major: chunk = tap * C1/32 + channel chunk)
-        if (MODE == 1 && g.cls) {
+        if (use_cls) {
           const int cpt = p.C1 >> 5, te = S.c / cpt;
           const int ky0 = ((S.x.cls >> 1) + p.pad) & 1, kx0 = ((S.x.cls & 1) + p.pad) & 1;
           wc = ((ky0 + 2 * (te >> 1)) * KS + kx0 + 2 * (te & 1)) * cpt + (S.c - te * cpt);
         }
         const uint8_t* wsrc = S.x.wsrc + (size_t)wc * (2 * b_tile_f);
-        if (g.nslice == 1) {
+        if (nslice == 1) {
           bulk_g2s(st + TA * a_tile, wsrc, TA * b_tile, &full_bar[s]);          // hi and lo images are adjacent
         } else {
           bulk_g2s(st + TA * a_tile, wsrc, b_tile, &full_bar[s]);
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     // fast epilogues (operand of the fused op prefetched one 16-channel group ahead of the stores): plain, residual
     // add, and the LeakyReLU-derivative mask of F_net's data gradients; everything else takes the generic path
-    const bool epi_mask = p.mask_y && !p.bias && !p.act && !p.accumulate && !p.residual;
+    const bool epi_mask = (KS > 1) && p.mask_y && !p.bias && !p.act && !p.accumulate && !p.residual;
     const bool epi_other = (p.bias || p.act || p.mask_y || p.accumulate) && !epi_mask;
     const bool epi_plain = !epi_other && !epi_mask && !p.residual, epi_res = !epi_other && !epi_mask && p.residual;
     uint32_t tcount = 0;
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
       int b, pix;
       bool valid;
-      if (g.cls) {
+      if (use_cls) {
         const int cl = mt / g.tpc;
         const long r = (long)(mt - cl * g.tpc) * 128 + row;
         const int q = HWr >> 2, hw2 = p.Wr >> 1;
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
-      const int nbase = (pass / g.nslice) * g.BNf + (pass % g.nslice) * BN;
+      const int nbase = (pass / nslice) * g.BNf + (pass % nslice) * BN;
       float* o = p.out + (size_t)b * p.out_bs + (size_t)(p.out_coff + nbase) * HWr + pix;
       const float* mk = p.mask_y ? p.mask_y + (size_t)b * p.mask_bs + (size_t)nbase * HWr + pix : nullptr;
       const float* rs = p.residual ? p.residual + (size_t)b * p.res_bs + (size_t)nbase * HWr + pix : nullptr;
