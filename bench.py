@@ -267,9 +267,10 @@ def run_b200(args):
         achieved = tv["bytes"] / 1e9 / (tv["ms"] / 1e3)
         # DRAM bytes per launch of that kernel from the committed ncu capture of the same workload (if present)
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
+        import glob
+        tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))   # newest capture last (r1, r1b, r2 ...)
+        if tps:
+            tj = json.load(open(tps[-1]))
             if tj.get("kernel") == top and tj.get("per_gpu_batch") == B and tj.get("patch") == P:
                 traffic = tj["dram_bytes_per_launch"]
         roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
