@@ -417,9 +417,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         }
       }
       const size_t ao = (size_t)nb * p.a_bs + nq0, bo = (size_t)nb * p.b_bs + nq0;
-      // the next chunk's statistics are requested first, a whole chunk before their use (their consumer was the
-      // top stall: 44 % of the samples when the request sat in the middle of the iteration)
-      const float2 st_next = __ldg(stats + (size_t)nb * HW + nq0 + lane);
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* stg = smem + (size_t)s * stage_bytes;
 #pragma unroll
@@ -428,6 +425,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         ld8(ra[m], a_ptr[m] + ao);
       }
       const float2 stc = st;                      // statistics of pixel q0 + lane of THIS chunk
+      st = __ldg(stats + (size_t)nb * HW + nq0 + lane);   // (requesting these earlier in the iteration measured slower)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {               // this thread's 8 pixels are held by lanes k8*8+i (all lanes shuffle)
         const float mu = __shfl_sync(0xffffffffu, stc.x, k8 * 8 + i);
@@ -441,7 +439,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         if (b_ok[j]) op_store8<TERMS>(b_hi, b_hi + b_tile, r0 + 128 * j, k8, rb[j]);
         ld8(rb[j], b_ptr[j] + bo);
       }
-      st = st_next;
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
