@@ -227,7 +227,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(256)
     dw_bwd2_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
                    const float* __restrict__ w, float* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
-                   const DwGeom g, const int ppt) {
+                   const DwGeom g, const int ppt, const int ipc, const int B) {
   DwThread t = dw_map(g, ROWS);
   const int HW = g.H * g.W;
   float acc[9];
@@ -236,8 +236,12 @@ __global__ void __launch_bounds__(256)
   float wf[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) wf[i] = __ldg(w + t.ch * 9 + 8 - i);   // flipped taps
-  // large planes: a thread walks `ppt` patches (stride = patches covered by the grid) before the tap sums
-  // are reduced, so the 9 warp reductions are amortised
+  // The 9 tap sums are reduced once per thread, after it has walked `ppt` patches of a large plane (stride = patches
+  // covered by the grid) or, on small planes (ppt == 1), the same patch of `ipc` consecutive images: the warp
+  // reductions and atomics cost as much as one patch of work and are amortised that way.
+  for (int bi = 0; bi < ipc; ++bi) {
+  const int b = blockIdx.z * ipc + bi;
+  if (b >= B) break;
   for (int it = 0; it < ppt; ++it) {
     if (it > 0) {
       const int patch = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -250,10 +254,10 @@ __global__ void __launch_bounds__(256)
     float d[ROWS][4];
     {
       Patch<ROWS> P;
-      load_patch<ROWS>(P, dout + (size_t)t.b * dout_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+      load_patch<ROWS>(P, dout + (size_t)b * dout_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
       float o[ROWS][4];
       conv_patch<ROWS>(P, wf, o);
-      float* dp = din + (size_t)t.b * din_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
+      float* dp = din + (size_t)b * din_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) {
         *reinterpret_cast<float4*>(dp + r * g.W) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(256)
       }
     }
     Patch<ROWS> Q;
-    load_patch<ROWS>(Q, in + (size_t)t.b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+    load_patch<ROWS>(Q, in + (size_t)b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(256)
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[ky * 3 + kx] = fmaf(d[r][j], Q.v[r + ky][j + kx], acc[ky * 3 + kx]);
+  }
   }
   // reduce the 9 tap sums over the threads that share a channel, one atomicAdd per group
   if (g.pshift < 0) {   // whole CTA = one channel
@@ -595,10 +600,13 @@ int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t d
     if (ppt < 1) ppt = 1;
     grid.x = cdiv(g.ppp, 256 * ppt);
   }
+  int ipc = 1;          // small planes: up to 4 images per thread while >= 8 CTAs per SM remain
+  while (ppt == 1 && ipc < 4 && (long)grid.x * grid.y * cdiv(B, ipc * 2) >= 8 * 148) ipc *= 2;
+  grid.z = cdiv(B, ipc);
   if (rows == 4)
-    dw_bwd2_kernel<4><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt);
+    dw_bwd2_kernel<4><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
   else
-    dw_bwd2_kernel<2><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt);
+    dw_bwd2_kernel<2><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
   return 1;
 }
 

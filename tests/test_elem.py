@@ -150,11 +150,12 @@ def test_pixel_shuffle_axpby(cuda_lib):
                                al.view(2, 1, 1, 1) * x + (1 - al.view(2, 1, 1, 1)) * y)
 
 
-def test_dwconv_bwd_fused(cuda_lib):
-    """din and dW of the depthwise conv from one kernel vs autograd."""
+@pytest.mark.parametrize("B,Cn,H,W", [(3, 37, 10, 16), (16, 600, 32, 32), (5, 9, 64, 64)])
+def test_dwconv_bwd_fused(cuda_lib, B, Cn, H, W):
+    """din and dW of the depthwise conv from one kernel vs autograd (small planes with several images per thread,
+    large planes with several patches per thread)."""
     from rcot_b200 import ops
     g = torch.Generator().manual_seed(16)
-    B, Cn, H, W = 3, 37, 10, 16
     x = torch.randn(B, Cn, H, W, generator=g)
     w = torch.randn(Cn, 1, 3, 3, generator=g) / 3
     dout = torch.randn(B, Cn, H, W, generator=g)

@@ -115,3 +115,19 @@ def test_fnet_dropin_autograd(gold, setup):
     _rel("dx", xd.grad, x.grad, 2e-3)
     for k, p in F.named_parameters():
         _rel(k, p.grad, Fl[k].grad, 2e-3)
+
+
+@pytest.mark.parametrize("H,W", [(40, 72), (128, 128), (24, 32)])
+def test_tnet_whole_image_inference_matches_oracle(setup, H, W):
+    """evaluate() / the testers run T_net on whole images of arbitrary size (multiples of 8; reference
+    trainer.py:179-227, tester.py:62-114): feature maps such as 10x18 and 5x9 take the generic depthwise /
+    register-prefetch GEMM paths, 128x128 the TMA-staged one.  Same weights, CPU oracle as the checker."""
+    from oracle import restormer_ref as R
+    T, _, T_sd, *_ = setup
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = torch.rand(1, 3, H, W, generator=g)
+    with torch.no_grad():
+        out = T(x.cuda())
+        ref = R.tnet_forward(T_sd, x)
+    assert out.shape == ref.shape == (1, 3, H, W)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-4)
