@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
     const int row = tid & 127, khalf = tid >> 7;
     int rs = 0, ps_ = 0;
     uint32_t rph = 0, pph_ = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    // (image, pixel) of this thread's row in tile t
+    auto locate = [&](int t, int& b, int& pix) {
       const int pass = t / g.tiles_m, mt = t - pass * g.tiles_m;
-      int b, pix;
       if (g.flat) {
         const long r = (long)mt * 128 + row;
         b = (int)(r / HWr);
@@ -159,11 +159,26 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         b = mt / g.tiles_per_img;
         pix = (mt - b * g.tiles_per_img) * 128 + row;
       }
+    };
+    // LayerNorm statistics are requested one tile ahead (unconditionally, clamped to the last tile): at K = 48..96 a
+    // tile is two or three chunks, and the exposed load was 43 % of the stall samples
+    float2 st_next = make_float2(0.f, 0.f);
+    if (LN && blockIdx.x < total_tiles) {
+      int b0, p0;
+      locate(blockIdx.x, b0, p0);
+      st_next = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b0 * HWs + p0);
+    }
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int pass = t / g.tiles_m;
+      int b, pix;
+      locate(t, b, pix);
       float mu = 0.f, rstd = 0.f;
       if (LN) {
-        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWs + pix);
-        mu = st.x;
-        rstd = st.y;
+        mu = st_next.x;
+        rstd = st_next.y;
+        int bn, pn;
+        locate(min(t + (int)gridDim.x, total_tiles - 1), bn, pn);
+        st_next = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)bn * HWs + pn);
       }
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
                             (size_t)pass * g.nk_full * (2 * b_tile_f);
@@ -513,6 +528,29 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         pix = (mt - b * g.tiles_per_img) * 128 + row;
         valid = pix < HWr;
       }
+      if (TMA && epi_res) {
+        // pull the residual rows of this CTA's NEXT tile into L2 while this tile is drained (TMA variant: whole
+        // 128-pixel tiles inside one image): the residual loads below run only 16 channels ahead of the stores
+        const int tn = t + gridDim.x;
+        if (tn < total_tiles) {
+          const int passn = tn / g.tiles_m, mtn = tn - passn * g.tiles_m;
+          int bn, pixn;
+          if (g.flat) {
+            const long r = (long)mtn * 128;
+            bn = (int)(r / HWr);
+            pixn = (int)(r - (long)bn * HWr);
+          } else {
+            bn = mtn / g.tiles_per_img;
+            pixn = (mtn - bn * g.tiles_per_img) * 128;
+          }
+          const int nb0 = passn * BN;
+          const int nc = max(0, min(BN, p.N - nb0));
+          const float* rn = p.residual + (size_t)bn * p.res_bs + (size_t)nb0 * HWr + pixn;
+          const int et = (warp & 3) * 32 + lane;                       // 0..127 over the four epilogue warps
+          for (int L = et; L < 4 * nc; L += 128)                       // 128-byte lines: channel L/4, quarter L%4
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + (size_t)(L >> 2) * HWr + (L & 3) * 32));
+        }
+      }
       const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
@@ -624,17 +662,26 @@ static int g_num_sms = 0;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_act_map(CUtensorMap* tm, const float* base, int64_t bs, int C, long HW, int B) {
+// The encoder comes from the driver through the runtime (no link dependency on libcuda); if a driver does not
+// export it the 1x1 GEMMs simply stay on the register-prefetch producers (still sm_100a kernels, no other fallback).
+static EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn encode = nullptr;
-  if (!encode) {
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-      set_error("pm_gemm: cuTensorMapEncodeTiled is not available from this driver");
-      return RCOT_ERR_CUDA;
-    }
-    encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) encode = reinterpret_cast<EncodeTiledFn>(fn);
+    (void)cudaGetLastError();
+  }
+  return encode;
+}
+static int make_act_map(CUtensorMap* tm, const float* base, int64_t bs, int C, long HW, int B) {
+  EncodeTiledFn encode = tensor_map_encoder();
+  if (!encode) {
+    set_error("pm_gemm: cuTensorMapEncodeTiled is not available from this driver");
+    return RCOT_ERR_CUDA;
   }
   const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)bs * sizeof(float)};
@@ -765,7 +812,7 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
         tma_on = (e && e[0] == '0') ? 0 : 1;
       }
       const long HW = (long)p.Hr * p.Wr;
-      const bool tma = tma_on && HW % 128 == 0 && p.in_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 &&
+      const bool tma = tma_on && tensor_map_encoder() != nullptr && HW % 128 == 0 && p.in_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 &&
                        (p.in2 == nullptr || (p.C1 % 32 == 0 && p.in2_bs % 4 == 0 &&
                                              (reinterpret_cast<uintptr_t>(p.in2) & 15) == 0));
       if (tma) {
