@@ -140,6 +140,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         } else if (!GENERAL) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) R.b[j][i] = (q + i < HWa) ? __ldg(sp + q + i) : 0.f;
+        } else if (p.stride == 1 && (p.Wa & 7) == 0 && q + 8 <= HWa) {
+          // stride-1 conv on a map whose width is a multiple of 8: this thread's 8 pixels share one image row, so
+          // the row test is done once and only the two ends of the 8-float segment can fall outside
+          const int qy = q / p.Wa, qx = q - qy * p.Wa;
+          const int sy = qy + b_ky[j] - p.pad, sx0 = qx + b_kx[j] - p.pad;
+          const bool row_in = (unsigned)sy < (unsigned)p.Hb;
+          const float* r = sp + (row_in ? sy : 0) * p.Wb + sx0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            R.b[j][i] = (row_in && (unsigned)(sx0 + i) < (unsigned)p.Wb) ? __ldg(r + i) : 0.f;
         } else {
           int qy = q / p.Wa, qx = q - qy * p.Wa;
 #pragma unroll

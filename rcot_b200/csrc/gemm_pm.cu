@@ -174,11 +174,17 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       locate(t, b, pix);
       float mu = 0.f, rstd = 0.f;
       if (LN) {
-        mu = st_next.x;
-        rstd = st_next.y;
-        int bn, pn;
-        locate(min(t + (int)gridDim.x, total_tiles - 1), bn, pn);
-        st_next = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)bn * HWs + pn);
+        if (p.debug & 1) {          // A/B knob: statistics loaded at the tile's start
+          const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWs + pix);
+          mu = st.x;
+          rstd = st.y;
+        } else {
+          mu = st_next.x;
+          rstd = st_next.y;
+          int bn, pn;
+          locate(min(t + (int)gridDim.x, total_tiles - 1), bn, pn);
+          st_next = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)bn * HWs + pn);
+        }
       }
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (g.flat ? 0 : (size_t)b * p.wpack_bs) +
                             (size_t)pass * g.nk_full * (2 * b_tile_f);
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         pix = (mt - b * g.tiles_per_img) * 128 + row;
         valid = pix < HWr;
       }
-      if (TMA && epi_res) {
+      if (TMA && epi_res && !(p.debug & 2)) {
         // pull the residual rows of this CTA's NEXT tile into L2 while this tile is drained (TMA variant: whole
         // 128-pixel tiles inside one image): the residual loads below run only 16 channels ahead of the stores
         const int tn = t + gridDim.x;

@@ -6,6 +6,7 @@ with torch's caching allocator (the library never allocates).  No op has a PyTor
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -106,6 +107,9 @@ def _img_view(t, name="tensor"):
 
 
 # ------------------------------------------------------------------ weight packing
+_PM_DEBUG = int(os.environ.get("RCOT_PM_DEBUG", "0"))   # A/B knobs of the pm_gemm TMA variant (see gemm_pm.cu)
+
+
 def packed_bytes(N: int, K: int) -> int:
     return int(L().rcot_packed_bytes(N, K))
 
@@ -217,6 +221,7 @@ def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None
     p.act, p.slope, p.accumulate = int(act), slope, int(accumulate)
     p.debug = debug
     p.tap_major = int(tap_major)
+    p.debug = debug or _PM_DEBUG
     st = None
     if stats_out and N <= 256 and out_coff == 0:
         # LayerNorm statistics of the output rows come out of the epilogue; the consumer finds them on the tensor
