@@ -9,6 +9,7 @@
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace rcot {
 
@@ -410,7 +411,16 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
     }
     attr_set = true;
   }
-  const int nsub = 1;   // sub-chunks per CTA: longer CTAs (2, 4) measured slower at C = 192 / 384, so one chunk each
+  // sub-chunks of 32 rows per CTA: 1 gives the most CTAs (needed when heads*B is small), more sub-chunks mean fewer
+  // dA atomics; RCOT_ATTN_NSUB overrides the choice (A/B knob)
+  static int nsub_env = -1;
+  if (nsub_env < 0) {
+    const char* e = getenv("RCOT_ATTN_NSUB");
+    nsub_env = e ? atoi(e) : 0;
+  }
+  int nsub = 1;
+  if (nsub_env > 0) nsub = nsub_env;
+  if (nsub > cdiv(p.C, AB_CH)) nsub = cdiv(p.C, AB_CH);
   dim3 grid1(p.heads, p.B, cdiv(p.C, AB_CH * nsub));
   attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p, nsub);
   rc = check_launch("attn_bwd(p1)");
