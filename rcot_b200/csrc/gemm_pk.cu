@@ -10,6 +10,7 @@
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
+#include "tmap.cuh"
 #include <stdlib.h>
 
 namespace rcot {
@@ -579,6 +580,248 @@ static int try_pk_mm(const rcot_pk_params& p, cudaStream_t stream) {
   return launch_pk_mm<TERMS, 2, 2>(p, BN, stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant of the plain 1x1 kernel (per-image Grams q k^T / dy v^T, dW of GDFN's project_out): both
+// operands are K-major in NCHW as they lie, so a 32-pixel chunk of the A tile (128 channels) and of the B tile
+// (BN <= 128 channels) is ONE 3-D tensor copy each (box 32 px x rows x 1 image) into a ring of raw fp32 slots issued
+// by a loader warp; the 16 producer warps convert from shared memory.  With register prefetch one chunk ahead the
+// producers keep ~40 KB in flight per SM (3.1-3.4 TB/s measured); the ring holds PK_RAW chunks.
+constexpr int PK_RAW_MAX = 4;
+
+template <int TERMS>
+__global__ void __launch_bounds__(PK_THREADS + 32, 1)
+    pk_tma_kernel(const rcot_pk_params p, const int BN, const int nt, const int cpi, const int per_cta,
+                  const int total_chunks, const int stages, const int nraw, const uint32_t tmem_cols, const int tr,
+                  const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full_bar[PK_MAX_STAGES], empty_bar[PK_MAX_STAGES], done_bar;
+  __shared__ uint64_t raw_full[PK_RAW_MAX], raw_empty[PK_RAW_MAX];
+  __shared__ uint32_t tmem_base_s;
+  constexpr int TA = (TERMS > 1) ? 2 : 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt_i = blockIdx.x / nt, nt_i = blockIdx.x - mt_i * nt;
+  const int m0 = mt_i * 128, n0 = nt_i * BN;
+  const int g = blockIdx.z % p.groups;
+  const int bz = blockIdx.z / p.groups;  // image index when per_image, else 0
+  const int HW = p.Ha * p.Wa;
+  const int Ntot = p.CB1;
+  const uint32_t a_tile = op_tile_bytes(128), b_tile = op_tile_bytes(BN);
+  const uint32_t stage_bytes = TA * (a_tile + b_tile);
+  const uint32_t rawA_bytes = 128u * KC * sizeof(float);           // 16 KB: 128 channels x 32 pixels
+  const uint32_t raw_bytes = rawA_bytes + (uint32_t)BN * KC * sizeof(float);
+  uint8_t* raw_ring = smem + (size_t)stages * stage_bytes;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], PK_PROD_WARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < nraw; ++i) {
+      mbar_init(&raw_full[i], 1);               // the loader's expect_tx arrival (+ the two copies' bytes)
+      mbar_init(&raw_empty[i], PK_PROD_WARPS);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  const int c_begin = blockIdx.y * per_cta;
+  int c_end = c_begin + per_cta;
+  if (c_end > total_chunks) c_end = total_chunks;
+  const int nchunks = c_end - c_begin;
+
+  if (warp == PK_PROD_WARPS + 1) {
+    // ---- loader: one tensor copy per operand and chunk
+    int nb = p.per_image ? bz : c_begin / cpi;
+    int nq0 = (p.per_image ? c_begin : c_begin - nb * cpi) * KC;
+    int rs = 0;
+    uint32_t rph = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&raw_empty[rs], rph ^ 1);
+      if (lane == 0) {
+        uint8_t* slot = raw_ring + (size_t)rs * raw_bytes;
+        mbar_arrive_expect_tx(&raw_full[rs], raw_bytes);       // rows outside the tensors are zero-filled and counted
+        tensor_g2s_3d(slot, &tmA, nq0, g * p.CA + m0, nb, &raw_full[rs]);
+        tensor_g2s_3d(slot + rawA_bytes, &tmB, nq0, g * p.CB1 + n0, nb, &raw_full[rs]);
+      }
+      __syncwarp();
+      if (++rs == nraw) {
+        rs = 0;
+        rph ^= 1;
+      }
+      nq0 += KC;
+      if (!p.per_image && nq0 >= HW) {
+        nq0 = 0;
+        ++nb;
+      }
+    }
+  } else if (warp < PK_PROD_WARPS) {
+    // ---- producers: raw slot -> bf16 hi/lo operand stage.  Thread = (row r0, 8-pixel group k8).
+    const int k8 = tid & 3, r0 = tid >> 2;
+    const bool a_ok = (m0 + r0) < p.CA;
+    const bool b_ok = (r0 < BN) && (n0 + r0) < Ntot;
+    int rs = 0, s = 0;
+    uint32_t rph = 0, ph = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&raw_full[rs], rph);
+      const uint8_t* slot = raw_ring + (size_t)rs * raw_bytes;
+      float va[8], vb[8];
+      {
+        const float4* ra = reinterpret_cast<const float4*>(slot + (size_t)r0 * (KC * 4) + k8 * 32);
+        const float4 x0 = ra[0], x1 = ra[1];
+        va[0] = x0.x; va[1] = x0.y; va[2] = x0.z; va[3] = x0.w;
+        va[4] = x1.x; va[5] = x1.y; va[6] = x1.z; va[7] = x1.w;
+        const float4* rb = reinterpret_cast<const float4*>(slot + rawA_bytes + (size_t)(b_ok ? r0 : 0) * (KC * 4) + k8 * 32);
+        const float4 y0 = rb[0], y1 = rb[1];
+        vb[0] = y0.x; vb[1] = y0.y; vb[2] = y0.z; vb[3] = y0.w;
+        vb[4] = y1.x; vb[5] = y1.y; vb[6] = y1.z; vb[7] = y1.w;
+      }
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      if (a_ok) op_store8<TERMS>(st, st + a_tile, r0, k8, va);
+      if (b_ok) op_store8<TERMS>(st + TA * a_tile, st + TA * a_tile + b_tile, r0, k8, vb);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&full_bar[s]);
+        mbar_arrive(&raw_empty[rs]);     // every lane's raw values have been consumed (stored) by now
+      }
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+      }
+      if (++rs == nraw) {
+        rs = 0;
+        rph ^= 1;
+      }
+    }
+  } else if (warp == PK_PROD_WARPS) {
+    // ---- MMA issuer warp
+    const uint32_t idesc = make_idesc_bf16(128, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        issue_stage<TERMS>(tmem, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, it == 0);
+        tc_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+    if (lane == 0 && nchunks > 0) tc_commit(&done_bar);
+  }
+  if (warp < PK_PROD_WARPS && nchunks > 0) {
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    // ---- epilogue (same as pk_gemm_kernel): thread = row m, four warp groups split the columns
+    const uint32_t lane_base = tmem_lane_base(tmem);
+    const int m = m0 + (warp & 3) * 32 + lane;
+    const int part = warp >> 2;
+    const int ncols8 = BN / 8;
+    const int c8_begin = (ncols8 * part) / 4, c8_end = (ncols8 * (part + 1)) / 4;
+    float* ob = p.out + (size_t)g * p.out_gs + (p.per_image ? (size_t)bz * p.out_bs : 0);
+    const bool vec = !tr && ((reinterpret_cast<uintptr_t>(ob) & 15) == 0) && (p.ldo % 4 == 0);
+    for (int c8 = c8_begin; c8 < c8_end; ++c8) {
+      if (n0 + c8 * 8 >= Ntot) break;
+      float v[8];
+      tmem_ld8(lane_base + c8 * 8, v);
+      if (m < p.CA) {
+        if (tr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = n0 + c8 * 8 + i;
+            if (n < Ntot) atomicAdd(ob + (size_t)n * p.ldo + m, v[i]);
+          }
+        } else if (vec && n0 + c8 * 8 + 8 <= Ntot) {
+          float* dst = ob + (size_t)m * p.ldo + n0 + c8 * 8;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                       "f"(v[3])
+                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                       "f"(v[7])
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = n0 + c8 * 8 + i;
+            if (n < Ntot) atomicAdd(ob + (size_t)m * p.ldo + n, v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// Returns -100 when the call does not qualify (the caller then launches the register-staged kernel).
+template <int TERMS>
+static int try_pk_tma(const rcot_pk_params& p, cudaStream_t stream, int tr) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("RCOT_PK_TMA");      // RCOT_PK_TMA=0: A/B switch back to the register-staged kernel
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int HW = p.Ha * p.Wa;
+  const int Ntot = p.CB1;
+  int BN = round_up(Ntot, 16);
+  if (BN > 256) BN = 256;
+  if (!enabled || tensor_map_encoder() == nullptr || HW % KC != 0 || BN > 128 || p.b2 != nullptr) return -100;
+  const int nt = cdiv(Ntot, BN), mt = cdiv(p.CA, 128);
+  const int cpi = HW / KC;
+  const int total_chunks = p.per_image ? cpi : cpi * p.B;
+  const int zdim = p.groups * (p.per_image ? p.B : 1);
+  const long tiles = (long)mt * nt * zdim;
+  int S = (int)((2 * 148 + tiles - 1) / tiles);
+  int maxS = total_chunks / 4;
+  if (maxS < 1) maxS = 1;
+  if (S > maxS) S = maxS;
+  if (S < 1) S = 1;
+  int per_cta = cdiv(total_chunks, S);
+  S = cdiv(total_chunks, per_cta);
+  constexpr int TA = (TERMS > 1) ? 2 : 1;
+  const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(BN));
+  const size_t raw_bytes = (size_t)(128 + BN) * KC * sizeof(float);
+  int nraw = 3, stages = (int)((196 * 1024 - nraw * raw_bytes) / stage_bytes);
+  if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
+  if (stages > 3) {                              // room left: a fourth raw slot instead of a fourth operand stage
+    nraw = 4;
+    stages = (int)((196 * 1024 - nraw * raw_bytes) / stage_bytes);
+    if (stages > 3) stages = 3;
+  }
+  if (stages < 2) return -100;
+  const size_t smem = stages * stage_bytes + nraw * raw_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pk_tma_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
+    if (e != cudaSuccess) {
+      set_error("pk_gemm(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return RCOT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  RCOT_REQUIRE(zdim <= 65535 && S <= 65535, "pk_gemm(tma): grid too large");
+  CUtensorMap tmA, tmB;
+  int rc = make_act_map(&tmA, p.a, p.a_bs, p.groups * p.CA, HW, p.B, KC, 128, "pk_gemm");
+  if (rc == RCOT_OK) rc = make_act_map(&tmB, p.b, p.b_bs, p.groups * p.CB1, HW, p.B, KC, BN, "pk_gemm");
+  if (rc != RCOT_OK) return rc;
+  dim3 grid(mt * nt, S, zdim);
+  pk_tma_kernel<TERMS><<<grid, PK_THREADS + 32, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks, stages, nraw,
+                                                              tmem_cols_pow2(BN), tr, tmA, tmB);
+  return check_launch("pk_gemm(tma)");
+}
+
 template <int TERMS, bool GENERAL, bool LN, int NBT>
 static int launch_pk_n(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   const int Ntot = (p.CB1 + p.CB2) * p.ks * p.ks;
@@ -668,6 +911,10 @@ extern "C" int rcot_pk_gemm(const rcot_pk_params* pp, rcot_stream_t stream_) {
     q.CB1 = p.CA;
     p = q;
     tr = 1;
+  }
+  {
+    const int rc = p.terms == 3 ? try_pk_tma<3>(p, stream, tr) : try_pk_tma<1>(p, stream, tr);
+    if (rc != -100) return rc;
   }
   return p.terms == 3 ? launch_pk<3, false, false>(p, stream, tr) : launch_pk<1, false, false>(p, stream, tr);
 }

@@ -16,7 +16,7 @@
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
-#include <cuda.h>      // CUtensorMap + enums only: the encoder is fetched through cudaGetDriverEntryPoint
+#include "tmap.cuh"
 #include <stdlib.h>
 
 namespace rcot {
@@ -128,11 +128,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
           const bool second = k >= p.C1;
           const CUtensorMap* tm = second ? &tm2 : &tm1;
           const int kc = second ? k - p.C1 : k;
-          asm volatile(
-              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-              ::"r"(smem_u32(raw_ring + (size_t)rs * PM_RAW_BYTES)),
-              "l"(reinterpret_cast<uint64_t>(tm)), "r"(pix0), "r"(kc), "r"(b), "r"(smem_u32(&raw_full[rs]))
-              : "memory");
+          tensor_g2s_3d(raw_ring + (size_t)rs * PM_RAW_BYTES, tm, pix0, kc, b, &raw_full[rs]);
         }
         __syncwarp();
         if (++rs == PM_RAW) {
@@ -663,46 +659,6 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
 
 static int g_num_sms = 0;
 
-// CUtensorMap of an fp32 activation [B, C, HW] (per-image block contiguous, batch stride bs elements) with a
-// 128-pixel x 32-channel x 1-image box, no swizzle: the box lands in shared memory as [channel][pixel].
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// The encoder comes from the driver through the runtime (no link dependency on libcuda); if a driver does not
-// export it the 1x1 GEMMs simply stay on the register-prefetch producers (still sm_100a kernels, no other fallback).
-static EncodeTiledFn tensor_map_encoder() {
-  static EncodeTiledFn encode = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) encode = reinterpret_cast<EncodeTiledFn>(fn);
-    (void)cudaGetLastError();
-  }
-  return encode;
-}
-static int make_act_map(CUtensorMap* tm, const float* base, int64_t bs, int C, long HW, int B) {
-  EncodeTiledFn encode = tensor_map_encoder();
-  if (!encode) {
-    set_error("pm_gemm: cuTensorMapEncodeTiled is not available from this driver");
-    return RCOT_ERR_CUDA;
-  }
-  const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
-  const cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)bs * sizeof(float)};
-  const cuuint32_t box[3] = {128, (cuuint32_t)KC, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("pm_gemm: cuTensorMapEncodeTiled failed (%d) for C=%d HW=%ld B=%d bs=%lld", (int)r, C, HW, B, (long long)bs);
-    return RCOT_ERR_CUDA;
-  }
-  return RCOT_OK;
-}
-
 template <int KS, int MODE, int TERMS, bool LN, bool TMA = false>
 static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   PmGeom g;
@@ -774,8 +730,8 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   memset(&tm1, 0, sizeof(tm1));
   memset(&tm2, 0, sizeof(tm2));
   if (TMA) {
-    int rc = make_act_map(&tm1, p.in, p.in_bs, p.C1, HWr, p.B);
-    if (rc == RCOT_OK && p.in2) rc = make_act_map(&tm2, p.in2, p.in2_bs, p.C2, HWr, p.B);
+    int rc = make_act_map(&tm1, p.in, p.in_bs, p.C1, HWr, p.B, 128, KC, "pm_gemm");
+    if (rc == RCOT_OK && p.in2) rc = make_act_map(&tm2, p.in2, p.in2_bs, p.C2, HWr, p.B, 128, KC, "pm_gemm");
     if (rc != RCOT_OK) return rc;
   }
   pm_gemm_kernel<KS, MODE, TERMS, LN, TMA><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g, tm1, tm2);

@@ -61,7 +61,9 @@ def test_wgrad_ln_and_concat(cuda_lib):
     _close("dW_cat", out2, ref2)
 
 
-@pytest.mark.parametrize("C,heads,HW", [(48, 1, (16, 16)), (96, 4, (8, 8)), (384, 8, (4, 4)), (384, 4, (4, 8))])
+@pytest.mark.parametrize("C,heads,HW", [(48, 1, (16, 16)), (96, 4, (8, 8)), (384, 8, (4, 4)), (384, 4, (4, 8)),
+                                           # H*W % 32 == 0 and <= 128 B-operand rows: the TMA-staged kernel
+                                           (96, 1, (16, 24)), (192, 4, (8, 16)), (96, 2, (32, 32))])
 def test_gram_per_image(cuda_lib, C, heads, HW):
     from rcot_b200 import ops
     g = torch.Generator().manual_seed(C)
