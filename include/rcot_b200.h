@@ -87,7 +87,8 @@ typedef struct {
   int64_t res_bs;
   float* stats_out;     /* optional [B, Hr*Wr, 2]: LayerNorm (mean, rstd) over the N output channels of every pixel,
                            computed in the epilogue (needs N <= 256, i.e. one pass) for the LN that consumes `out` */
-  int32_t debug;        /* unused (bring-up knobs) */
+  int32_t debug;        /* A/B knobs of the TMA-staged 1x1 variant (0 = all on): bit 0 loads the LayerNorm statistics at
+                           the tile's start instead of one tile ahead, bit 1 disables the residual L2 prefetch */
   int32_t tap_major;    /* ks > 1: K is ordered (ky, kx, channel); needs C1 % 16 == 0 and no concat: a producer
                            thread's 16 K indices are 16 channels at ONE tap: a strided read like the 1x1 case */
 } rcot_pm_params;
