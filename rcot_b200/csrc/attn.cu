@@ -153,24 +153,16 @@ constexpr int AB_T = 6;    // largest register tile edge: ceil(96 / 16)
 // T = ceil(c/16); partial over this CTA's rows -> atomics into the zeroed scratch dA) and
 // dW_out[co,(h,i)] += sum_j P[co,(h,j)] A[i,j]  (2 x T outputs per thread, complete for these rows).
 // One CTA per (head, image) for all of it ran at < 1 IPC on 32 SMs; split by rows it fills the machine.
-__global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params p, const int nsub) {
+__global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params p, const int ipc) {
   extern __shared__ __align__(16) float sm[];
-  const int h = blockIdx.x, b = blockIdx.y, c = p.C / p.heads, C = p.C;
+  const int h = blockIdx.x, c = p.C / p.heads, C = p.C;
+  const int b0 = blockIdx.y * ipc;        // this CTA's images b0 .. b0+ipc-1 (W_out rows staged once for all of them)
+  const int co0 = blockIdx.z * AB_CH;
   const int ca = c + 1;         // padded row stride of sA: threads that differ in the row hit different banks
-  float* sA = sm;               // [c*ca] softmax probabilities A[i][j]
+  float* sA = sm;               // [c*ca] softmax probabilities A[i][j] of the current image
   float* sW = sA + c * ca;      // [AB_CH*c] rows of W_out[:, head block]
-  float* sP = sW + AB_CH * c;   // [AB_CH*c] rows of P[:, head block]
+  float* sP = sW + AB_CH * c;   // [AB_CH*c] rows of P[:, head block] of the current image
   const int tid = threadIdx.x;
-  const size_t hb = ((size_t)b * p.heads + h) * c * c;
-  const float* Pm = p.P + (size_t)b * C * C;  // [co, ci]
-  for (int i = tid / c, j = tid - (tid / c) * c; i < c;) {   // (i, j) walk without a division per element
-    sA[i * ca + j] = __ldg(p.A + hb + i * c + j);
-    j += 256;
-    while (j >= c) {
-      j -= c;
-      ++i;
-    }
-  }
   const int T = (c + 15) >> 4;            // register tile edge (<= AB_T)
   const int nt = (c + T - 1) / T;         // tiles per dimension (<= 16)
   // dA role: thread (ti, tj) owns rows ti*T.., columns tj*T.. of dA
@@ -182,25 +174,38 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
     ia[q] = min(ti * T + q, c - 1);       // clamped: duplicates are never stored
     ja[q] = min(tj * T + q, c - 1);
   }
-  float acc[AB_T][AB_T];
-#pragma unroll
-  for (int x = 0; x < AB_T; ++x)
-#pragma unroll
-    for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
   // dW_out role: thread (rg, ig) owns staged rows 2rg, 2rg+1 and head columns ig*T..
   const int rg = tid >> 4, ig = tid & 15;
   int iw[AB_T];
 #pragma unroll
   for (int q = 0; q < AB_T; ++q) iw[q] = min(ig * T + q, c - 1) * ca;
-  // a CTA walks nsub sub-chunks of AB_CH rows (wide layers: fewer, longer CTAs -> fewer dA atomics)
-  for (int sub = 0; sub < nsub; ++sub) {
-    const int co0 = (blockIdx.z * nsub + sub) * AB_CH;
-    if (co0 >= C) break;
-    __syncthreads();                          // sA filled (first pass) / previous sub-chunk consumed
+  for (int r = tid / c, i = tid - (tid / c) * c; r < AB_CH;) {   // (r, i) walk without a division per element
+    sW[r * c + i] = (co0 + r < C) ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;   // partial chunk: zeros
+    i += 256;
+    while (i >= c) {
+      i -= c;
+      ++r;
+    }
+  }
+  float aw[2][AB_T];            // dW_out partial sums, accumulated over this CTA's images: one atomic per entry
+#pragma unroll
+  for (int q = 0; q < AB_T; ++q) aw[0][q] = aw[1][q] = 0.f;
+  for (int bi = 0; bi < ipc; ++bi) {
+    const int b = b0 + bi;
+    if (b >= p.B) break;
+    const size_t hb = ((size_t)b * p.heads + h) * c * c;
+    const float* Pm = p.P + (size_t)b * C * C;  // [co, ci]
+    __syncthreads();                          // previous image's sA / sP fully consumed
+    for (int i = tid / c, j = tid - (tid / c) * c; i < c;) {
+      sA[i * ca + j] = __ldg(p.A + hb + i * c + j);
+      j += 256;
+      while (j >= c) {
+        j -= c;
+        ++i;
+      }
+    }
     for (int r = tid / c, i = tid - (tid / c) * c; r < AB_CH;) {
-      const bool in = co0 + r < C;            // a partial last chunk is zero-filled
-      sW[r * c + i] = in ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;
-      sP[r * c + i] = in ? __ldg(Pm + (size_t)(co0 + r) * C + h * c + i) : 0.f;
+      sP[r * c + i] = (co0 + r < C) ? __ldg(Pm + (size_t)(co0 + r) * C + h * c + i) : 0.f;
       i += 256;
       while (i >= c) {
         i -= c;
@@ -209,6 +214,11 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
     }
     __syncthreads();
     if (da_on) {
+      float acc[AB_T][AB_T];
+#pragma unroll
+      for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+        for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
 #pragma unroll 4
       for (int r = 0; r < AB_CH; ++r) {
         float wv[AB_T], pv[AB_T];
@@ -224,10 +234,13 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
           for (int y = 0; y < AB_T; ++y)
             if (x < T && y < T) acc[x][y] = fmaf(wv[x], pv[y], acc[x][y]);
       }
-    }
-    float aw[2][AB_T];
+      float* dA = p.dA + hb;
 #pragma unroll
-    for (int q = 0; q < AB_T; ++q) aw[0][q] = aw[1][q] = 0.f;
+      for (int x = 0; x < AB_T; ++x)
+#pragma unroll
+        for (int y = 0; y < AB_T; ++y)
+          if (x < T && y < T && ti * T + x < c && tj * T + y < c) atomicAdd(dA + (ti * T + x) * c + tj * T + y, acc[x][y]);
+    }
     const float* p0 = sP + (2 * rg) * c;
     const float* p1 = p0 + c;
 #pragma unroll 4
@@ -241,23 +254,15 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
           aw[1][q] = fmaf(x1, a, aw[1][q]);
         }
     }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int co = co0 + 2 * rg + k;
-      if (co < C) {
-#pragma unroll
-        for (int q = 0; q < AB_T; ++q)
-          if (q < T && ig * T + q < c) atomicAdd(p.dw_out + (size_t)co * C + h * c + ig * T + q, aw[k][q]);
-      }
-    }
   }
-  if (da_on) {
-    float* dA = p.dA + hb;
 #pragma unroll
-    for (int x = 0; x < AB_T; ++x)
+  for (int k = 0; k < 2; ++k) {
+    const int co = co0 + 2 * rg + k;
+    if (co < C) {
 #pragma unroll
-      for (int y = 0; y < AB_T; ++y)
-        if (x < T && y < T && ti * T + x < c && tj * T + y < c) atomicAdd(dA + (ti * T + x) * c + tj * T + y, acc[x][y]);
+      for (int q = 0; q < AB_T; ++q)
+        if (q < T && ig * T + q < c) atomicAdd(p.dw_out + (size_t)co * C + h * c + ig * T + q, aw[k][q]);
+    }
   }
 }
 
@@ -411,18 +416,18 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
     }
     attr_set = true;
   }
-  // sub-chunks of 32 rows per CTA: 1 gives the most CTAs (needed when heads*B is small), more sub-chunks mean fewer
-  // dA atomics; RCOT_ATTN_NSUB overrides the choice (A/B knob)
-  static int nsub_env = -1;
-  if (nsub_env < 0) {
-    const char* e = getenv("RCOT_ATTN_NSUB");
-    nsub_env = e ? atoi(e) : 0;
+  // images per CTA (RCOT_ATTN_IPC, default 1): with more, W_out rows are staged once and the dW_out sums leave as one
+  // atomic per entry and CTA instead of one per image -- measured neutral at C = 384 (235 us for 1, 2, 4) and slower
+  // elsewhere, so the atomics are not what bounds this kernel; one image per CTA keeps the most CTAs in flight.
+  static int ipc_env = -1;
+  if (ipc_env < 0) {
+    const char* e = getenv("RCOT_ATTN_IPC");
+    ipc_env = e ? atoi(e) : 0;
   }
-  int nsub = 1;
-  if (nsub_env > 0) nsub = nsub_env;
-  if (nsub > cdiv(p.C, AB_CH)) nsub = cdiv(p.C, AB_CH);
-  dim3 grid1(p.heads, p.B, cdiv(p.C, AB_CH * nsub));
-  attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p, nsub);
+  const int chunks = cdiv(p.C, AB_CH);
+  const int ipc = ipc_env > 0 ? ipc_env : 1;
+  dim3 grid1(p.heads, cdiv(p.B, ipc), chunks);
+  attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p, ipc);
   rc = check_launch("attn_bwd(p1)");
   if (rc) return rc;
   dim3 grid2(p.heads, p.B);
