@@ -1,0 +1,30 @@
+"""bench.py's reference arm (the CPU oracle port timed on the host cores) prints ONE JSON line carrying the keys the
+driver's contract names -- checked here on a 32x32 patch so it runs in seconds without a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--patch", "32"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] >= 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_is_silent_on_nonzero_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps",
+                        "1", "--warmup", "0", "--patch", "32"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
