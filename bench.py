@@ -37,17 +37,18 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--patch", type=int, default=128)
     ap.add_argument("--terms", type=int, default=3, help="3: bf16x3 split products (fp32-class), 1: bf16 products")
     ap.add_argument("--graph", action="store_true", help="replay each iteration as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
 
 
-def synth_host_batches(n, B, P, seed=0):
+def synth_host_batches(n, B, P, seed=0, pin=True):
     """n pinned host batches shaped like the reference DataLoader's: ([names, de_id], degraded, target).
     Half of each batch is denoise sigma=25 (de_id 1, |F|^2 branch), half derain-like (de_id 3, |F| branch)."""
     out = []
@@ -59,7 +60,7 @@ def synth_host_batches(n, B, P, seed=0):
         rain = torch.clamp(tgt + streak, 0, 1)
         de_id = torch.tensor([1 if j % 2 == 0 else 3 for j in range(B)])
         deg = torch.where((de_id == 1).view(B, 1, 1, 1), deg, rain)
-        pin = torch.cuda.is_available()
+        pin = pin and torch.cuda.is_available()
         out.append(([[f"s{i}_{j}" for j in range(B)], de_id],
                     deg.pin_memory() if pin else deg, tgt.pin_memory() if pin else tgt))
     return out
@@ -121,22 +122,31 @@ def block_algorithmic_bytes(B, P):
     return 13 * B * elems * 4 + 3 * wbytes
 
 
-# ---------------------------------------------------------------------------------- CPU arm
+# ---------------------------------------------------------------------------------- reference arms
+REF_CPU_BATCH = 2      # bounded sample of the bs=32 workload: one CPU iteration at batch 2 costs ~3 s on 16 threads
+
+
 def cpu_reference_rate(P, B, steps, warmup, budget_s=200.0):
-    """The reference algorithm on the host cores: oracle/train_ref.py (a restatement of trainer.py:247-346 +
-    Net_Restormer.py validated against the unmodified reference; the reference itself is Python and is not
-    on the GPU box).  Returns (images/s, cores, steps actually timed)."""
-    import Net_Restormer as N
-    from oracle import train_ref
+    """The reference's OWN trainer.train() (verbatim, oracle/_ref or /root/reference through oracle.ref_shim) on the
+    host cores, PyTorch CPU fp32, all threads.  Falls back to the validated port (oracle/train_ref.py) only when the
+    reference files did not travel.  Returns (images/s, cores, steps timed, kind)."""
+    from oracle import ref_shim
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    batches = synth_host_batches(max(1, min(4, warmup + steps)), B, P, seed=1, pin=False)
+    if ref_shim.available():
+        from oracle import ref_run
+        torch.manual_seed(0)
+        rate, done, _ = ref_run.time_reference(batches, P, B, steps, warmup, device="cpu", budget_s=budget_s)
+        return rate, cores, done, "reference"
+    import Net_Restormer as N
+    from oracle import train_ref
     torch.manual_seed(0)
     T = N.T_net(decoder=True)
     F = N.F_net(patch_size=P)
     T_sd = {k: v.detach().clone() for k, v in T.state_dict().items()}
     F_sd = {k: v.detach().clone() for k, v in F.state_dict().items()}
     Ts, Fs = {}, {}
-    batches = synth_host_batches(max(1, warmup + steps), B, P, seed=1)
     t_used, done, t0 = 0.0, 0, time.perf_counter()
     for i in range(warmup + steps):
         ([_, de_id], deg, tgt) = batches[i % len(batches)]
@@ -150,24 +160,64 @@ def cpu_reference_rate(P, B, steps, warmup, budget_s=200.0):
             done += 1
         if e - t0 > budget_s and done >= 1:
             break
-    return B * done / t_used, cores, done
+    return B * done / t_used, cores, done, "port"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Bs = 2
-    rate, cores, done = cpu_reference_rate(args.patch, Bs, args.steps, min(args.warmup, 1))
+    Bs = REF_CPU_BATCH
+    W = max(1, min(args.warmup, 1))
+    rate, cores, done, kind = cpu_reference_rate(args.patch, Bs, args.steps, W, budget_s=150.0)
+    cfg = make_config(args.patch, Bs, 1)
+    cfg["workload"] += (f"  [reference arm: bounded sample -- the same iteration at batch {Bs} per step instead of 32, "
+                        "verbatim trainer.train() on the host cores]")
+    what = ("the reference's own trainer.train() (verbatim, oracle/_ref)" if kind == "reference"
+            else "oracle/train_ref.py port (reference files absent)")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * Bs / rate, "higher_is_better": True,
+            "warmup": W, "ms_per_step": 1000.0 * Bs / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": make_config(args.patch, args.batch, args.gpus),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{done} iteration(s) of the same step at batch {Bs} (bounded sample), PyTorch CPU fp32, "
-                                       f"{cores} threads; oracle/train_ref.py"},
+            "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{done} timed iteration(s) after {W} warm-up of {what} at batch {Bs}, {args.patch}x"
+                                       f"{args.patch}, PyTorch CPU fp32, {cores} threads"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def run_eager_baseline(args):
+    """Child process of the b200 arm (`--impl eager`): the verbatim reference trainer.train() in PyTorch eager on
+    cuda:0 -- the honest GPU competitor (SURVEY 8d "secondary").  Prints one JSON object."""
+    from oracle import ref_run, ref_shim
+    out = {"what": "verbatim reference trainer.train() (oracle/_ref), PyTorch eager on cuda:0, cudnn.benchmark=True, "
+                   "save_image disabled", "patch": args.patch, "unit": UNIT}
+    if not ref_shim.available():
+        out["unavailable"] = "reference files absent (oracle/build_ref.sh not run)"
+        print(json.dumps(out))
+        return
+    for label, tf32 in (("tf32_default", None), ("tf32_off", False), ("tf32_on", True)):
+        B = args.batch
+        while B >= 1:
+            try:
+                batches = synth_host_batches(2, B, args.patch, seed=1, pin=False)
+                torch.manual_seed(0)
+                rate, done, secs = ref_run.time_reference(batches, args.patch, B, max(3, args.steps), 2, device="cuda",
+                                                          tf32=tf32)
+                out[label] = {"value": rate, "batch": B, "steps": done, "ms_per_step": 1000.0 * secs / done,
+                              "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
+                break
+            except torch.cuda.OutOfMemoryError:
+                out.setdefault("oom_at_batch", []).append(B)
+                B //= 2
+            finally:
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats()
+    out["note"] = ("tf32_default = torch defaults, what `python trainer.py` runs with (cudnn.allow_tf32=True for the convs, "
+                   "matmul fp32); tf32_off = both switches off (true fp32); tf32_on = both on")
+    print(json.dumps(out))
 
 
 # ---------------------------------------------------------------------------------- B200 arm
@@ -178,6 +228,17 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        # the honest GPU competitor, in a child process so that its memory is gone before our arm starts
+        import subprocess
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "eager", "--batch", str(args.batch),
+                                "--patch", str(args.patch), "--steps", "3"], capture_output=True, text=True, timeout=600)
+            js = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            eager = json.loads(js[-1]) if js else {"unavailable": (r.stderr or "no output")[-300:]}
+        except Exception as e:
+            eager = {"unavailable": f"{type(e).__name__}: {e}"}
     torch.cuda.set_device(local)
     if world > 1:
         torch.distributed.init_process_group("nccl")
@@ -239,6 +300,8 @@ def run_b200(args):
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    if not all(map(lambda v: v == v and abs(v) != float("inf"), losses)):
+        raise SystemExit(f"bench: non-finite losses in the timed region: {losses}")
     ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
@@ -307,13 +370,24 @@ def run_b200(args):
                                    "frac": ab / 1e9 / (tb / 1e3) / peak}
     if not args.no_cpu_baseline and world == 1:
         try:
-            rate, cores, done = cpu_reference_rate(P, 2, 1, 1, budget_s=60.0)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{done} iteration of the same step at batch 2 after 1 warm-up, PyTorch CPU "
-                                              f"fp32 on {cores} threads (oracle/train_ref.py)"}
+            rate, cores, done, kind = cpu_reference_rate(P, REF_CPU_BATCH, 8, 1, budget_s=25.0)
+            what = ("the reference's own trainer.train() (verbatim, oracle/_ref)" if kind == "reference"
+                    else "oracle/train_ref.py port")
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{done} timed iteration(s) after 1 warm-up of {what} at batch {REF_CPU_BATCH} "
+                                              f"(bounded sample of the bs={B} step), {P}x{P}, PyTorch CPU fp32, {cores} threads"}
         except Exception as e:  # the baseline must never take the GPU number down with it
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {type(e).__name__}: {e}"}
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
+        ev = (eager.get("tf32_default") or {}).get("value")
+        if ev:
+            line["vs_gpu_eager"] = {"ratio_value": value / ev, "ratio_e2e": e2e / ev,
+                                    "note": "this arm's images/s / the verbatim reference in PyTorch eager on the same B200 "
+                                            "(torch-default TF32 convs), same patch size" +
+                                            ("" if eager["tf32_default"]["batch"] == B else
+                                             f"; the eager run fits only batch {eager['tf32_default']['batch']}")}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -323,6 +397,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager":
+        run_eager_baseline(args)
     else:
         run_b200(args)
 
