@@ -81,6 +81,7 @@ class _ProgramFn(torch.autograd.Function):
         return out.detach()
 
     @staticmethod
+    @torch.autograd.function.once_differentiable     # hand-derived first-order backward: create_graph=True raises
     def backward(ctx, dout):
         prog, tape = ctx.prog, ctx.tape
         prog.ps.zero_grad()
@@ -177,10 +178,24 @@ class WithBias_LayerNorm(nn.Module):
         self.bias = nn.Parameter(torch.zeros(self.normalized_shape))
 
 
-class LayerNorm(nn.Module):
+class LayerNorm(_EngineModule):
+    """Per-pixel LayerNorm over channels on an NCHW tensor (reference :190-200).  Inside TransformerBlock /
+    T_net it runs as the prologue of the consuming GEMM; called on its own it is one `rcot_ln_fwd` launch."""
+
     def __init__(self, dim, LayerNorm_type):
         super().__init__()
         self.body = BiasFree_LayerNorm(dim) if LayerNorm_type == 'BiasFree' else WithBias_LayerNorm(dim)
+
+    def _build_program(self, named, device):
+        from rcot_b200 import engine
+        return engine.LeafProgram(named, device, "ln", 0, 0)
+
+    def forward(self, x):
+        if isinstance(self.body, BiasFree_LayerNorm):
+            return self.body(x)
+        self._require_cuda(x)
+        prog = self._get_program(x.device)
+        return _run_program(self, prog, lambda p, t, tape: p.run(t, tape), x)
 
 
 class TransformerBlock(_EngineModule):
@@ -316,8 +331,10 @@ class T_net(_EngineModule):
         prog = self._get_program(inp_img.device)
         holder = {}
 
+        want_dx = torch.is_grad_enabled() and inp_img.requires_grad
+
         def run(p, t, tape):
-            out, res = p.forward(t, tape, return_residual=True)
+            out, res = p.forward(t, tape, return_residual=True, input_grad=want_dx)
             holder["res"] = res
             return out
 
@@ -356,7 +373,9 @@ class F_net(_EngineModule):
 
     def _build_program(self, named, device):
         from rcot_b200.fnet import FnetProgram
-        return FnetProgram(named, device, self.patch_size)
+        # (a module unpickled from a reference checkpoint has no `patch_size` attribute: recover it from fc, P*P/2 inputs)
+        P = self.__dict__.get("patch_size") or int(round((2 * self.fc.in_features) ** 0.5))
+        return FnetProgram(named, device, P)
 
     def forward(self, input):
         self._require_cuda(input)

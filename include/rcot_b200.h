@@ -128,6 +128,10 @@ int rcot_pk_gemm(const rcot_pk_params* p, rcot_stream_t stream);
  * Net_Restormer.py:173-200 (WithBias_LayerNorm on the 'b (h w) c' view): stats[b, p] = (mean, rstd)
  * with biased variance and eps 1e-5; the normalisation itself is applied as a GEMM prologue. */
 int rcot_ln_stats(const float* x, int64_t x_bs, int B, int C, int HW, float* stats, rcot_stream_t stream);
+/* Stand-alone LayerNorm forward (Net_Restormer.py:186-189,198-200): y = (x-mu)*rstd*gamma+beta per pixel over C;
+ * also writes the (mu, rstd) pairs rcot_ln_bwd needs. */
+int rcot_ln_fwd(const float* x, int64_t x_bs, const float* gamma, const float* beta, float* y, int64_t y_bs, int B, int C,
+                int HW, float* stats, rcot_stream_t stream);
 /* dx = [dy +] LN'(dz); dgamma += sum dz*xhat; dbeta += sum dz  (dy may be NULL; dx may alias dy or dz) */
 int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64_t x_bs, const float* stats,
                 const float* gamma, const float* dy, int64_t dy_bs, float* dx, int64_t dx_bs, float* dgamma,

@@ -38,6 +38,36 @@ __global__ void __launch_bounds__(256)
   stats[(size_t)b * HW + p] = make_float2(s + m, 1.0f / sqrtf(var + 1e-5f));
 }
 
+// ------------------------------------------------------------------ LayerNorm forward (stand-alone module)
+// y = (x - mu) * rstd * gamma + beta per pixel over C (Net_Restormer.py:186-189), statistics written for the backward.
+// Inside the blocks LayerNorm is a prologue of the consuming GEMM; this kernel backs `LayerNorm.forward` on its own.
+__global__ void __launch_bounds__(256)
+    ln_fwd_kernel(const float* __restrict__ x, int64_t x_bs, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* __restrict__ y, int64_t y_bs, int C, int HW,
+                  float2* __restrict__ stats) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (p >= HW) return;
+  const float* xp = x + (size_t)b * x_bs + p;
+  const float s = __ldg(xp);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {
+    const float d = __ldg(xp + (size_t)c * HW) - s;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+  }
+  const float inv = 1.f / (float)C;
+  const float m = s1 * inv;
+  const float var = fmaxf(s2 * inv - m * m, 0.f);
+  const float mu = s + m, rstd = 1.0f / sqrtf(var + 1e-5f);
+  stats[(size_t)b * HW + p] = make_float2(mu, rstd);
+  float* yp = y + (size_t)b * y_bs + p;
+#pragma unroll 8
+  for (int c = 0; c < C; ++c)
+    yp[(size_t)c * HW] = (__ldg(xp + (size_t)c * HW) - mu) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+}
+
 // ------------------------------------------------------------------ LayerNorm backward
 // g = dz*gamma ; dx = [dy +] rstd*(g - mean_c(g) - xhat*mean_c(g*xhat)) ; dgamma += sum dz*xhat ;
 // dbeta += sum dz.  CTA = 32 pixels (lanes) x 8 channel groups (warps); warp w owns channels w, w+8, ...
@@ -535,6 +565,15 @@ extern "C" int rcot_ln_stats(const float* x, int64_t x_bs, int B, int C, int HW,
   dim3 grid(cdiv(HW, 256), B);
   ln_stats_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(x, x_bs, C, HW, reinterpret_cast<float2*>(stats));
   return check_launch("ln_stats");
+}
+
+extern "C" int rcot_ln_fwd(const float* x, int64_t x_bs, const float* gamma, const float* beta, float* y, int64_t y_bs,
+                           int B, int C, int HW, float* stats, rcot_stream_t st) {
+  RCOT_REQUIRE(x && gamma && beta && y && stats && B > 0 && C > 0 && HW > 0, "ln_fwd: bad arguments");
+  RCOT_REQUIRE(B <= 65535, "ln_fwd: batch too large");
+  dim3 grid(cdiv(HW, 256), B);
+  ln_fwd_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(x, x_bs, gamma, beta, y, y_bs, C, HW, reinterpret_cast<float2*>(stats));
+  return check_launch("ln_fwd");
 }
 
 extern "C" int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64_t x_bs, const float* stats,

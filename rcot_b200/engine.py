@@ -437,6 +437,8 @@ class LeafProgram:
             self.bs = BlockSpec(self.ps, "", C, 1, has_attn=False)
         elif kind in ("down", "up", "embed"):
             self.cs = ConvSpec(self.ps, next(iter(named)), 3, 1)
+        elif kind == "ln":
+            pass
         else:
             raise ValueError(kind)
         self.ps.finalize()
@@ -459,6 +461,13 @@ class LeafProgram:
                     _, ctx = mdta_fwd(bs, x, None, False, True)
                     tape.add_grad(x, mdta_bwd(bs, x, dy, None, False, ctx))
                 tape.record(y, bwd)
+            return y
+        if kind == "ln":
+            ps, st = self.ps, self.strip
+            y, stats = ops.ln_fwd(x, ps.p[st + "body.weight"], ps.p[st + "body.bias"])
+            if tape.enabled:
+                tape.record(y, lambda dy: tape.add_grad(x, ops.ln_bwd(dy, x, stats, ps.p[st + "body.weight"],
+                                                                      ps.g[st + "body.weight"], ps.g[st + "body.bias"])))
             return y
         if kind == "ffn":
             bs = self.bs

@@ -271,6 +271,16 @@ def ln_stats(x, out=None):
     return out
 
 
+def ln_fwd(x, gamma, beta):
+    """Stand-alone LayerNorm forward; returns (y, stats)."""
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(B, H * W, 2, device=x.device, dtype=torch.float32)
+    _lib.check(L().rcot_ln_fwd(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(y),
+                               C.c_int64(_img_view(y, "y")), B, Cc, H * W, _ptr(stats), _stream()), "ln_fwd")
+    return y, stats
+
+
 def ln_bwd(dz, x, stats, gamma, dgamma, dbeta, dy=None, dx=None):
     B, Cc, H, W = x.shape
     if dx is None:
@@ -533,6 +543,7 @@ def _pm_bytes(a, k, r):
 pm_gemm = _instrument("pm_gemm", _pm_bytes)(pm_gemm)
 pk_gemm = _instrument("pk_gemm", lambda a, k, r: _nb(a[0], a[1], k.get("b2"), a[2]))(pk_gemm)
 ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
+ln_fwd = _instrument("ln_fwd", lambda a, k, r: _nb(a[0], r[0]))(ln_fwd)
 ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)
 dwconv = _instrument("dwconv", lambda a, k, r: _nb(a[0], r, k.get("dg"), k.get("g_out")))(dwconv)
 dwconv_wgrad = _instrument("dwconv_wgrad", lambda a, k, r: _nb(a[0], a[1]))(dwconv_wgrad)

@@ -76,7 +76,7 @@ class TnetProgram:
     def _up(self, x, name, tape, out=None):
         return engine.shuffle_fwd(engine.conv_fwd(self.conv[name], x, tape), False, tape, out=out)
 
-    def _decode(self, latent, e1, e2, e3, img, tape):
+    def _decode(self, latent, e1, e2, e3, img, tape, input_grad=False):
         cv = self.conv
         t = engine.block_fwd(self.single["noise_level3"], latent, tape)
         t = engine.conv_fwd(cv["reduce_noise_level3"], t, tape)
@@ -94,25 +94,27 @@ class TnetProgram:
         t = engine.shuffle_cat_fwd(t, e1, tape)            # PixelShuffle + cat([., e1]) in one buffer
         t = self._stage(t, "decoder_level1", tape)
         t = self._stage(t, "refinement", tape)
-        return engine.conv_fwd(cv["output"], t, tape, residual=img, need_res_grad=False)
+        return engine.conv_fwd(cv["output"], t, tape, residual=img, need_res_grad=input_grad)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, img, tape: Tape | None = None, return_residual=False):
-        """img: [B,3,P,P] fp32 CUDA, P % 8 == 0.  Returns out (and res = img - first pass)."""
+    def forward(self, img, tape: Tape | None = None, return_residual=False, input_grad=False):
+        """img: [B,3,P,P] fp32 CUDA, P % 8 == 0.  Returns out (and res = img - first pass).
+        input_grad: also propagate the gradient to ``img`` (training never needs it: the degraded image is data;
+        the drop-in module sets it when its input requires grad)."""
         if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] % 8 or img.shape[3] % 8:
             raise ValueError(f"T_net input must be [B,3,H,W] with H,W multiples of 8, got {tuple(img.shape)}")
         img = img.contiguous()
         cv = self.conv
-        e1 = self._stage(engine.conv_fwd(cv["patch_embed"], img, tape, need_dx=False), "encoder_level1", tape)
+        e1 = self._stage(engine.conv_fwd(cv["patch_embed"], img, tape, need_dx=input_grad), "encoder_level1", tape)
         e2 = self._stage(self._down(e1, "down1_2", tape), "encoder_level2", tape)
         e3 = self._stage(self._down(e2, "down2_3", tape), "encoder_level3", tape)
         latent = self._stage(self._down(e3, "down3_4", tape), "latent", tape)
-        first = self._decode(latent, e1, e2, e3, img, tape)
-        res = engine.axpby_fwd(img, first, 1.0, -1.0, tape, need_dx=False)
+        first = self._decode(latent, e1, e2, e3, img, tape, input_grad)
+        res = engine.axpby_fwd(img, first, 1.0, -1.0, tape, need_dx=input_grad)
         r = self._stage(engine.conv_fwd(cv["patch_embed"], res, tape), "resencoder_level1", tape)
         r = self._stage(self._down(r, "resdown1_2", tape), "resencoder_level2", tape)
         r = self._stage(self._down(r, "resdown2_3", tape), "resencoder_level3", tape)
         r = self._stage(self._down(r, "down3_4", tape), "reslatent", tape)
         latent2 = engine.axpby_fwd(latent, r, 1.0, 0.8, tape)
-        out = self._decode(latent2, e1, e2, e3, img, tape)
+        out = self._decode(latent2, e1, e2, e3, img, tape, input_grad)
         return (out, res) if return_residual else out

@@ -32,6 +32,9 @@ class FlatOptimizer:
         self.ps, self.kind = ps, kind
         self.sq = torch.zeros_like(ps.flat)
         self.m = torch.zeros_like(ps.flat) if kind == "Adam" else None
+        # ONE step counter per network.  Known deviation (Adam only): torch.optim.Adam counts steps per parameter, and
+        # fc2.bias is skipped in every gradient-penalty step (its gradient is None there, trainer.py:307), so the
+        # reference's bias correction for that single scalar uses t/2.  RMSprop (the default) has no step count.
         self.steps = 0
 
     def step(self, lr, n=None, hyper=None, lr_mult=1.0):
@@ -161,7 +164,11 @@ class OTTrainStep:
         if ent is None:
             st = {"deg": torch.empty_like(degraded), "tgt": torch.empty_like(target),
                   "ids": torch.empty_like(de_id), "alpha": torch.empty_like(alpha),
-                  "hyper": torch.zeros(9, device=dev), "hyper_host": torch.zeros(9).pin_memory()}
+                  "hyper": torch.zeros(9, device=dev),
+                  # the host may run several replays ahead of the device (train() only syncs every 10 iterations):
+                  # each replay gets its own pinned staging slot, reused only after the copy out of it has executed
+                  "hyper_ring": [torch.zeros(9).pin_memory() for _ in range(8)],
+                  "hyper_ev": [None] * 8, "hyper_i": 0}
             st["deg"].copy_(degraded); st["tgt"].copy_(target); st["ids"].copy_(de_id); st["alpha"].copy_(alpha)
             # one eager iteration first: lazy allocations (scratch, saved-tensor caches, kernel attributes)
             snap = self._snapshot()
@@ -185,12 +192,19 @@ class OTTrainStep:
         st["tgt"].copy_(target, non_blocking=True)
         st["ids"].copy_(de_id, non_blocking=True)
         st["alpha"].copy_(alpha, non_blocking=True)
-        h = st["hyper_host"]
+        hi = st["hyper_i"]
+        st["hyper_i"] = (hi + 1) % len(st["hyper_ring"])
+        if st["hyper_ev"][hi] is not None:
+            st["hyper_ev"][hi].synchronize()
+        h = st["hyper_ring"][hi]
         fs, ts = self.F_opt.steps, self.T_opt.steps
         for slot, (opt, stepno) in enumerate(((self.F_opt, fs + 1), (self.F_opt, fs + 2), (self.T_opt, ts + 1))):
             bc1, bc2 = opt.bias_corrections(stepno)
             h[3 * slot], h[3 * slot + 1], h[3 * slot + 2] = lr, bc1, bc2
         st["hyper"].copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st["hyper_ev"][hi] = ev
         g.replay()
         self.F_opt.steps += 2
         self.T_opt.steps += 1

@@ -114,6 +114,30 @@ class EngineOptimizer:
         self.param_groups = [{"lr": lr}]
 
 
+def _optimizer_kind(optimizer):
+    """'RMSprop' / 'Adam' for an EngineOptimizer or for the torch.optim object the reference's main() builds
+    (trainer.py:121-126).  A torch.optim instance is accepted as a hyper-parameter carrier: its ``param_groups[0]['lr']``
+    is written by the schedule exactly like the reference does, while the update itself runs in the fused flat-buffer
+    kernel (the module parameters are views of that buffer, so they change in place).  Non-default hyper-parameters
+    would silently differ from what the kernel applies, so they are rejected."""
+    kind = getattr(optimizer, "kind", None)
+    if kind is not None:
+        return kind
+    name = type(optimizer).__name__
+    d = optimizer.defaults if hasattr(optimizer, "defaults") else {}
+    if name == "RMSprop":
+        ok = (d.get("alpha", 0.99) == 0.99 and d.get("eps", 1e-8) == 1e-8 and not d.get("momentum", 0)
+              and not d.get("centered", False) and not d.get("weight_decay", 0))
+    elif name == "Adam":
+        ok = (tuple(d.get("betas", (0.9, 0.999))) == (0.9, 0.999) and d.get("eps", 1e-8) == 1e-8
+              and not d.get("weight_decay", 0) and not d.get("amsgrad", False))
+    else:
+        raise TypeError(f"train(): optimizer must be RMSprop or Adam (torch.optim or EngineOptimizer), got {name}")
+    if not ok:
+        raise ValueError(f"train(): {name} with non-default hyper-parameters is not supported by the fused optimizer kernels")
+    return name
+
+
 _STEPS = {}
 
 
@@ -171,7 +195,7 @@ def train(training_data_loader, T_optimizer, F_optimizer, Tnet, Fnet, epoch):
     rank, _ = _world()
     if rank == 0:
         print("Epoch={}, lr={}".format(epoch, F_optimizer.param_groups[0]["lr"]))
-    step = _train_step(Tnet, Fnet, F_optimizer.kind)
+    step = _train_step(Tnet, Fnet, _optimizer_kind(F_optimizer))
     mse, Tloss, Dloss = [], [], []
     for iteration, batch in enumerate(training_data_loader):
         if opt.max_iters and iteration >= opt.max_iters:
@@ -242,7 +266,14 @@ def main(argv=None):
     if not opt.cuda or not torch.cuda.is_available():
         raise Exception("rcot_b200 runs on a B200 only (no CPU path); the reference's CPU mode is the oracle in oracle/")
     opt.seed = random.randint(1, 10000) if opt.seed is None else opt.seed
-    print("Random Seed: ", opt.seed)
+    if world > 1:
+        # every rank must build the same weights, shuffle the same way and draw the same alpha stream: the seed
+        # rank 0 drew (the reference draws a random one, :79) is broadcast before anything consumes an RNG
+        t = torch.tensor([opt.seed], dtype=torch.int64, device="cuda")
+        torch.distributed.broadcast(t, 0)
+        opt.seed = int(t.item())
+    if rank == 0:
+        print("Random Seed: ", opt.seed)
     torch.manual_seed(opt.seed)
     random.seed(opt.seed)
     Tnet = T_net(decoder=True).cuda()
@@ -256,6 +287,12 @@ def main(argv=None):
         w = torch.load(opt.pretrained, weights_only=False)
         Tnet.load_state_dict(w['model'].state_dict())
         Fnet.load_state_dict(w['discr'].state_dict())
+    if world > 1:
+        # belt and braces after init / --resume / --pretrained: replicas start from rank 0's weights bit for bit
+        for net in (Tnet, Fnet):
+            prog = net._get_program(torch.device("cuda", torch.cuda.current_device()))
+            torch.distributed.broadcast(prog.ps.flat, 0)
+            prog.ps.repack()
     T_optimizer = EngineOptimizer(opt.optimizer, opt.lr / 2)
     F_optimizer = EngineOptimizer(opt.optimizer, opt.lr)
     if opt.synthetic:
@@ -267,8 +304,11 @@ def main(argv=None):
             raise SystemExit("real-data training needs the reference's util/ package on PYTHONPATH "
                              "(or use --synthetic N): " + str(e))
         train_set = TrainDataset(opt)
+    # the reference keeps the last partial batch (:132-135); under data parallelism (batch must divide by the ranks)
+    # or CUDA-graph replay (one captured batch shape) it is dropped instead
     loader = torch.utils.data.DataLoader(train_set, num_workers=opt.threads, batch_size=opt.batchSize, shuffle=True,
-                                         generator=torch.Generator().manual_seed(opt.seed), pin_memory=True)
+                                         generator=torch.Generator().manual_seed(opt.seed), pin_memory=True,
+                                         drop_last=(world > 1 or opt.cuda_graph))
     deg_list, tar_list = sorted(glob.glob(opt.degset + "*")), sorted(glob.glob(opt.tarset + "*"))
     for epoch in range(opt.start_epoch, opt.nEpochs + 1):
         train(loader, T_optimizer, F_optimizer, Tnet, Fnet, epoch)
