@@ -59,7 +59,8 @@ class FlatOptimizer:
 
 
 class OTTrainStep:
-    def __init__(self, Tprog, Fprog, optimizer="RMSprop", sigma=1.0, Sigma=10000.0, group=None, save_hidden=None):
+    def __init__(self, Tprog, Fprog, optimizer="RMSprop", sigma=1.0, Sigma=10000.0, group=None, save_hidden=None,
+                 data_parallel=True):
         self.T, self.F = Tprog, Fprog
         self.sigma, self.Sigma = float(sigma), float(Sigma)
         self.T_opt = FlatOptimizer(Tprog.ps, optimizer)
@@ -69,8 +70,10 @@ class OTTrainStep:
         self.timing = None                  # set to [] to collect (section, start_event, end_event) per iteration
         self._graphs = {}                   # (B, P, paired) -> captured iteration
         self._hyper = None                  # device [3 optimizer steps x (lr, bc1, bc2)] while capturing/replaying
+        self.capture = None                 # set to {} to keep clones of the three (all-reduced) gradient buffers (tests)
         self.world = 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if data_parallel and (group is not None or
+                              (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(group)
 
     def _mark(self, name):
@@ -111,6 +114,8 @@ class OTTrainStep:
         F.ps.zero_grad()
         loss_F = F.critic_step(target, out, Bg)
         self._allreduce(F.ps.grad)
+        if self.capture is not None:
+            self.capture["F"] = F.ps.grad.clone()
         hy = self._hyper
         self.F_opt.step(lr, hyper=None if hy is None else hy[0:3])
         # ---------------- gradient penalty (on the updated potential)
@@ -119,6 +124,8 @@ class OTTrainStep:
         interp = ops.axpby(target, out, a_vec=alpha)
         loss_gp = F.penalty_step(interp, Bg)
         self._allreduce(F.ps.grad)
+        if self.capture is not None:
+            self.capture["GP"] = F.ps.grad.clone()
         self.F_opt.step(lr, n=F.n_without_fc2_bias,      # fc2.bias has no gradient here -> skipped
                         hyper=None if hy is None else hy[3:6])
         # ---------------- T-sub
@@ -138,6 +145,9 @@ class OTTrainStep:
         tape.backward(out, dout)
         self._mark("T_allreduce_and_optimizer")
         self._allreduce(T.ps.grad[:T.ps.n_used])
+        if self.capture is not None:
+            self.capture["T"] = T.ps.grad.clone()
+            self.capture["dout"] = dout.clone()
         self.T_opt.step(lr / 2, n=T.ps.n_used,           # never-used modules have grad None -> skipped
                         hyper=None if hy is None else hy[6:9], lr_mult=0.5)
         self._mark("end")

@@ -1,0 +1,70 @@
+"""Worker of tests/test_dp_nccl.py (launched with torch.distributed.run, 2 ranks, one B200 each): one OTTrainStep
+iteration with the global batch sharded over the ranks vs the same iteration on the whole batch in one process."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import Net_Restormer as N
+    from rcot_b200.fnet import FnetProgram
+    from rcot_b200.tnet import TnetProgram
+    from rcot_b200.train_step import OTTrainStep
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    torch.distributed.init_process_group("nccl")
+    P, B = 32, 4
+
+    def nets():
+        torch.manual_seed(0)
+        T = N.T_net(decoder=True)
+        F = N.F_net(patch_size=P)
+        return (TnetProgram({k: v.detach().cuda() for k, v in T.named_parameters()}, "cuda"),
+                FnetProgram({k: v.detach().cuda() for k, v in F.named_parameters()}, "cuda", P))
+
+    g = torch.Generator().manual_seed(4)
+    tgt = torch.rand(B, 3, P, P, generator=g)
+    deg = tgt + 0.1 * torch.randn(B, 3, P, P, generator=g)
+    de_id = torch.tensor([1, 4, 3, 0])
+    alpha = torch.rand(B, generator=g)
+    for paired in (True, False):
+        Tp, Fp = nets()
+        dp = OTTrainStep(Tp, Fp, "RMSprop")
+        assert dp.world == world
+        dp.capture = {}
+        sl = slice(rank * B // world, (rank + 1) * B // world)
+        r = dp.iteration(deg[sl].cuda(), tgt[sl].cuda(), de_id[sl].cuda(), alpha[sl].cuda(), paired, 1e-4)
+        Tp1, Fp1 = nets()
+        one = OTTrainStep(Tp1, Fp1, "RMSprop", data_parallel=False)
+        assert one.world == 1
+        one.capture = {}
+        r1 = one.iteration(deg.cuda(), tgt.cuda(), de_id.cuda(), alpha.cuda(), paired, 1e-4)
+        for k in ("loss_F", "loss_gp", "loss_T", "loss_mse"):
+            a, b = r[k].item(), r1[k].item()
+            assert abs(a - b) <= 1e-5 * abs(b) + 1e-7, (k, a, b)
+        for k in ("F", "GP", "T"):
+            a, b = dp.capture[k].double(), one.capture[k].double()
+            err = ((a - b).norm() / b.norm()).item()
+            assert err < 2e-5, (paired, k, err)
+            if rank == 0:
+                print(f"paired={paired} grads {k}: 2 ranks x {B // world} vs 1 x {B}: rel-L2 {err:.2e}")
+        # post-step weights: identical updates up to sign flips of ~zero gradients (RMSprop's first step is sign-like)
+        for a, b, lr in ((Tp.ps.flat, Tp1.ps.flat, 5e-5), (Fp.ps.flat, Fp1.ps.flat, 1e-4)):
+            d = (a - b).abs()
+            assert d.max().item() <= 2 * 2 * 10 * lr + 1e-7 and (d > 1e-6).float().mean().item() < 1e-3
+        # replicas stay bit-identical
+        w = Tp.ps.flat.clone()
+        torch.distributed.broadcast(w, 0)
+        assert torch.equal(w, Tp.ps.flat)
+    torch.distributed.barrier()
+    if rank == 0:
+        print("DP_NCCL_OK")
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,3 +110,32 @@ def test_shared_block_invoked_twice_on_one_tape(cuda_lib, save):
     _check("dx", tape.grad_of(leaves, xd), x64.grad)
     for k in sd:
         _check(k, ps.g[k], sd64[k].grad)
+
+
+@pytest.mark.parametrize("C,heads,H,W", [(48, 1, 128, 128), (96, 1, 128, 128), (96, 2, 64, 64)])
+def test_block_fwd_bwd_at_bench_size(cuda_lib, C, heads, H, W):
+    """The shapes that carry 85 % of the bytes of the benchmarked step (level 1: 128x128, level 2: 64x64), hidden
+    tensors kept (the mode bench.py runs at batch 32): forward, dX and every dW against the fp64 oracle."""
+    from oracle import restormer_ref as R
+    from rcot_b200 import engine
+
+    g = torch.Generator().manual_seed(7 * C + heads)
+    B = 2
+    sd = _block_params(C, heads, g)
+    x = torch.randn(B, C, H, W, generator=g)
+    dy = torch.randn(B, C, H, W, generator=g)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    y64 = R.transformer_block(x64, sd64, "b.", heads)
+    y64.backward(dy.double())
+    ps = engine.ParamSet({k: v for k, v in sd.items()}, "cuda")
+    bs = engine.BlockSpec(ps, "b.", C, heads)
+    ps.finalize()
+    tape = engine.Tape(save_hidden=True)
+    xd = x.cuda()
+    y = engine.block_fwd(bs, xd, tape)
+    _check("y", y, y64.detach())
+    leaves = tape.backward(y, dy.cuda().clone())
+    _check("dx", tape.grad_of(leaves, xd), x64.grad)
+    for k in sd:
+        _check(k, ps.g[k], sd64[k].grad)
