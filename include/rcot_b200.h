@@ -124,6 +124,22 @@ typedef struct {
 
 int rcot_pk_gemm(const rcot_pk_params* p, rcot_stream_t stream);
 
+/* ---------------------------------------------------------------- device-side training patches (data path)
+ * util/dataset_utils.py:215-278 (TrainDataset.__getitem__), util/image_utils.py:59-65,133-182,
+ * util/degradation_utils.py:21-27 for a whole batch: centre crop to multiples of 16, P x P crop at (y0, x0),
+ * augmentation `mode` (0..7), then either Gaussian noise on the uint8 grid (sigma > 0; `noise` = [B,P,P,3] float32
+ * standard normals) or the paired degraded image (sigma == 0).  Images: uint8 HWC in one pool buffer.
+ * Outputs: degraded, clean = fp32 NCHW [B,3,P,P] in [0,1]. */
+typedef struct {
+  int64_t clean_off, deg_off;   /* byte offsets of the clean / degraded image inside the pool (deg unused if sigma>0) */
+  int32_t H, W;                 /* image size before the centre crop                                                */
+  int32_t y0, x0;               /* random-crop origin inside the centre-cropped image                               */
+  int32_t mode;                 /* augmentation 0..7 (util/image_utils.py:133-163)                                   */
+  float sigma;                  /* 15 / 25 / 50 for the denoise tasks, 0 for paired tasks                            */
+} rcot_patch_desc;
+int rcot_make_patches(const uint8_t* pool, const rcot_patch_desc* desc, const float* noise, float* degraded,
+                      float* clean, int B, int P, rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- LayerNorm over channels
  * Net_Restormer.py:173-200 (WithBias_LayerNorm on the 'b (h w) c' view): stats[b, p] = (mean, rstd)
  * with biased variance and eps 1e-5; the normalisation itself is applied as a GEMM prologue. */

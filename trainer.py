@@ -59,6 +59,9 @@ parser.add_argument("--seed", type=int, default=None, help="fixed seed (default:
 parser.add_argument("--synthetic", type=int, default=0, help="train on this many seeded synthetic pairs")
 parser.add_argument("--no_dump", action="store_true", help="skip checksample PNG dumps")
 parser.add_argument("--max_iters", type=int, default=0, help="stop each epoch after this many iterations (0 = all)")
+parser.add_argument("--device_data", action="store_true",
+                    help="assemble the training patches on the GPU (rcot_b200.data: crop / augmentation / uint8-grid "
+                         "noise in one kernel per batch) instead of a CPU DataLoader; with --synthetic N")
 parser.add_argument("--cuda_graph", action="store_true",
                     help="replay each iteration as one CUDA graph (for small per-GPU batches; needs a fixed batch size)")
 
@@ -99,6 +102,25 @@ class SyntheticPairs(torch.utils.data.Dataset):
         else:
             deg = torch.clamp(clean + 0.1 * torch.randn(3, P, P, generator=g), 0, 1)
         return [f"synthetic_{i}", de_id], deg, clean
+
+
+class DeviceLoader:
+    """Loader facade over rcot_b200.data.DeviceTrainData: yields ([names, de_id(global batch)], degraded, clean) with
+    the image tensors already on the GPU -- under data parallelism only this rank's shard is assembled (every rank
+    draws the same integers from the same seeded RNG)."""
+
+    def __init__(self, data, batch, iters, rank=0, world=1):
+        self.data, self.B, self.iters, self.rank, self.world = data, batch, iters, rank, world
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        B, r, w = self.B, self.rank, self.world
+        for _ in range(self.iters):
+            draws = self.data.draw(B)
+            _, deg, cln = self.data.assemble(draws[r * B // w:(r + 1) * B // w])
+            yield [[f"pool_{d[1]}" for d in draws], torch.tensor([d[0] for d in draws])], deg, cln
 
 
 # ---------------------------------------------------------------------------------- optimizer facade
@@ -169,17 +191,22 @@ def train_one(step, batch, iteration, lr):
     """One iteration on a host batch ([names, de_id], degraded, target); returns device-side losses."""
     ([_, de_id], degraded, target) = batch
     rank, world = _world()
-    B = degraded.shape[0]
+    de_id = torch.as_tensor(de_id)
+    B = de_id.shape[0]                              # the GLOBAL batch
     alpha = torch.rand(B, 1, 1, 1).view(B)          # CPU RNG, global batch, like trainer.py:284
     if world > 1:
         if B % world:
             raise ValueError(f"global batch {B} is not divisible by {world} ranks")
         sl = slice(rank * B // world, (rank + 1) * B // world)
-        degraded, target, de_id, alpha = degraded[sl], target[sl], de_id[sl], alpha[sl]
+        de_id, alpha = de_id[sl], alpha[sl]
+        if degraded.shape[0] == B:                  # host loader: every rank holds the global batch
+            degraded, target = degraded[sl], target[sl]
+        elif degraded.shape[0] != B // world:       # DeviceLoader: already this rank's shard
+            raise ValueError(f"batch of {degraded.shape[0]} images for a global batch of {B} on {world} ranks")
     dev = step.T.ps.flat.device
     degraded = degraded.to(dev, non_blocking=True)
     target = target.to(dev, non_blocking=True)
-    de_id = torch.as_tensor(de_id).to(dev, non_blocking=True).long()
+    de_id = de_id.to(dev, non_blocking=True).long()
     alpha = alpha.to(dev, non_blocking=True)
     paired = iteration < opt.pairnum // opt.batchSize
     run = step.iteration_graphed if getattr(opt, "cuda_graph", False) else step.iteration
@@ -309,6 +336,14 @@ def main(argv=None):
     loader = torch.utils.data.DataLoader(train_set, num_workers=opt.threads, batch_size=opt.batchSize, shuffle=True,
                                          generator=torch.Generator().manual_seed(opt.seed), pin_memory=True,
                                          drop_last=(world > 1 or opt.cuda_graph))
+    if opt.device_data:
+        if not opt.synthetic:
+            raise SystemExit("--device_data currently takes its images from --synthetic N (real folders: fill a "
+                             "rcot_b200.data.DevicePool with the decoded uint8 images)")
+        from rcot_b200.data import DeviceTrainData, synthetic_pool
+        pool, samples = synthetic_pool(opt.synthetic, opt.patch_size + 37, opt.patch_size + 52, opt.de_type, opt.seed)
+        loader = DeviceLoader(DeviceTrainData(pool, samples, opt.patch_size, opt.seed), opt.batchSize,
+                              max(1, opt.synthetic // opt.batchSize), rank, world)
     deg_list, tar_list = sorted(glob.glob(opt.degset + "*")), sorted(glob.glob(opt.tarset + "*"))
     for epoch in range(opt.start_epoch, opt.nEpochs + 1):
         train(loader, T_optimizer, F_optimizer, Tnet, Fnet, epoch)
