@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--patch", type=int, default=128)
     ap.add_argument("--terms", type=int, default=3, help="3: bf16x3 split products (fp32-class), 1: bf16 products")
-    ap.add_argument("--graph", action="store_true", help="replay each iteration as one CUDA graph")
+    ap.add_argument("--graph", type=int, default=-1,
+                    help="replay each iteration as one CUDA graph: 1 on, 0 off, -1 (default) on when the per-GPU batch <= 8")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the strong-scaling and c2/c4/c5 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -244,8 +246,9 @@ def run_b200(args):
         torch.distributed.init_process_group("nccl")
     ops.TERMS = args.terms
     B, P, K, W = args.batch, args.patch, args.steps, max(args.warmup, 3)
+    args.graph = (B <= 8) if args.graph < 0 else bool(args.graph)
     trainer.opt = trainer.parser.parse_args(["--batchSize", str(B * world), "--patch_size", str(P), "--pairnum", "1000000000",
-                                             "--no_dump"] + (["--cuda_graph"] if args.graph else []))
+                                             "--no_dump", "--cuda_graph", "1" if args.graph else "0"])
     torch.manual_seed(0)
     Tnet = N.T_net(decoder=True).cuda()
     Fnet = N.F_net(patch_size=P).cuda()
@@ -307,6 +310,74 @@ def run_b200(args):
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
     e2e = B * world * K / (ms2.item() / 1000.0)
 
+    # ---- side measurements (not the headline): strong scaling at global batch 32 and BASELINE configs c2 / c4 / c5
+    def side_run(Bs, paired, ksteps=5, graph=None, Ps=None):
+        """ms per step (max over ranks) of the same iteration at per-GPU batch Bs."""
+        Ps = P if Ps is None else Ps
+        hb = synth_host_batches(2, Bs, Ps, seed=50 + rank, pin=False)
+        dv = [(b[1].cuda(), b[2].cuda(), b[0][1].cuda()) for b in hb]
+        al = [torch.rand(Bs).cuda() for _ in range(2)]
+        use_graph = (Bs <= 8) if graph is None else graph
+        run = step.iteration_graphed if use_graph else step.iteration
+        for i in range(3):
+            run(dv[i % 2][0], dv[i % 2][1], dv[i % 2][2], al[i % 2], paired, lr)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(ksteps):
+            rr = run(dv[i % 2][0], dv[i % 2][1], dv[i % 2][2], al[i % 2], paired, lr)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device="cuda")
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        fin = bool(torch.isfinite(torch.stack([rr["loss_F"], rr["loss_T"], rr["loss_mse"]])).all().item())
+        return t.item() / ksteps, use_graph, fin
+
+    extras = {}
+    if not args.no_extra_configs and B == 32 and P == 128:
+        if world > 1 and 32 % world == 0:
+            Bs = 32 // world
+            m, gq, fin = side_run(Bs, True)
+            extras["strong"] = {"what": "same iteration, GLOBAL batch fixed at 32 (BASELINE config c3's shape)",
+                                "global_batch": 32, "per_gpu_batch": Bs, "value": 32 / (m / 1e3), "unit": UNIT,
+                                "ms_per_step": m, "cuda_graph": gq, "scaling": "strong", "finite": fin}
+        else:
+            extras["strong"] = {"what": "global batch 32 on one GPU = the headline run", "global_batch": 32,
+                                "per_gpu_batch": 32, "value": value, "unit": UNIT, "ms_per_step": ms / K,
+                                "cuda_graph": args.graph, "scaling": "strong"}
+        if world == 1:
+            m, gq, fin = side_run(8, True)
+            extras["c2"] = {"what": "BASELINE config c2: single GPU, 128x128, batch 8, fp32, paired", "value": 8 / (m / 1e3),
+                            "unit": UNIT, "ms_per_step": m, "cuda_graph": gq, "finite": fin}
+            m, gq, fin = side_run(2, False)
+            extras["c4"] = {"what": "BASELINE config c4 per-GPU share: unpaired (pairnum=0) full G/D alternation with the "
+                                    "Fourier-residual cost, 128x128, 2 images per GPU (16 global on 8 GPUs)",
+                            "value": 2 / (m / 1e3), "unit": UNIT, "ms_per_step": m, "cuda_graph": gq, "finite": fin}
+            m, gq, fin = side_run(4, True)
+            extras["c3_shape_fp32"] = {"what": "BASELINE config c3's per-GPU share (4 images, paired) at fp32 storage",
+                                       "value": 4 / (m / 1e3), "unit": UNIT, "ms_per_step": m, "cuda_graph": gq, "finite": fin}
+            # c5: T_net forward only, 256x256, 8 images per GPU (64 global on 8 GPUs)
+            x5 = torch.rand(8, 3, 256, 256, device="cuda")
+            with torch.no_grad():
+                for _ in range(2):
+                    step.T.forward(x5)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    y5 = step.T.forward(x5)
+                b.record()
+                torch.cuda.synchronize()
+            m5 = a.elapsed_time(b) / 5
+            fwd_bytes = 5 * 8 * 49.35e6 * 4 * 4 + 0.2567e9
+            extras["c5"] = {"what": "BASELINE config c5 per-GPU share: T_net forward only (inference), 256x256, 8 images",
+                            "value": 8 / (m5 / 1e3), "unit": "images/s", "ms_per_step": m5,
+                            "roofline_blocks_fwd": {"bytes": fwd_bytes, "achieved": fwd_bytes / 1e9 / (m5 / 1e3),
+                                                    "frac": fwd_bytes / 1e9 / (m5 / 1e3) / peaks()[0], "unit": "GB/s"},
+                            "finite": bool(torch.isfinite(y5).all().item())}
+            del x5, y5
+
     # ---- per-kernel CUDA-event timing of the same step (one extra step, outside the timed regions)
     roof, kernels = None, None
     peak, peak_src = peaks()
@@ -356,6 +427,7 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms2.item() / K},
             "losses_last_step": losses}
+    line.update(extras)
     if roof:
         line["roofline"] = roof
         line["kernels"] = kernels

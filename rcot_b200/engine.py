@@ -29,12 +29,18 @@ class ParamSet:
     """Parameters of one network as views into ONE flat fp32 buffer, a matching flat gradient
     buffer, and the packed bf16 hi/lo tcgen05 operand images of every GEMM weight."""
 
-    def __init__(self, named_params, device, used=None):
+    def __init__(self, named_params, device, used=None, bucket_of=None):
         """named_params: ordered {name: tensor}. ``used``: names that receive gradients (the rest
-        is placed at the tail of the flat buffers so optimizer kernels can skip it)."""
+        is placed at the tail of the flat buffers so optimizer kernels can skip it).
+        ``bucket_of(name) -> int``: groups the used parameters into contiguous gradient buckets (bucket 0 first),
+        so each bucket can be all-reduced as soon as the backward has finished it (``bucket_ranges``)."""
         names = list(named_params)
         if used is not None:
             names = [n for n in names if n in used] + [n for n in names if n not in used]
+        if bucket_of is not None:
+            head = [n for n in names if used is None or n in used]
+            tail = [n for n in names if not (used is None or n in used)]
+            names = sorted(head, key=bucket_of) + tail          # stable: state_dict order inside a bucket
         self.names = names
         # every tensor starts on a 16-byte boundary of the flat buffers (vector reductions into .grad, float4
         # optimizer passes); the padding elements stay zero in both buffers, so the optimizers leave them alone
@@ -49,6 +55,18 @@ class ParamSet:
         self.numel = off
         if self.n_used is None:
             self.n_used = off
+        self.bucket_ranges = [(0, self.n_used)]
+        if bucket_of is not None:
+            self.bucket_ranges, cur, start = [], None, 0
+            for n in names:
+                if used is not None and n not in used:
+                    break
+                b = bucket_of(n)
+                if cur is not None and b != cur:
+                    self.bucket_ranges.append((start, self.offsets[n]))
+                    start = self.offsets[n]
+                cur = b
+            self.bucket_ranges.append((start, self.n_used))
         self.flat = torch.zeros(off, device=device, dtype=torch.float32)
         self.grad = torch.zeros(off, device=device, dtype=torch.float32)
         self.p, self.g = {}, {}
@@ -94,6 +112,7 @@ class Tape:
         self.ops = []
         self.grads = {}
         self.calls = {}
+        self.on_marker = None            # callback(k): bucket k of the weight gradients is final (see marker())
 
     def slot(self, key):
         """How many times `key` (a block) has been invoked on this tape so far."""
@@ -104,6 +123,11 @@ class Tape:
     def record(self, out, bwd):
         if self.enabled:
             self.ops.append((out, bwd))
+
+    def marker(self, k):
+        """Placed in the FORWARD order; fires in backward once every op recorded after it has run its backward."""
+        if self.enabled:
+            self.ops.append((None, k))
 
     def add_grad(self, t, g):
         k = id(t)
@@ -118,6 +142,10 @@ class Tape:
         self.add_grad(out, dout)
         while self.ops:
             t, bwd = self.ops.pop()
+            if t is None:
+                if self.on_marker is not None:
+                    self.on_marker(bwd)
+                continue
             ent = self.grads.pop(id(t), None)
             if ent is not None:
                 bwd(ent[1])

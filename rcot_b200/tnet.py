@@ -43,9 +43,27 @@ def used_names(names):
     return {n for n in names if not n.startswith(UNUSED_PREFIXES)}
 
 
+# Gradient buckets in the order the backward FINISHES them (modules shared by the two passes accumulate until their
+# pass-1 use has been differentiated): 0 = residual conditioner, 1 = decoder side (both passes), 2 = latent,
+# 3 = encoder + patch_embed + down3_4 (last).  TnetProgram.forward places tape markers at the matching points.
+_BUCKET0 = ("resencoder_level", "reslatent.", "resdown1_2.", "resdown2_3.")
+_BUCKET1 = ("noise_level", "reduce_noise_level", "up4_3.", "up3_2.", "up2_1.", "reduce_chan_level", "decoder_level",
+            "refinement.", "output.")
+
+
+def bucket_of(name):
+    if name.startswith(_BUCKET0):
+        return 0
+    if name.startswith(_BUCKET1):
+        return 1
+    if name.startswith("latent."):
+        return 2
+    return 3
+
+
 class TnetProgram:
     def __init__(self, named_params, device):
-        self.ps = ParamSet(named_params, device, used=used_names(named_params))
+        self.ps = ParamSet(named_params, device, used=used_names(named_params), bucket_of=bucket_of)
         ps = self.ps
         self.stages = {name: [BlockSpec(ps, f"{name}.{i}.", C, h) for i in range(n)] for name, n, C, h in STAGES}
         self.single = {name: BlockSpec(ps, name + ".", C, h) for name, C, h in SINGLE_BLOCKS}
@@ -108,9 +126,16 @@ class TnetProgram:
         e1 = self._stage(engine.conv_fwd(cv["patch_embed"], img, tape, need_dx=input_grad), "encoder_level1", tape)
         e2 = self._stage(self._down(e1, "down1_2", tape), "encoder_level2", tape)
         e3 = self._stage(self._down(e2, "down2_3", tape), "encoder_level3", tape)
-        latent = self._stage(self._down(e3, "down3_4", tape), "latent", tape)
+        l4 = self._down(e3, "down3_4", tape)
+        if tape is not None:
+            tape.marker(2)                 # backward: latent's weight gradients are final here
+        latent = self._stage(l4, "latent", tape)
+        if tape is not None:
+            tape.marker(1)                 # ... the decoder side (both passes) is final here
         first = self._decode(latent, e1, e2, e3, img, tape, input_grad)
         res = engine.axpby_fwd(img, first, 1.0, -1.0, tape, need_dx=input_grad)
+        if tape is not None:
+            tape.marker(0)                 # ... the residual conditioner is final here
         r = self._stage(engine.conv_fwd(cv["patch_embed"], res, tape), "resencoder_level1", tape)
         r = self._stage(self._down(r, "resdown1_2", tape), "resencoder_level2", tape)
         r = self._stage(self._down(r, "resdown2_3", tape), "resencoder_level3", tape)

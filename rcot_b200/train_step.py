@@ -70,6 +70,9 @@ class OTTrainStep:
         self.timing = None                  # set to [] to collect (section, start_event, end_event) per iteration
         self._graphs = {}                   # (B, P, paired) -> captured iteration
         self._hyper = None                  # device [3 optimizer steps x (lr, bc1, bc2)] while capturing/replaying
+        self.overlap = True                 # data parallel: bucketed T-gradient all-reduce overlapped with the backward
+        self._side = None
+        self._reduced = set()
         self.capture = None                 # set to {} to keep clones of the three (all-reduced) gradient buffers (tests)
         self.world = 1
         if data_parallel and (group is not None or
@@ -93,6 +96,19 @@ class OTTrainStep:
     def _allreduce(self, t):
         if self.world > 1:
             torch.distributed.all_reduce(t, group=self.group)
+
+    def _bucket_ready(self, k):
+        """Tape marker callback: gradient bucket k of T_net is final -> all-reduce it on the side stream while the
+        backward of the remaining modules keeps the SMs busy."""
+        a, b = self.T.ps.bucket_ranges[k]
+        if b <= a:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            torch.distributed.all_reduce(self.T.ps.grad[a:b], group=self.group)
+        self._reduced.add(k)
 
     def iteration(self, degraded, target, de_id, alpha, paired, lr):
         """degraded/target: [B,3,P,P] local shard; de_id: int64 [B]; alpha: [B] gradient-penalty
@@ -142,9 +158,23 @@ class OTTrainStep:
         dout = torch.empty_like(out)
         ops.cost_stage2(out, degraded, tgt, gfou, dF, acc, dout, self.sigma, self.Sigma, n_global)
         self._mark("T_backward")
+        overlap = self.world > 1 and self.overlap and len(T.ps.bucket_ranges) > 1
+        if overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._reduced = set()
+            tape.on_marker = self._bucket_ready
         tape.backward(out, dout)
         self._mark("T_allreduce_and_optimizer")
-        self._allreduce(T.ps.grad[:T.ps.n_used])
+        if overlap:
+            for k, (a, b) in enumerate(T.ps.bucket_ranges):       # what no marker covered (the encoder bucket)
+                if k not in self._reduced and b > a:
+                    self._allreduce(T.ps.grad[a:b])
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+        else:
+            self._allreduce(T.ps.grad[:T.ps.n_used])
         if self.capture is not None:
             self.capture["T"] = T.ps.grad.clone()
             self.capture["dout"] = dout.clone()

@@ -62,8 +62,9 @@ parser.add_argument("--max_iters", type=int, default=0, help="stop each epoch af
 parser.add_argument("--device_data", action="store_true",
                     help="assemble the training patches on the GPU (rcot_b200.data: crop / augmentation / uint8-grid "
                          "noise in one kernel per batch) instead of a CPU DataLoader; with --synthetic N")
-parser.add_argument("--cuda_graph", action="store_true",
-                    help="replay each iteration as one CUDA graph (for small per-GPU batches; needs a fixed batch size)")
+parser.add_argument("--cuda_graph", type=int, default=-1,
+                    help="replay each iteration as one CUDA graph (fixed batch shape: the last partial batch of an epoch "
+                         "is dropped): 1 on, 0 off, -1 (default) on when the per-GPU batch is <= 8")
 
 opt = None
 DE_IDS = {'denoise_15': 0, 'denoise_25': 1, 'denoise_50': 2, 'derain': 3, 'dehaze': 4, 'deblur': 5, 'lowlight': 6,
@@ -175,6 +176,12 @@ def _train_step(Tnet, Fnet, kind):
     return ent
 
 
+def _use_graph(per_gpu_batch):
+    g = getattr(opt, "cuda_graph", 0)
+    g = int(g) if not isinstance(g, bool) else (1 if g else 0)
+    return per_gpu_batch <= 8 if g < 0 else bool(g)
+
+
 def _world():
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         return torch.distributed.get_rank(), torch.distributed.get_world_size()
@@ -209,7 +216,7 @@ def train_one(step, batch, iteration, lr):
     de_id = de_id.to(dev, non_blocking=True).long()
     alpha = alpha.to(dev, non_blocking=True)
     paired = iteration < opt.pairnum // opt.batchSize
-    run = step.iteration_graphed if getattr(opt, "cuda_graph", False) else step.iteration
+    run = step.iteration_graphed if _use_graph(degraded.shape[0]) else step.iteration
     return run(degraded.contiguous(), target.contiguous(), de_id, alpha, paired, lr), degraded, target
 
 
@@ -335,7 +342,7 @@ def main(argv=None):
     # or CUDA-graph replay (one captured batch shape) it is dropped instead
     loader = torch.utils.data.DataLoader(train_set, num_workers=opt.threads, batch_size=opt.batchSize, shuffle=True,
                                          generator=torch.Generator().manual_seed(opt.seed), pin_memory=True,
-                                         drop_last=(world > 1 or opt.cuda_graph))
+                                         drop_last=(world > 1 or _use_graph(opt.batchSize // world)))
     if opt.device_data:
         if not opt.synthetic:
             raise SystemExit("--device_data currently takes its images from --synthetic N (real folders: fill a "
