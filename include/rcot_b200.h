@@ -140,6 +140,37 @@ typedef struct {
 int rcot_make_patches(const uint8_t* pool, const rcot_patch_desc* desc, const float* noise, float* degraded,
                       float* clean, int B, int P, rcot_stream_t stream);
 
+/* ---------------------------------------------------------------- fused GDFN forward (one kernel)
+ * Net_Restormer.py:80-85 (+ the block's norm2 and residual, :212-213):
+ *     y = [x +] project_out( gelu(dwconv(project_in(LN(x)))[:hid]) * dwconv(project_in(LN(x)))[hid:] )
+ * with the hidden tensor kept on chip (8x16-pixel tiles with a 1-pixel halo, hidden dimension walked in slices of 16
+ * channel pairs, both 1x1 convs on tcgen05).  Built for C in {48, 96} (the levels that carry 84 % of the bytes), H % 8
+ * == 0, W % 16 == 0; other shapes use the three-launch path.  Weights come as one blob made by rcot_gdfn_pack from
+ * project_in.weight [2*hid, C], dwconv.weight [2*hid, 9] and project_out.weight [C, hid] (re-pack after each step).
+ * Optional save_u [B, 2*hid, H, W] / save_g [B, hid, H, W] receive the hidden tensors for a backward that wants them. */
+typedef struct {
+  const float* x;            /* [B, C, H, W], per-image block contiguous                     */
+  int64_t x_bs;
+  const float* ln_stats;     /* [B, H*W, 2] (mean, rstd) or NULL = no LayerNorm              */
+  const float* ln_gamma;
+  const float* ln_beta;
+  const void* wblob;         /* rcot_gdfn_pack output                                        */
+  float* y;                  /* [B, C, H, W]                                                 */
+  int64_t y_bs;
+  float* stats_out;          /* optional: LayerNorm statistics of y                          */
+  float* save_u;             /* optional                                                      */
+  int64_t u_bs;
+  float* save_g;             /* optional (16-byte aligned)                                    */
+  int64_t g_bs;
+  int32_t B, C, H, W, hid;
+  int32_t residual;          /* y = x + out                                                   */
+} rcot_gdfn_params;
+int rcot_gdfn_supported(int C, int H, int W);
+size_t rcot_gdfn_blob_bytes(int C, int hid);
+int rcot_gdfn_pack(const float* w_in, const float* w_dw, const float* w_out, void* blob, int C, int hid,
+                   rcot_stream_t stream);
+int rcot_gdfn_fwd(const rcot_gdfn_params* p, rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- LayerNorm over channels
  * Net_Restormer.py:173-200 (WithBias_LayerNorm on the 'b (h w) c' view): stats[b, p] = (mean, rstd)
  * with biased variance and eps 1e-5; the normalisation itself is applied as a GEMM prologue. */

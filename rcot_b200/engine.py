@@ -22,6 +22,9 @@ from . import ops
 # It moves 13.3 instead of 29.3 C*H*W passes but is issue-bound (8 k warp-instructions per 32x32 tile, measured
 # 1.49 ms vs 1.29 ms for the two kernels at C=96, 128x128, B=32), so the two-kernel form stays the default.
 FUSED_GDFN_MID = os.environ.get("RCOT_FUSED_GDFN_MID", "0") == "1"
+# RCOT_FUSED_GDFN=0 switches the one-kernel GDFN forward (csrc/gdfn_fused.cu; C in {48, 96}, H % 8 == 0, W % 16 == 0)
+# back to the three-launch path (pm_gemm -> dw_gate -> pm_gemm) for A/B measurements.
+FUSED_GDFN = os.environ.get("RCOT_FUSED_GDFN", "1") == "1"
 
 
 # ---------------------------------------------------------------------------------- parameters
@@ -79,6 +82,7 @@ class ParamSet:
             self.g[n] = self.grad[o:o + src.numel()].view(src.shape)
         self.table = ops.PackTable(device)
         self.pack_idx = {}
+        self.gdfn = {}                 # block prefix -> weight blob of the fused GDFN forward kernel
 
     def add_pack(self, name, kind):
         key = (name, kind)
@@ -91,9 +95,16 @@ class ParamSet:
         self.repack()
         return self
 
+    def add_gdfn(self, prefix, C, hid):
+        if prefix not in self.gdfn:
+            self.gdfn[prefix] = torch.empty(ops.gdfn_blob_bytes(C, hid), dtype=torch.uint8, device=self.flat.device)
+
     def repack(self):
         if self.table.entries:
             self.table.repack()
+        for pre, blob in self.gdfn.items():
+            f = pre + "ffn."
+            ops.gdfn_pack(self.p[f + "project_in.weight"], self.p[f + "dwconv.weight"], self.p[f + "project_out.weight"], blob)
 
     def pack(self, name, kind):
         return self.table.ptr(self.pack_idx[(name, kind)])
@@ -232,6 +243,8 @@ class BlockSpec:
             for n in ("project_in.weight", "project_out.weight"):
                 ps.add_pack(f + n, "fwd")
                 ps.add_pack(f + n, "dgrad")
+            if FUSED_GDFN and C in (48, 96):
+                ps.add_gdfn(prefix, C, self.hid)
 
 
 def _stats_of(x):
@@ -299,6 +312,10 @@ def gdfn_fwd(bs: BlockSpec, x, norm_name, residual, keep=False):
     hid = bs.hid
     stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
+    if bs.pre in ps.gdfn and ops.TERMS == 3 and ops.gdfn_supported(C, x.shape[2], x.shape[3]):
+        # one kernel, hidden tensor on chip; u / g are written out only when the backward wants them kept
+        y, u, g = ops.gdfn_fwd(x, ps.gdfn[bs.pre], hid, ln=ln, residual=residual, stats_out=bool(norm_name), save=keep)
+        return (y, (stats, u, g)) if keep else y
     u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
     g = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=1)
     y = ops.pm_gemm(g, ps.pack(f + "project_out.weight", "fwd"), C, residual=x if residual else None,

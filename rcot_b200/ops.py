@@ -262,6 +262,60 @@ def pk_gemm(a, b, out, *, ldo, ks=1, stride=1, pad=0, b2=None, ln=None, per_imag
     return out
 
 
+# ------------------------------------------------------------------ fused GDFN forward
+class GdfnParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_bs", C.c_int64), ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p),
+                ("ln_beta", C.c_void_p), ("wblob", C.c_void_p), ("y", C.c_void_p), ("y_bs", C.c_int64),
+                ("stats_out", C.c_void_p), ("save_u", C.c_void_p), ("u_bs", C.c_int64), ("save_g", C.c_void_p),
+                ("g_bs", C.c_int64), ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("hid", C.c_int32), ("residual", C.c_int32)]
+
+
+def gdfn_supported(Cc, H, W):
+    return bool(L().rcot_gdfn_supported(Cc, H, W))
+
+
+def gdfn_blob_bytes(Cc, hid):
+    L().rcot_gdfn_blob_bytes.restype = C.c_size_t
+    return int(L().rcot_gdfn_blob_bytes(Cc, hid))
+
+
+def gdfn_pack(w_in, w_dw, w_out, blob):
+    """Weight blob of the fused GDFN kernel from project_in [2hid,C,1,1], dwconv [2hid,1,3,3], project_out [C,hid,1,1]."""
+    global LAUNCHES
+    LAUNCHES += 1
+    Cc, hid = w_out.shape[0], w_out.shape[1]
+    _lib.check(L().rcot_gdfn_pack(_ptr(_f32(w_in)), _ptr(_f32(w_dw)), _ptr(_f32(w_out)), _ptr(blob), Cc, hid, _stream()),
+               "gdfn_pack")
+    return blob
+
+
+def gdfn_fwd(x, blob, hid, ln=None, residual=True, stats_out=False, save=False):
+    """One-kernel GDFN forward.  Returns (y, u or None, g or None); LayerNorm statistics of y are left on
+    ``y._rcot_ln_stats`` when stats_out."""
+    B, Cc, H, W = x.shape
+    p = GdfnParams()
+    p.x, p.x_bs = x.data_ptr(), _img_view(x, "x")
+    if ln is not None:
+        stats, gamma, beta = ln
+        p.ln_stats, p.ln_gamma, p.ln_beta = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    p.wblob = blob.data_ptr()
+    y = torch.empty_like(x)
+    p.y, p.y_bs = y.data_ptr(), _img_view(y, "y")
+    if stats_out:
+        st = torch.empty(B, H * W, 2, device=x.device, dtype=torch.float32)
+        p.stats_out = st.data_ptr()
+        y._rcot_ln_stats = st
+    u = g = None
+    if save:
+        u = torch.empty(B, 2 * hid, H, W, device=x.device, dtype=torch.float32)
+        g = torch.empty(B, hid, H, W, device=x.device, dtype=torch.float32)
+        p.save_u, p.u_bs, p.save_g, p.g_bs = u.data_ptr(), _img_view(u, "u"), g.data_ptr(), _img_view(g, "g")
+    p.B, p.C, p.H, p.W, p.hid, p.residual = B, Cc, H, W, hid, int(bool(residual))
+    _lib.check(L().rcot_gdfn_fwd(C.byref(p), _stream()), "gdfn_fwd")
+    return y, u, g
+
+
 # ------------------------------------------------------------------ LayerNorm
 def ln_stats(x, out=None):
     B, Cc, H, W = x.shape
@@ -542,6 +596,7 @@ def _pm_bytes(a, k, r):
 
 pm_gemm = _instrument("pm_gemm", _pm_bytes)(pm_gemm)
 pk_gemm = _instrument("pk_gemm", lambda a, k, r: _nb(a[0], a[1], k.get("b2"), a[2]))(pk_gemm)
+gdfn_fwd = _instrument("gdfn_fwd", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(gdfn_fwd)
 ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
 ln_fwd = _instrument("ln_fwd", lambda a, k, r: _nb(a[0], r[0]))(ln_fwd)
 ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)
