@@ -310,6 +310,41 @@ def run_b200(args):
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
     e2e = B * world * K / (ms2.item() / 1000.0)
 
+    # ---- per-kernel CUDA-event timing of the same step (one extra step, outside the timed regions)
+    roof, kernels = None, None
+    peak, peak_src = peaks()
+    phases = None
+    if not args.no_profile:
+        # phase breakdown of one more step (events only at 7 section boundaries)
+        step.timing = []
+        resident_step(0)
+        torch.cuda.synchronize()
+        phases = {k: round(v, 3) for k, v in step.sections_ms().items()}
+        step.timing = None
+        ops.PROF = ops.Profiler()
+        resident_step(0)
+        summ = ops.PROF.summary()
+        ops.PROF = None
+        tot = sum(v["ms"] for v in summ.values())
+        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4),
+                       "GBps": round(v["bytes"] / 1e9 / (v["ms"] / 1e3), 1) if v["ms"] > 0 else None}
+                   for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+        top, tv = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        achieved = tv["bytes"] / 1e9 / (tv["ms"] / 1e3)
+        # DRAM bytes per launch of that kernel from the committed ncu capture of the same workload (if present)
+        traffic = None
+        import glob
+        tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))   # newest capture last (r1, r1b, r2 ...)
+        if tps:
+            tj = json.load(open(tps[-1]))
+            if tj.get("kernel") == top and tj.get("per_gpu_batch") == B and tj.get("patch") == P:
+                traffic = tj["dram_bytes_per_launch"]
+        roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                "peak_source": peak_src,
+                "launches": tv["launches"], "avg_launch_ms": tv["ms"] / tv["launches"],
+                "note": "achieved = algorithmic bytes of all launches of this kernel in one step / their summed "
+                        "CUDA-event time, taken on one extra step right after the timed region"}
     # ---- side measurements (not the headline): strong scaling at global batch 32 and BASELINE configs c2 / c4 / c5
     def side_run(Bs, paired, ksteps=5, graph=None, Ps=None):
         """ms per step (max over ranks) of the same iteration at per-GPU batch Bs."""
@@ -378,41 +413,6 @@ def run_b200(args):
                             "finite": bool(torch.isfinite(y5).all().item())}
             del x5, y5
 
-    # ---- per-kernel CUDA-event timing of the same step (one extra step, outside the timed regions)
-    roof, kernels = None, None
-    peak, peak_src = peaks()
-    phases = None
-    if not args.no_profile:
-        # phase breakdown of one more step (events only at 7 section boundaries)
-        step.timing = []
-        resident_step(0)
-        torch.cuda.synchronize()
-        phases = {k: round(v, 3) for k, v in step.sections_ms().items()}
-        step.timing = None
-        ops.PROF = ops.Profiler()
-        resident_step(0)
-        summ = ops.PROF.summary()
-        ops.PROF = None
-        tot = sum(v["ms"] for v in summ.values())
-        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4),
-                       "GBps": round(v["bytes"] / 1e9 / (v["ms"] / 1e3), 1) if v["ms"] > 0 else None}
-                   for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
-        top, tv = max(summ.items(), key=lambda kv: kv[1]["ms"])
-        achieved = tv["bytes"] / 1e9 / (tv["ms"] / 1e3)
-        # DRAM bytes per launch of that kernel from the committed ncu capture of the same workload (if present)
-        traffic = None
-        import glob
-        tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))   # newest capture last (r1, r1b, r2 ...)
-        if tps:
-            tj = json.load(open(tps[-1]))
-            if tj.get("kernel") == top and tj.get("per_gpu_batch") == B and tj.get("patch") == P:
-                traffic = tj["dram_bytes_per_launch"]
-        roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
-                "peak_source": peak_src,
-                "launches": tv["launches"], "avg_launch_ms": tv["ms"] / tv["launches"],
-                "note": "achieved = algorithmic bytes of all launches of this kernel in one step / their summed "
-                        "CUDA-event time, taken on one extra step right after the timed region"}
     barrier()
     if rank != 0:
         if world > 1:

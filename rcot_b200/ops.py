@@ -159,6 +159,8 @@ class PackTable:
 
     def finalize(self):
         self.buf = torch.empty(max(self.total, 256), dtype=torch.uint8, device=self.device)
+        if not self.entries:          # a program without GEMM weights (stand-alone LayerNorm)
+            return self
         arr = (PackDesc * len(self.entries))()
         for i, (w, N, K, R, sk, sn, off, ski) in enumerate(self.entries):
             arr[i] = PackDesc(w.data_ptr(), self.buf.data_ptr() + off, N, K, R, sk, sn, ski)

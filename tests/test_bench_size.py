@@ -73,7 +73,7 @@ def test_full_iteration_128(cuda_lib, paired):
     alpha = torch.tensor([0.25, 0.7])
     step = OTTrainStep(Tp, Fp, "RMSprop", sigma=1.0, Sigma=10000.0)
     step.capture = {}
-    Tflat0 = Tp.ps.flat.clone()
+    Tflat0, Fflat0 = Tp.ps.flat.clone(), Fp.ps.flat.clone()
     r = step.iteration(deg.cuda(), tgt.cuda(), de_id.cuda(), alpha.cuda(), paired, 1e-4)
     o = train_ref.train_iteration(T_sd, F_sd, {}, {}, deg, tgt, de_id, alpha, 1e-4, 1.0, 10000.0, paired)
     got = [r["loss_F"].item(), r["loss_gp"].item(), r["loss_T"].item(), r["loss_mse"].item()]
@@ -84,8 +84,19 @@ def test_full_iteration_128(cuda_lib, paired):
     assert abs(got[2] - want[2]) <= 2e-4 * abs(want[2])
     assert abs(got[3] - want[3]) <= 2e-4 * abs(want[3])
     torch.testing.assert_close(r["out"].cpu(), o["out"], rtol=1e-3, atol=1e-4)
-    _cmp_grads(Fp.ps, step.capture["F"], o["grads_F"], 3e-3, "F-sub")
+    # F-sub inside the iteration: L_F = mean f(fake) - mean f(real) ~ 5e-5 at initialisation -- its gradient is a ~1 %
+    # residue of two cancelling terms, so the 1e-5-level difference between our T(x) and the oracle's shows up as ~1e-2
+    _cmp_grads(Fp.ps, step.capture["F"], o["grads_F"], 3e-2, "F-sub (own T output)", tol_tensor=6e-2)
     _cmp_grads(Fp.ps, step.capture["GP"], o["grads_GP"], 2e-2, "GP")   # weights differ by +-10*lr where ~0 gradients flipped sign
+    # ... and the potential's backward itself, fed the ORACLE's fake batch at the initial weights: tight
+    Ff = Fp.ps.flat.clone()
+    Fp.ps.flat.copy_(Fflat0)
+    Fp.ps.repack()
+    Fp.ps.zero_grad()
+    Fp.critic_step(tgt.cuda(), o["out"].cuda(), B)
+    _cmp_grads(Fp.ps, Fp.ps.grad, o["grads_F"], 3e-3, "F-sub (oracle's T output)", tol_tensor=1e-2)
+    Fp.ps.flat.copy_(Ff)
+    Fp.ps.repack()
     if not paired:
         _cmp_grads(Tp.ps, step.capture["T"], o["grads_T"], 3e-3, "T-sub (unpaired)")
         return
@@ -141,7 +152,7 @@ def test_batch32_equals_sum_of_shards(cuda_lib):
         sl = slice(i, i + S)
         g, o = t_grads(sl)
         sT += g
-        torch.testing.assert_close(o, out[sl], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(o, out[sl], rtol=1e-4, atol=2e-5)     # MDTA's Gram atomics: summation order only
         a, b = f_grads(sl, o)
         sF += a
         sGP += b

