@@ -164,6 +164,7 @@ typedef struct {
   int64_t g_bs;
   int32_t B, C, H, W, hid;
   int32_t residual;          /* y = x + out                                                   */
+  int32_t debug;             /* measurement knobs (0 in production): 1 skip MMAs, 2 skip stencil, 4 skip drain stores */
 } rcot_gdfn_params;
 int rcot_gdfn_supported(int C, int H, int W);
 size_t rcot_gdfn_blob_bytes(int C, int hid);

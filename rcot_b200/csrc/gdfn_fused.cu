@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
   auto issue_gemm1 = [&](long n) {                    // tid 0: U[n & 1] = Z . W_in[slice n]^T, both 128-row tiles
     const uint32_t wb = win_base + (uint32_t)(n & 1) * L::WIN;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < ((p.debug & 1) ? 0 : 2); ++mt) {
       const uint32_t d = tmem + (uint32_t)(n & 1) * 64 + mt * 32;
       const uint32_t ah = z_base + (mt * 2 + 0) * L::ZT, al = z_base + (mt * 2 + 1) * L::ZT;
 #pragma unroll
@@ -131,9 +131,11 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
     const uint32_t wh = wo_base + (uint32_t)(n & 3) * L::WO + GF_DW_BYTES, wl = wh + L::WOUT_T;
     const uint64_t dgh = make_sdesc(gh, 128, GF_G_SBO), dgl = make_sdesc(gl, 128, GF_G_SBO);
     const uint64_t dwh = make_sdesc(wh, 128, 256), dwl = make_sdesc(wl, 128, 256);
-    tc_mma_bf16(tmem_y, dgh, dwh, idesc2, first ? 0u : 1u);
-    tc_mma_bf16(tmem_y, dgl, dwh, idesc2, 1u);
-    tc_mma_bf16(tmem_y, dgh, dwl, idesc2, 1u);
+    if (!(p.debug & 1)) {
+      tc_mma_bf16(tmem_y, dgh, dwh, idesc2, first ? 0u : 1u);
+      tc_mma_bf16(tmem_y, dgl, dwh, idesc2, 1u);
+      tc_mma_bf16(tmem_y, dgh, dwl, idesc2, 1u);
+    }
     tc_commit(&gbar[n & 1]);
   };
 
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
         uint32_t r[16];
         tmem_ld16_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(n & 1) * 64 + mt * 32 + ch0, r);
         tmem_ld_wait();
-        if (hp < GF_NHP) {
+        if (hp < GF_NHP && !(p.debug & 4)) {
           const int hy = hp / GF_HW, hx = hp - hy * GF_HW;
           float* up = Usm + ch0 * GF_CS + hy * GF_RS + hx;
 #pragma unroll
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
       tc_fence_before();
       __syncthreads();                                           // (B)
       // ---- stencil + gate: warp = pair j of the slice, lane = (row r, 4-pixel strip xq)
-      {
+      if (!(p.debug & 2)) {
         const int j = warp, xq = lane & 3, r = lane >> 2;
         const float* wdw = reinterpret_cast<const float*>(smem + L::OFF_WO + (n & 3) * L::WO);
         float wa[9], wb[9];

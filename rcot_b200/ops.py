@@ -270,7 +270,7 @@ class GdfnParams(C.Structure):
                 ("ln_beta", C.c_void_p), ("wblob", C.c_void_p), ("y", C.c_void_p), ("y_bs", C.c_int64),
                 ("stats_out", C.c_void_p), ("save_u", C.c_void_p), ("u_bs", C.c_int64), ("save_g", C.c_void_p),
                 ("g_bs", C.c_int64), ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("hid", C.c_int32), ("residual", C.c_int32)]
+                ("hid", C.c_int32), ("residual", C.c_int32), ("debug", C.c_int32)]
 
 
 def gdfn_supported(Cc, H, W):
@@ -314,6 +314,7 @@ def gdfn_fwd(x, blob, hid, ln=None, residual=True, stats_out=False, save=False):
         g = torch.empty(B, hid, H, W, device=x.device, dtype=torch.float32)
         p.save_u, p.u_bs, p.save_g, p.g_bs = u.data_ptr(), _img_view(u, "u"), g.data_ptr(), _img_view(g, "g")
     p.B, p.C, p.H, p.W, p.hid, p.residual = B, Cc, H, W, hid, int(bool(residual))
+    p.debug = int(os.environ.get("RCOT_GDFN_DEBUG", "0"))
     _lib.check(L().rcot_gdfn_fwd(C.byref(p), _stream()), "gdfn_fwd")
     return y, u, g
 
