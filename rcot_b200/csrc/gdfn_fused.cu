@@ -29,7 +29,9 @@ constexpr int GF_NHP = GF_HH * GF_HW;                // 180 halo pixels
 constexpr int GF_RS = 20;                            // shared-memory row stride of a halo row (floats)
 constexpr int GF_CS = 208;                           // channel stride (floats) >= 10 * 20
 constexpr int GF_HS = 16;                            // (a, b) pairs per hidden slice
-constexpr int GF_THREADS = 512;
+constexpr int GF_WORKER_WARPS = 16;                  // drain / stencil / epilogue warps
+constexpr int GF_THREADS = (GF_WORKER_WARPS + 1) * 32;   // + the issuer warp (TMA weight ring, every tcgen05.mma)
+constexpr int GF_WIN_SLOTS = 3;                      // W_in slice ring
 constexpr uint32_t GF_G_SBO = 272;                   // g operand: 8-row group stride (256 + 16 B pad against bank conflicts)
 constexpr uint32_t GF_G_TILE = 16 * GF_G_SBO;        // one term of the [128 x 16] g operand
 constexpr uint32_t GF_DW_BYTES = 32 * 9 * sizeof(float);
@@ -47,7 +49,7 @@ struct GfLayout {
   static constexpr uint32_t OFF_U = OFF_Z + 4 * ZT;
   static constexpr uint32_t OFF_G = OFF_U + 32 * GF_CS * 4;
   static constexpr uint32_t OFF_WIN = OFF_G + 2 * 2 * GF_G_TILE;
-  static constexpr uint32_t OFF_WO = OFF_WIN + 2 * WIN;
+  static constexpr uint32_t OFF_WO = OFF_WIN + GF_WIN_SLOTS * WIN;
   static constexpr uint32_t OFF_GB = OFF_WO + 4 * WO;          // gamma, beta
   static constexpr uint32_t OFF_ST = OFF_GB + 2 * C * 4;       // partial statistics [4][128][2]
   static constexpr uint32_t TOTAL = OFF_ST + 4 * 128 * 2 * 4;
@@ -59,12 +61,18 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
                : "r"(taddr));
 }
 
+// Named barrier among the 16 worker warps only (the issuer warp never joins it).
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 template <int C>
 __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn_params p, const int tiles_x,
                                                                 const int tiles_per_img, const int total_tiles) {
   using L = GfLayout<C>;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t winbar[2], wobar[4], ubar[2], gbar[2];
+  // TMA completions: winbar, wobar.  tcgen05.commit: ubar (U slice ready), gbar (GEMM-2 done: g slot + W_out slot free).
+  // workers -> issuer (one arrival per worker warp): zbar (Z of the tile ready), dbar (U TMEM buffer drained),
+  // sbar (g slice written), ybar (Y drained by the epilogue).
+  __shared__ uint64_t winbar[GF_WIN_SLOTS], wobar[4], ubar[2], gbar[2], zbar, dbar[2], sbar[2], ybar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, W = p.W, HWp = H * W, hid = p.hid;
@@ -81,12 +89,16 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
     }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
   if (tid == 0) {
+    for (int i = 0; i < GF_WIN_SLOTS; ++i) mbar_init(&winbar[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&wobar[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&winbar[i], 1);
       mbar_init(&ubar[i], 1);
       mbar_init(&gbar[i], 1);
+      mbar_init(&dbar[i], GF_WORKER_WARPS);
+      mbar_init(&sbar[i], GF_WORKER_WARPS);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&wobar[i], 1);
+    mbar_init(&zbar, GF_WORKER_WARPS);
+    mbar_init(&ybar, GF_WORKER_WARPS);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -94,65 +106,100 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tmem_y = tmem + 128;                 // U buffers: columns [0,128); Y: [128, 128 + C)
-
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const long total_slices = (long)my_tiles * NS;
-  const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.wblob);
-  auto load_slice = [&](long n) {                     // tid 0: weight slice n -> its ring slots
-    const uint8_t* src = blob + (size_t)(n % NS) * L::SLICE;
-    mbar_arrive_expect_tx(&winbar[n & 1], L::WIN);
-    bulk_g2s(smem + L::OFF_WIN + (n & 1) * L::WIN, src, L::WIN, &winbar[n & 1]);
-    mbar_arrive_expect_tx(&wobar[n & 3], L::WO);
-    bulk_g2s(smem + L::OFF_WO + (n & 3) * L::WO, src + L::WIN, L::WO, &wobar[n & 3]);
-  };
-  const uint32_t idesc1 = make_idesc_bf16(128, 32), idesc2 = make_idesc_bf16(128, C);
-  const uint32_t z_base = smem_u32(smem + L::OFF_Z), g_base = smem_u32(smem + L::OFF_G);
-  const uint32_t win_base = smem_u32(smem + L::OFF_WIN), wo_base = smem_u32(smem + L::OFF_WO);
-  auto issue_gemm1 = [&](long n) {                    // tid 0: U[n & 1] = Z . W_in[slice n]^T, both 128-row tiles
-    const uint32_t wb = win_base + (uint32_t)(n & 1) * L::WIN;
+  const int total_slices = my_tiles * NS;
+
+  if (warp == GF_WORKER_WARPS) {
+    // ================================================================ issuer warp: TMA weight ring + every MMA
+    const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.wblob);
+    const uint32_t idesc1 = make_idesc_bf16(128, 32), idesc2 = make_idesc_bf16(128, C);
+    const uint32_t z_base = smem_u32(smem + L::OFF_Z), g_base = smem_u32(smem + L::OFF_G);
+    const uint32_t win_base = smem_u32(smem + L::OFF_WIN), wo_base = smem_u32(smem + L::OFF_WO);
+    // descriptor templates: everything but the 14-bit start address
+    const uint64_t dz_t = make_sdesc(0, 128, L::SBOZ), dg_t = make_sdesc(0, 128, GF_G_SBO), dw_t = make_sdesc(0, 128, 256);
+    auto load_slice = [&](int n) {
+      const uint8_t* src = blob + (size_t)(n % NS) * L::SLICE;
+      const int ws = n % GF_WIN_SLOTS;
+      mbar_arrive_expect_tx(&winbar[ws], L::WIN);
+      bulk_g2s(smem + L::OFF_WIN + ws * L::WIN, src, L::WIN, &winbar[ws]);
+      mbar_arrive_expect_tx(&wobar[n & 3], L::WO);
+      bulk_g2s(smem + L::OFF_WO + (n & 3) * L::WO, src + L::WIN, L::WO, &wobar[n & 3]);
+    };
+    auto issue_gemm1 = [&](int n) {                   // U[n & 1] = Z . W_in[slice n]^T, both 128-row tiles
+      const uint32_t wb = (win_base + (uint32_t)(n % GF_WIN_SLOTS) * L::WIN) >> 4;
+      if (!(p.debug & 1)) {
 #pragma unroll
-    for (int mt = 0; mt < ((p.debug & 1) ? 0 : 2); ++mt) {
-      const uint32_t d = tmem + (uint32_t)(n & 1) * 64 + mt * 32;
-      const uint32_t ah = z_base + (mt * 2 + 0) * L::ZT, al = z_base + (mt * 2 + 1) * L::ZT;
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t d = tmem + (uint32_t)(n & 1) * 64 + mt * 32;
+          const uint32_t ah = (z_base + (mt * 2 + 0) * L::ZT) >> 4, al = (z_base + (mt * 2 + 1) * L::ZT) >> 4;
 #pragma unroll
-      for (int ks = 0; ks < C / 16; ++ks) {
-        const uint32_t ko = ks * 256;
-        const uint64_t dah = make_sdesc(ah + ko, 128, L::SBOZ), dal = make_sdesc(al + ko, 128, L::SBOZ);
-        const uint64_t dbh = make_sdesc(wb + ko, 128, L::SBOZ), dbl = make_sdesc(wb + 4 * L::SBOZ + ko, 128, L::SBOZ);
-        tc_mma_bf16(d, dah, dbh, idesc1, ks == 0 ? 0u : 1u);
-        tc_mma_bf16(d, dal, dbh, idesc1, 1u);
-        tc_mma_bf16(d, dah, dbl, idesc1, 1u);
+          for (int ks = 0; ks < C / 16; ++ks) {
+            const uint64_t dah = dz_t | (uint64_t)((ah + ks * 16) & 0x3FFFu), dal = dz_t | (uint64_t)((al + ks * 16) & 0x3FFFu);
+            const uint64_t dbh = dz_t | (uint64_t)((wb + ks * 16) & 0x3FFFu);
+            const uint64_t dbl = dz_t | (uint64_t)((wb + (4 * L::SBOZ >> 4) + ks * 16) & 0x3FFFu);
+            tc_mma_bf16(d, dah, dbh, idesc1, ks == 0 ? 0u : 1u);
+            tc_mma_bf16(d, dal, dbh, idesc1, 1u);
+            tc_mma_bf16(d, dah, dbl, idesc1, 1u);
+          }
+        }
       }
+      tc_commit(&ubar[n & 1]);
+    };
+    auto issue_gemm2 = [&](int n, bool first) {       // Y (+)= g[n & 1] . W_out[:, slice n]^T   (K = 16)
+      const uint32_t gh = (g_base + (uint32_t)(n & 1) * 2 * GF_G_TILE) >> 4, gl = gh + (GF_G_TILE >> 4);
+      const uint32_t wh = (wo_base + (uint32_t)(n & 3) * L::WO + GF_DW_BYTES) >> 4, wl = wh + (L::WOUT_T >> 4);
+      if (!(p.debug & 1)) {
+        const uint64_t dgh = dg_t | (uint64_t)(gh & 0x3FFFu), dgl = dg_t | (uint64_t)(gl & 0x3FFFu);
+        const uint64_t dwh = dw_t | (uint64_t)(wh & 0x3FFFu), dwl = dw_t | (uint64_t)(wl & 0x3FFFu);
+        tc_mma_bf16(tmem_y, dgh, dwh, idesc2, first ? 0u : 1u);
+        tc_mma_bf16(tmem_y, dgl, dwh, idesc2, 1u);
+        tc_mma_bf16(tmem_y, dgh, dwl, idesc2, 1u);
+      }
+      tc_commit(&gbar[n & 1]);
+    };
+    if (lane == 0) {
+      if (total_slices > 0) load_slice(0);
+      if (total_slices > 1) load_slice(1);
     }
-    tc_commit(&ubar[n & 1]);
-  };
-  auto issue_gemm2 = [&](long n, bool first) {        // tid 0: Y (+)= g[n & 1] . W_out[:, slice n]^T   (K = 16)
-    const uint32_t gh = g_base + (uint32_t)(n & 1) * 2 * GF_G_TILE, gl = gh + GF_G_TILE;
-    const uint32_t wh = wo_base + (uint32_t)(n & 3) * L::WO + GF_DW_BYTES, wl = wh + L::WOUT_T;
-    const uint64_t dgh = make_sdesc(gh, 128, GF_G_SBO), dgl = make_sdesc(gl, 128, GF_G_SBO);
-    const uint64_t dwh = make_sdesc(wh, 128, 256), dwl = make_sdesc(wl, 128, 256);
-    if (!(p.debug & 1)) {
-      tc_mma_bf16(tmem_y, dgh, dwh, idesc2, first ? 0u : 1u);
-      tc_mma_bf16(tmem_y, dgl, dwh, idesc2, 1u);
-      tc_mma_bf16(tmem_y, dgh, dwl, idesc2, 1u);
+    int n = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      mbar_wait(&zbar, (uint32_t)ti & 1);                          // Z of this tile is in shared memory
+      for (int s = 0; s < NS; ++s, ++n) {
+        // ---- GEMM-1(n): needs W_in(n) and the U buffer n&1 drained (slice n-2)
+        mbar_wait(&winbar[n % GF_WIN_SLOTS], (uint32_t)(n / GF_WIN_SLOTS) & 1);
+        if (n >= 2) mbar_wait(&dbar[n & 1], (uint32_t)((n - 2) >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) issue_gemm1(n);
+        __syncwarp();
+        // ---- weight prefetch for slice n+2: W_in slot of slice n-1 (GEMM-1(n-1) done), W_out slot of slice n-2
+        if (n + 2 < total_slices) {
+          if (n >= 1) mbar_wait(&ubar[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
+          if (n >= 2) mbar_wait(&gbar[n & 1], (uint32_t)((n - 2) >> 1) & 1);
+          if (lane == 0) load_slice(n + 2);
+          __syncwarp();
+        }
+        // ---- GEMM-2(n-1): needs g(n-1); the first one of a tile overwrites Y, which the epilogue must have drained
+        if (s > 0) {
+          mbar_wait(&sbar[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
+          if (s == 1 && ti > 0) mbar_wait(&ybar, (uint32_t)(ti - 1) & 1);
+          tc_fence_after();
+          if (lane == 0) issue_gemm2(n - 1, s == 1);
+          __syncwarp();
+        }
+      }
+      mbar_wait(&sbar[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
+      if (NS == 1 && ti > 0) mbar_wait(&ybar, (uint32_t)(ti - 1) & 1);
+      tc_fence_after();
+      if (lane == 0) issue_gemm2(n - 1, NS == 1);
+      __syncwarp();
     }
-    tc_commit(&gbar[n & 1]);
-  };
-
-  if (tid == 0) {
-    if (total_slices > 0) load_slice(0);
-    if (total_slices > 1) load_slice(1);
-  }
-
-  long n = 0;                                          // running slice counter of this CTA
-  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-    const int b = t / tiles_per_img, tr = t - b * tiles_per_img;
-    const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
-    const int y0 = ty * GF_TH, x0 = tx * GF_TW;
-    const float* xb = p.x + (size_t)b * p.x_bs;
-
-    // ------------------------------------------------------------ Z: LN(x) of the halo tile as bf16 hi/lo operand
-    {
+  } else {
+    // ================================================================ 16 worker warps
+    // Z phase of one tile: LN(x) of the halo tile as the bf16 hi/lo operand; arrives on zbar
+    auto produce_z = [&](int t) {
+      const int b = t / tiles_per_img, tr = t - b * tiles_per_img;
+      const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+      const int y0 = ty * GF_TH, x0 = tx * GF_TW;
       const int hp = tid & 255, half = tid >> 8;
       const int hy = hp / GF_HW, hx = hp - hy * GF_HW;
       const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
@@ -162,7 +209,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
       uint8_t* zl = zh + L::ZT;
       constexpr int NG = C / 16;                      // 8-channel groups per thread (half of the channels)
       if (inimg) {
-        const float* xp = xb + (size_t)gy * W + gx + (size_t)(half * (C / 2)) * HWp;
+        const float* xp = p.x + (size_t)b * p.x_bs + (size_t)gy * W + gx + (size_t)(half * (C / 2)) * HWp;
         float v[NG][8];
 #pragma unroll
         for (int g = 0; g < NG; ++g)
@@ -196,159 +243,156 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
           *reinterpret_cast<uint4*>(zl + ko) = z4;
         }
       }
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&winbar[n & 1], (uint32_t)(n >> 1) & 1);
-      tc_fence_after();
-      issue_gemm1(n);
-    }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&zbar);
+    };
 
-    // ------------------------------------------------------------ hidden slices
-    for (int s = 0; s < NS; ++s, ++n) {
-      if (tid == 0) {
-        mbar_wait(&ubar[n & 1], (uint32_t)(n >> 1) & 1);        // GEMM-1(n) done: U[n&1] ready, W_in slot n&1 free
-        mbar_wait(&wobar[n & 3], (uint32_t)(n >> 2) & 1);       // depthwise taps + W_out of slice n present
-        if (n >= 2) mbar_wait(&gbar[n & 1], (uint32_t)((n - 2) >> 1) & 1);   // GEMM-2(n-2) done: g slot n&1 free
-      }
-      __syncthreads();                                           // (A) also: stencil(n-1) finished writing g[(n-1)&1]
-      tc_fence_after();
-      if (tid == 0) {
-        if (s > 0) issue_gemm2(n - 1, s == 1);
-        if (s + 1 < NS) {
-          mbar_wait(&winbar[(n + 1) & 1], (uint32_t)((n + 1) >> 1) & 1);
-          issue_gemm1(n + 1);
-        }
-        if (n + 2 < total_slices) load_slice(n + 2);
-      }
-      // ---- drain U(n): TMEM -> shared [channel][halo row][halo col]
-      {
-        const int q = warp & 3, mt = (warp >> 2) & 1, ch0 = (warp >> 3) * 16;
-        const int hp = mt * 128 + q * 32 + lane;
-        uint32_t r[16];
-        tmem_ld16_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(n & 1) * 64 + mt * 32 + ch0, r);
-        tmem_ld_wait();
-        if (hp < GF_NHP && !(p.debug & 4)) {
-          const int hy = hp / GF_HW, hx = hp - hy * GF_HW;
-          float* up = Usm + ch0 * GF_CS + hy * GF_RS + hx;
+    int n = 0, ti = 0;
+    if (blockIdx.x < total_tiles) produce_z(blockIdx.x);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const int b = t / tiles_per_img, tr = t - b * tiles_per_img;
+      const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+      const int y0 = ty * GF_TH, x0 = tx * GF_TW;
+      const float* xb = p.x + (size_t)b * p.x_bs;
+      for (int s = 0; s < NS; ++s, ++n) {
+        mbar_wait(&ubar[n & 1], (uint32_t)(n >> 1) & 1);         // GEMM-1(n) done: U[n & 1] ready
+        tc_fence_after();
+        // ---- drain U(n): TMEM -> registers, release the TMEM buffer, then registers -> shared [ch][row][col]
+        {
+          const int q = warp & 3, mt = (warp >> 2) & 1, ch0 = (warp >> 3) * 16;
+          const int hp = mt * 128 + q * 32 + lane;
+          uint32_t r[16];
+          tmem_ld16_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(n & 1) * 64 + mt * 32 + ch0, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dbar[n & 1]);
+          worker_sync();                                           // stencil(n-1) has finished reading Usm
+          if (hp < GF_NHP && !(p.debug & 4)) {
+            const int hy = hp / GF_HW, hx = hp - hy * GF_HW;
+            float* up = Usm + ch0 * GF_CS + hy * GF_RS + hx;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) up[i * GF_CS] = __uint_as_float(r[i]);
-          if (p.save_u && hy >= 1 && hy <= GF_TH && hx >= 1 && hx <= GF_TW) {
-            // channel of row i: a-part (ch0 == 0): s*16 + i ; b-part: hid + s*16 + i
-            float* su = p.save_u + (size_t)b * p.u_bs + (size_t)(y0 + hy - 1) * W + (x0 + hx - 1);
-            const int cbase = s * GF_HS + (ch0 ? hid : 0);
+            for (int i = 0; i < 16; ++i) up[i * GF_CS] = __uint_as_float(r[i]);
+            if (p.save_u && hy >= 1 && hy <= GF_TH && hx >= 1 && hx <= GF_TW) {
+              // channel of row i: a-part (ch0 == 0): s*16 + i ; b-part: hid + s*16 + i
+              float* su = p.save_u + (size_t)b * p.u_bs + (size_t)(y0 + hy - 1) * W + (x0 + hx - 1);
+              const int cbase = s * GF_HS + (ch0 ? hid : 0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (s * GF_HS + i < hid) su[(size_t)(cbase + i) * HWp] = __uint_as_float(r[i]);
+              for (int i = 0; i < 16; ++i)
+                if (s * GF_HS + i < hid) su[(size_t)(cbase + i) * HWp] = __uint_as_float(r[i]);
+            }
           }
         }
+        worker_sync();                                             // Usm complete
+        mbar_wait(&wobar[n & 3], (uint32_t)(n >> 2) & 1);          // depthwise taps of slice n
+        // (g slot n&1 is free: GEMM-2(n-2) was issued before GEMM-1(n), whose completion ubar[n&1] signalled -- MMAs
+        //  retire in issue order, so no separate wait on gbar is needed here)
+        // ---- stencil + gate: warp = pair j of the slice, lane = (row r, 4-pixel strip xq)
+        if (!(p.debug & 2)) {
+          const int j = warp, xq = lane & 3, r = lane >> 2;
+          const float* wdw = reinterpret_cast<const float*>(smem + L::OFF_WO + (n & 3) * L::WO);
+          float wa[9], wb[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            wa[i] = wdw[j * 9 + i];
+            wb[i] = wdw[(16 + j) * 9 + i];
+          }
+          float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* ua = Usm + j * GF_CS + r * GF_RS + 4 * xq;
+          const float* ub = ua + 16 * GF_CS;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const float4 a4 = *reinterpret_cast<const float4*>(ua + dy * GF_RS);
+            const float2 a2 = *reinterpret_cast<const float2*>(ua + dy * GF_RS + 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(ub + dy * GF_RS);
+            const float2 b2 = *reinterpret_cast<const float2*>(ub + dy * GF_RS + 4);
+            const float va[6] = {a4.x, a4.y, a4.z, a4.w, a2.x, a2.y};
+            const float vb[6] = {b4.x, b4.y, b4.z, b4.w, b2.x, b2.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                a[i] = fmaf(wa[dy * 3 + dx], va[i + dx], a[i]);
+                bb[i] = fmaf(wb[dy * 3 + dx], vb[i + dx], bb[i]);
+              }
+          }
+          float g[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) g[i] = gelu_fast(a[i]) * bb[i];
+          uint8_t* gh = smem + L::OFF_G + (n & 1) * 2 * GF_G_TILE + (j >> 3) * 128 + (j & 7) * 2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pr = r * GF_TW + 4 * xq + i;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(g[i]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(g[i] - __bfloat162float(hi));
+            const uint32_t off = (uint32_t)(pr >> 3) * GF_G_SBO + (uint32_t)(pr & 7) * 16;
+            *reinterpret_cast<__nv_bfloat16*>(gh + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(gh + GF_G_TILE + off) = lo;
+          }
+          if (p.save_g && s * GF_HS + j < hid) {
+            float* sg = p.save_g + (size_t)b * p.g_bs + (size_t)(s * GF_HS + j) * HWp + (size_t)(y0 + r) * W + x0 + 4 * xq;
+            *reinterpret_cast<float4*>(sg) = make_float4(g[0], g[1], g[2], g[3]);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sbar[n & 1]);
       }
-      tc_fence_before();
-      __syncthreads();                                           // (B)
-      // ---- stencil + gate: warp = pair j of the slice, lane = (row r, 4-pixel strip xq)
-      if (!(p.debug & 2)) {
-        const int j = warp, xq = lane & 3, r = lane >> 2;
-        const float* wdw = reinterpret_cast<const float*>(smem + L::OFF_WO + (n & 3) * L::WO);
-        float wa[9], wb[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          wa[i] = wdw[j * 9 + i];
-          wb[i] = wdw[(16 + j) * 9 + i];
-        }
-        float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* ua = Usm + j * GF_CS + r * GF_RS + 4 * xq;
-        const float* ub = ua + 16 * GF_CS;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const float4 a4 = *reinterpret_cast<const float4*>(ua + dy * GF_RS);
-          const float2 a2 = *reinterpret_cast<const float2*>(ua + dy * GF_RS + 4);
-          const float4 b4 = *reinterpret_cast<const float4*>(ub + dy * GF_RS);
-          const float2 b2 = *reinterpret_cast<const float2*>(ub + dy * GF_RS + 4);
-          const float va[6] = {a4.x, a4.y, a4.z, a4.w, a2.x, a2.y};
-          const float vb[6] = {b4.x, b4.y, b4.z, b4.w, b2.x, b2.y};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              a[i] = fmaf(wa[dy * 3 + dx], va[i + dx], a[i]);
-              bb[i] = fmaf(wb[dy * 3 + dx], vb[i + dx], bb[i]);
-            }
-        }
-        float g[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) g[i] = gelu_fast(a[i]) * bb[i];
-        uint8_t* gh = smem + L::OFF_G + (n & 1) * 2 * GF_G_TILE + (j >> 3) * 128 + (j & 7) * 2;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pr = r * GF_TW + 4 * xq + i;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(g[i]);
-          const __nv_bfloat16 lo = __float2bfloat16_rn(g[i] - __bfloat162float(hi));
-          const uint32_t off = (uint32_t)(pr >> 3) * GF_G_SBO + (uint32_t)(pr & 7) * 16;
-          *reinterpret_cast<__nv_bfloat16*>(gh + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(gh + GF_G_TILE + off) = lo;
-        }
-        if (p.save_g && s * GF_HS + j < hid) {
-          float* sg = p.save_g + (size_t)b * p.g_bs + (size_t)(s * GF_HS + j) * HWp + (size_t)(y0 + r) * W + x0 + 4 * xq;
-          *reinterpret_cast<float4*>(sg) = make_float4(g[0], g[1], g[2], g[3]);
-        }
-      }
-      fence_async_smem();
-    }
-    // ------------------------------------------------------------ last GEMM-2, then the epilogue
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_gemm2(n - 1, NS == 1);
+      // ---- every GEMM-1 of this tile has completed (its U was drained): Z may be rebuilt for the next tile while
+      //      the tensor pipe finishes GEMM-2 of the last slice
+      if (t + (int)gridDim.x < total_tiles) produce_z(t + gridDim.x);
+      // ---- epilogue: Y (+ x) -> HBM, LayerNorm statistics of y
       mbar_wait(&gbar[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
-    }
-    __syncthreads();
-    tc_fence_after();
-    {
-      const int q = warp & 3, cg = warp >> 2;
-      const int pr = q * 32 + lane, r = pr >> 4, cx = pr & 15;
-      const size_t pix = (size_t)(y0 + r) * W + x0 + cx;
-      const float* xr = xb + pix;
-      float* yo = p.y + (size_t)b * p.y_bs + pix;
-      const bool want_stats = p.stats_out != nullptr;
-      const float shift = want_stats ? __ldg(xr) : 0.f;
-      float s1 = 0.f, s2 = 0.f;
-      for (int gi = cg; gi < C / 8; gi += 4) {
-        uint32_t rr[8];
-        tmem_ld8_nowait(tmem_y + ((uint32_t)(q * 32) << 16) + gi * 8, rr);
-        float res[8];
+      tc_fence_after();
+      {
+        const int q = warp & 3, cg = warp >> 2;
+        const int pr = q * 32 + lane, r = pr >> 4, cx = pr & 15;
+        const size_t pix = (size_t)(y0 + r) * W + x0 + cx;
+        const float* xr = xb + pix;
+        float* yo = p.y + (size_t)b * p.y_bs + pix;
+        const bool want_stats = p.stats_out != nullptr;
+        const float shift = want_stats ? __ldg(xr) : 0.f;
+        float s1 = 0.f, s2 = 0.f;
+        for (int gi = cg; gi < C / 8; gi += 4) {
+          uint32_t rr[8];
+          tmem_ld8_nowait(tmem_y + ((uint32_t)(q * 32) << 16) + gi * 8, rr);
+          float res[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) res[i] = p.residual ? __ldg(xr + (size_t)(gi * 8 + i) * HWp) : 0.f;
-        tmem_ld_wait();
+          for (int i = 0; i < 8; ++i) res[i] = p.residual ? __ldg(xr + (size_t)(gi * 8 + i) * HWp) : 0.f;
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float yv = __uint_as_float(rr[i]) + res[i];
-          yo[(size_t)(gi * 8 + i) * HWp] = yv;
-          const float d = yv - shift;
-          s1 += d;
-          s2 = fmaf(d, d, s2);
+          for (int i = 0; i < 8; ++i) {
+            const float yv = __uint_as_float(rr[i]) + res[i];
+            yo[(size_t)(gi * 8 + i) * HWp] = yv;
+            const float d = yv - shift;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ybar);                         // Y drained: the next tile's GEMM-2 may overwrite it
+        if (want_stats) {
+          stp[(cg * 128 + pr) * 2] = s1;
+          stp[(cg * 128 + pr) * 2 + 1] = s2;
+          worker_sync();
+          if (cg == 0) {
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              t1 += stp[(k * 128 + pr) * 2];
+              t2 += stp[(k * 128 + pr) * 2 + 1];
+            }
+            const float inv = 1.f / (float)C;
+            const float m = t1 * inv;
+            const float var = fmaxf(t2 * inv - m * m, 0.f);
+            reinterpret_cast<float2*>(p.stats_out)[(size_t)b * HWp + pix] = make_float2(shift + m, 1.0f / sqrtf(var + 1e-5f));
+          }
+          // (stp is rewritten by the next tile's epilogue only after 2 * NS worker barriers)
         }
       }
-      if (want_stats) {
-        stp[(cg * 128 + pr) * 2] = s1;
-        stp[(cg * 128 + pr) * 2 + 1] = s2;
-      }
-      tc_fence_before();
-      __syncthreads();
-      if (want_stats && cg == 0) {
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          t1 += stp[(k * 128 + pr) * 2];
-          t2 += stp[(k * 128 + pr) * 2 + 1];
-        }
-        const float inv = 1.f / (float)C;
-        const float m = t1 * inv;
-        const float var = fmaxf(t2 * inv - m * m, 0.f);
-        reinterpret_cast<float2*>(p.stats_out)[(size_t)b * HWp + pix] = make_float2(shift + m, 1.0f / sqrtf(var + 1e-5f));
-      }
     }
-    // the next tile's Z phase ends with a block barrier before any MMA is issued; stp is rewritten only after it
   }
   tc_fence_before();
   __syncthreads();

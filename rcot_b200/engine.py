@@ -22,9 +22,11 @@ from . import ops
 # It moves 13.3 instead of 29.3 C*H*W passes but is issue-bound (8 k warp-instructions per 32x32 tile, measured
 # 1.49 ms vs 1.29 ms for the two kernels at C=96, 128x128, B=32), so the two-kernel form stays the default.
 FUSED_GDFN_MID = os.environ.get("RCOT_FUSED_GDFN_MID", "0") == "1"
-# RCOT_FUSED_GDFN=0 switches the one-kernel GDFN forward (csrc/gdfn_fused.cu; C in {48, 96}, H % 8 == 0, W % 16 == 0)
-# back to the three-launch path (pm_gemm -> dw_gate -> pm_gemm) for A/B measurements.
-FUSED_GDFN = os.environ.get("RCOT_FUSED_GDFN", "1") == "1"
+# RCOT_FUSED_GDFN=1 selects the one-kernel GDFN forward (csrc/gdfn_fused.cu; C in {48, 96}, H % 8 == 0, W % 16 == 0)
+# instead of the three-launch path (pm_gemm -> dw_gate -> pm_gemm).  It is parity-green and moves ~8x fewer DRAM bytes,
+# but it is bound by its per-slice synchronisation and the CUDA-core stencil, not by HBM: measured 1.46 ms vs 0.97 ms
+# for the three launches at C=96, 128x128, B=32 -- so the three-launch path stays the default.
+FUSED_GDFN = os.environ.get("RCOT_FUSED_GDFN", "0") == "1"
 
 
 # ---------------------------------------------------------------------------------- parameters

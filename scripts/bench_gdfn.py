@@ -43,7 +43,9 @@ def main():
         for fused in (True, False):
             ps = engine.ParamSet(dict(sd), "cuda")
             bs = engine.BlockSpec(ps, "b.", C, 1, has_attn=False)
-            if not fused:
+            if fused:
+                ps.add_gdfn("b.", C, hid)
+            else:
                 ps.gdfn.clear()
             ps.finalize()
             for keep in (False, True):

@@ -74,7 +74,9 @@ def test_gdfn_fused_matches_unfused_block_path(cuda_lib):
     for fused in (True, False):
         ps = engine.ParamSet({k: v for k, v in sd.items()}, "cuda")
         bs = engine.BlockSpec(ps, "b.", C, 1, has_attn=False)
-        if not fused:
+        if fused:
+            ps.add_gdfn("b.", C, hid)          # what BlockSpec does under RCOT_FUSED_GDFN=1
+        else:
             ps.gdfn.clear()
         ps.finalize()
         y, kept = engine.gdfn_fwd(bs, x, "b.norm2", True, keep=True)
