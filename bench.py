@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--graph", type=int, default=-1,
                     help="replay each iteration as one CUDA graph: 1 on, 0 off, -1 (default) on when the per-GPU batch <= 8")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the strong-scaling and c2/c4/c5 side measurements")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="storage of the blocks' hidden tensors for the HEADLINE run (bf16: see rcot_b200.set_hidden_dtype)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -245,6 +247,8 @@ def run_b200(args):
     if world > 1:
         torch.distributed.init_process_group("nccl")
     ops.TERMS = args.terms
+    import rcot_b200
+    rcot_b200.set_hidden_dtype(args.dtype)
     B, P, K, W = args.batch, args.patch, args.steps, max(args.warmup, 3)
     args.graph = (B <= 8) if args.graph < 0 else bool(args.graph)
     trainer.opt = trainer.parser.parse_args(["--batchSize", str(B * world), "--patch_size", str(P), "--pairnum", "1000000000",
@@ -412,6 +416,23 @@ def run_b200(args):
                                                     "frac": fwd_bytes / 1e9 / (m5 / 1e3) / peaks()[0], "unit": "GB/s"},
                             "finite": bool(torch.isfinite(y5).all().item())}
             del x5, y5
+            if args.dtype == "fp32":
+                # bf16-storage mode of the hidden tensors (BASELINE config c3 names bf16): the headline step and c3's
+                # per-GPU share (4 images) again, with pre / qkv / u / g and their gradients stored as bf16
+                rcot_b200.set_hidden_dtype("bf16")
+                try:
+                    torch.cuda.reset_peak_memory_stats()
+                    m, gq, fin = side_run(32, True, graph=False)
+                    extras["bf16_storage"] = {"what": "the headline step (batch 32, paired) with bf16-stored hidden tensors "
+                                                      "on the C <= 96 levels; stated tolerance 2e-2 (tests/test_bf16_mode.py)",
+                                              "value": 32 / (m / 1e3), "unit": UNIT, "ms_per_step": m, "finite": fin,
+                                              "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
+                    m, gq, fin = side_run(4, True)
+                    extras["c3"] = {"what": "BASELINE config c3 per-GPU share: 128x128, 4 images per GPU (32 global on 8 "
+                                            "GPUs), paired, bf16-stored hidden tensors", "value": 4 / (m / 1e3), "unit": UNIT,
+                                    "ms_per_step": m, "cuda_graph": gq, "finite": fin}
+                finally:
+                    rcot_b200.set_hidden_dtype("fp32")
 
     barrier()
     if rank != 0:
@@ -420,7 +441,9 @@ def run_b200(args):
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32 storage, bf16x3 split products on tcgen05 (fp32-class)" if args.terms == 3 else "bf16 products, fp32 storage/accumulate",
+            "dtype": (("fp32 storage, bf16x3 split products on tcgen05 (fp32-class)" if args.terms == 3
+                       else "bf16 products, fp32 storage/accumulate") if args.dtype == "fp32" else
+                      "bf16-stored hidden tensors (C <= 96 levels), fp32 block I/O, weights and accumulation; stated tolerance 2e-2"),
             "data": "synthetic",
             "config": make_config(P, B, world, args.graph),
             "clocks": sampler.result(), "gpu_launches": launches,

@@ -91,6 +91,9 @@ typedef struct {
                            the tile's start instead of one tile ahead, bit 1 disables the residual L2 prefetch */
   int32_t tap_major;    /* ks > 1: K is ordered (ky, kx, channel); needs C1 % 16 == 0 and no concat: a producer
                            thread's 16 K indices are 16 channels at ONE tap: a strided read like the 1x1 case */
+  int32_t in_bf16;      /* bf16-storage mode: `in` is a bf16 tensor (1x1, no LayerNorm, no concat, H*W % 128 == 0): the A
+                           operand is exact in bf16, so its lo term and the fp32->bf16 split disappear */
+  int32_t out_bf16;     /* `out` is a bf16 tensor (1x1, plain epilogue: no bias/activation/mask/residual/accumulate/stats) */
 } rcot_pm_params;
 
 int rcot_pm_gemm(const rcot_pm_params* p, rcot_stream_t stream);
@@ -100,7 +103,7 @@ int rcot_pm_gemm(const rcot_pm_params* p, rcot_stream_t stream);
  * Weight gradients of every conv (dW = dOut * im2col(In)^T), and MDTA's per-image Gram
  * q k^T / dy v^T (Net_Restormer.py:42 and its backward). */
 typedef struct {
-  const float* a;       /* [B, CA, Ha*Wa] */
+  const float* a;       /* [B, CA, Ha*Wa] (bf16 when a_bf16) */
   int64_t a_bs;
   int32_t CA;
   const float* b;       /* [B, CB, Hb, Wb] gather source */
@@ -120,6 +123,8 @@ typedef struct {
   int32_t ldo;
   int32_t groups;       /* >1: a channels g*CA.., b channels g*CB1.., out + g*out_gs (MDTA heads) */
   int64_t out_gs;
+  int32_t a_bf16, b_bf16; /* bf16-storage mode: a / b is a bf16 tensor (1x1, aligned shapes with H*W % 32 == 0; b only
+                             without LayerNorm): the operand is exact in bf16, its lo term disappears */
 } rcot_pk_params;
 
 int rcot_pk_gemm(const rcot_pk_params* p, rcot_stream_t stream);
@@ -203,6 +208,8 @@ typedef struct {
   float* g_out;
   int64_t g_bs;
   float* sumsq;
+  int32_t bf16;         /* 1: in / out / dg / g_out are bf16 tensors (bf16-storage mode of the hidden tensors; fp32
+                           arithmetic).  Needs the aligned geometry of training patches (W % 4 == 0, even H). */
 } rcot_dw_params;
 int rcot_dwconv3x3(const rcot_dw_params* p, rcot_stream_t stream);
 /* dw[ch, k] += sum_{b,p} dout[b,ch,p] * in[b,ch,p+off_k] */
@@ -212,6 +219,10 @@ int rcot_dwconv3x3_wgrad(const float* in, int64_t in_bs, const float* dout, int6
 /* both halves of the depthwise backward in one pass: din = dw^T(dout), dw += corr(in, dout) */
 int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w, float* din,
                        int64_t din_bs, float* dw, int B, int Cn, int H, int W, rcot_stream_t stream);
+
+/* same, with in / dout / din stored as bf16 when bf16 != 0 (dw stays fp32) */
+int rcot_dwconv3x3_bwd_t(const void* in, int64_t in_bs, const void* dout, int64_t dout_bs, const float* w, void* din,
+                         int64_t din_bs, float* dw, int B, int Cn, int H, int W, int bf16, rcot_stream_t stream);
 
 /* GDFN middle backward in one pass (Net_Restormer.py:81-83 backward): with a = dw(u[j]),
  * b = dw(u[j+hid]): da = dg*b*gelu'(a), db = dg*gelu(a); du = dw^T([da; db]); dw += corr(u, [da; db]);

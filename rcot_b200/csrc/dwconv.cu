@@ -11,28 +11,50 @@
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
 #include "gelu.cuh"
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 namespace rcot {
+
+// Element access for the two storage types of the hidden tensors: fp32, or bf16 in the bf16-storage mode (arithmetic
+// is fp32 either way).  4-element row segments are one 16-byte resp. 8-byte access.
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld1(const __nv_bfloat16* p) {
+  return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+// the value a store of v will leave in memory (so that sums of squares match what later kernels read)
+__device__ __forceinline__ float stored(const float*, float v) { return v; }
+__device__ __forceinline__ float stored(const __nv_bfloat16*, float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 template <int ROWS>
 struct Patch {
   float v[ROWS + 2][6];  // rows y-1 .. y+ROWS, columns x0-1 .. x0+4
 };
 
-template <int ROWS>
-__device__ __forceinline__ void load_patch(Patch<ROWS>& P, const float* __restrict__ plane, int y, int x0, int H, int W) {
-  const float* p = plane + (y - 1) * W + x0;
+template <int ROWS, typename T>
+__device__ __forceinline__ void load_patch(Patch<ROWS>& P, const T* __restrict__ plane, int y, int x0, int H, int W) {
+  const T* p = plane + (y - 1) * W + x0;
   if (y > 0 && y + ROWS < H && x0 > 0 && x0 + 4 < W) {   // interior: no predicates
 #pragma unroll
     for (int r = 0; r < ROWS + 2; ++r) {
-      const float4 m = __ldg(reinterpret_cast<const float4*>(p + r * W));
-      P.v[r][0] = __ldg(p + r * W - 1);
+      const float4 m = ld4(p + r * W);
+      P.v[r][0] = ld1(p + r * W - 1);
       P.v[r][1] = m.x;
       P.v[r][2] = m.y;
       P.v[r][3] = m.z;
       P.v[r][4] = m.w;
-      P.v[r][5] = __ldg(p + r * W + 4);
+      P.v[r][5] = ld1(p + r * W + 4);
     }
     return;
   }
@@ -40,13 +62,13 @@ __device__ __forceinline__ void load_patch(Patch<ROWS>& P, const float* __restri
   for (int r = 0; r < ROWS + 2; ++r) {
     const int yy = y - 1 + r;
     if ((unsigned)yy < (unsigned)H) {
-      const float4 m = __ldg(reinterpret_cast<const float4*>(p + r * W));
-      P.v[r][0] = x0 > 0 ? __ldg(p + r * W - 1) : 0.f;
+      const float4 m = ld4(p + r * W);
+      P.v[r][0] = x0 > 0 ? ld1(p + r * W - 1) : 0.f;
       P.v[r][1] = m.x;
       P.v[r][2] = m.y;
       P.v[r][3] = m.z;
       P.v[r][4] = m.w;
-      P.v[r][5] = x0 + 4 < W ? __ldg(p + r * W + 4) : 0.f;
+      P.v[r][5] = x0 + 4 < W ? ld1(p + r * W + 4) : 0.f;
     } else {
 #pragma unroll
       for (int i = 0; i < 6; ++i) P.v[r][i] = 0.f;
@@ -107,9 +129,9 @@ __device__ __forceinline__ float warp_sum_dw(float v) {
 }
 
 // ------------------------------------------------------------------ plain / transposed
-template <int ROWS>
+template <int ROWS, typename T>
 __global__ void __launch_bounds__(256)
-    dw_plain_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ w, float* __restrict__ out,
+    dw_plain_kernel(const T* __restrict__ in, int64_t in_bs, const float* __restrict__ w, T* __restrict__ out,
                     int64_t out_bs, int flip, float* __restrict__ sumsq, int nsq, const DwGeom g) {
   const DwThread t = dw_map(g, ROWS);
   const int HW = g.H * g.W;
@@ -122,12 +144,15 @@ __global__ void __launch_bounds__(256)
     Patch<ROWS> P;
     load_patch<ROWS>(P, in + (size_t)t.b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
     conv_patch<ROWS>(P, wk, o);
-    float* op = out + (size_t)t.b * out_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
+    T* op = out + (size_t)t.b * out_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      *reinterpret_cast<float4*>(op + r * g.W) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
+      st4(op + r * g.W, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sq = fmaf(o[r][j], o[r][j], sq);
+      for (int j = 0; j < 4; ++j) {
+        const float v = stored(op, o[r][j]);
+        sq = fmaf(v, v, sq);
+      }
     }
   }
   if (sumsq) {   // uniform
@@ -144,10 +169,10 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------ GELU gate: forward / backward
 // mode 1: out[j] = gelu(dw(in[j])) * dw(in[j+hid])
 // mode 2: a = dw(in[j]), b = dw(in[j+hid]); out[j] = dg*b*gelu'(a); out[j+hid] = dg*gelu(a); g_out[j] = gelu(a)*b
-template <int MODE, int ROWS>
+template <int MODE, int ROWS, typename T>
 __global__ void __launch_bounds__(256)
-    dw_gate_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ w, float* __restrict__ out,
-                   int64_t out_bs, int hid, const float* __restrict__ dg, int64_t dg_bs, float* __restrict__ g_out,
+    dw_gate_kernel(const T* __restrict__ in, int64_t in_bs, const float* __restrict__ w, T* __restrict__ out,
+                   int64_t out_bs, int hid, const T* __restrict__ dg, int64_t dg_bs, T* __restrict__ g_out,
                    int64_t g_bs, const DwGeom g) {
   const DwThread t = dw_map(g, ROWS);
   if (!t.active) return;
@@ -158,7 +183,7 @@ __global__ void __launch_bounds__(256)
     w0[i] = __ldg(w + t.ch * 9 + i);
     w1[i] = __ldg(w + (t.ch + hid) * 9 + i);
   }
-  const float* inb = in + (size_t)t.b * in_bs;
+  const T* inb = in + (size_t)t.b * in_bs;
   float a[ROWS][4], gt[ROWS][4];
   {
     Patch<ROWS> P;
@@ -175,11 +200,11 @@ __global__ void __launch_bounds__(256)
   for (int r = 0; r < ROWS; ++r) {
     const int pr = pix + r * g.W;
     if (MODE == 1) {
-      *reinterpret_cast<float4*>(out + (size_t)t.b * out_bs + (size_t)t.ch * HW + pr) =
+      st4(out + (size_t)t.b * out_bs + (size_t)t.ch * HW + pr,
           make_float4(gelu_fast(a[r][0]) * gt[r][0], gelu_fast(a[r][1]) * gt[r][1], gelu_fast(a[r][2]) * gt[r][2],
-                      gelu_fast(a[r][3]) * gt[r][3]);
+                      gelu_fast(a[r][3]) * gt[r][3]));
     } else {
-      const float4 d4 = __ldg(reinterpret_cast<const float4*>(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pr));
+      const float4 d4 = ld4(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pr);
       const float d[4] = {d4.x, d4.y, d4.z, d4.w};
       float da[4], db[4], gg[4];
 #pragma unroll
@@ -190,21 +215,19 @@ __global__ void __launch_bounds__(256)
         db[j] = d[j] * ga;
         gg[j] = ga * gt[r][j];
       }
-      float* ob = out + (size_t)t.b * out_bs;
-      *reinterpret_cast<float4*>(ob + (size_t)t.ch * HW + pr) = make_float4(da[0], da[1], da[2], da[3]);
-      *reinterpret_cast<float4*>(ob + (size_t)(t.ch + hid) * HW + pr) = make_float4(db[0], db[1], db[2], db[3]);
-      if (g_out)
-        *reinterpret_cast<float4*>(g_out + (size_t)t.b * g_bs + (size_t)t.ch * HW + pr) =
-            make_float4(gg[0], gg[1], gg[2], gg[3]);
+      T* ob = out + (size_t)t.b * out_bs;
+      st4(ob + (size_t)t.ch * HW + pr, make_float4(da[0], da[1], da[2], da[3]));
+      st4(ob + (size_t)(t.ch + hid) * HW + pr, make_float4(db[0], db[1], db[2], db[3]));
+      if (g_out) st4(g_out + (size_t)t.b * g_bs + (size_t)t.ch * HW + pr, make_float4(gg[0], gg[1], gg[2], gg[3]));
     }
   }
 }
 
 // ------------------------------------------------------------------ fused backward: din and dW
-template <int ROWS>
+template <int ROWS, typename T>
 __global__ void __launch_bounds__(256)
-    dw_bwd2_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ dout, int64_t dout_bs,
-                   const float* __restrict__ w, float* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
+    dw_bwd2_kernel(const T* __restrict__ in, int64_t in_bs, const T* __restrict__ dout, int64_t dout_bs,
+                   const float* __restrict__ w, T* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
                    const DwGeom g, const int ppt, const int ipc, const int B) {
   DwThread t = dw_map(g, ROWS);
   const int HW = g.H * g.W;
@@ -235,10 +258,10 @@ __global__ void __launch_bounds__(256)
       load_patch<ROWS>(P, dout + (size_t)b * dout_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
       float o[ROWS][4];
       conv_patch<ROWS>(P, wf, o);
-      float* dp = din + (size_t)b * din_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
+      T* dp = din + (size_t)b * din_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) {
-        *reinterpret_cast<float4*>(dp + r * g.W) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
+        st4(dp + r * g.W, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
 #pragma unroll
         for (int j = 0; j < 4; ++j) d[r][j] = P.v[r + 1][j + 1];   // centre rows of dout
       }
@@ -524,19 +547,23 @@ static bool dw_geom(DwGeom& g, dim3& grid, int B, int planes, int H, int W, int 
   return true;
 }
 
-// Returns 1 if the aligned fast path handled the call, 0 if the caller must use the generic kernels.
-int dwconv_fast(const rcot_dw_params& p, int planes, cudaStream_t st) {
+template <typename T>
+static int dwconv_fast_t(const rcot_dw_params& p, int planes, cudaStream_t st) {
   const bool al = p.in_bs % 4 == 0 && p.out_bs % 4 == 0 && ((uintptr_t)p.in % 16 == 0) && ((uintptr_t)p.out % 16 == 0);
   if (!al) return 0;
+  const T* in = reinterpret_cast<const T*>(p.in);
+  T* out = reinterpret_cast<T*>(p.out);
+  const T* dg = reinterpret_cast<const T*>(p.dg);
+  T* g_out = reinterpret_cast<T*>(p.g_out);
   DwGeom g;
   dim3 grid;
   if (p.mode == 0) {
     if (dw_geom(g, grid, p.B, planes, p.H, p.W, 4)) {
-      dw_plain_kernel<4><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.flip, p.sumsq, p.nsq, g);
+      dw_plain_kernel<4, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.flip, p.sumsq, p.nsq, g);
       return 1;
     }
     if (dw_geom(g, grid, p.B, planes, p.H, p.W, 2)) {
-      dw_plain_kernel<2><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.flip, p.sumsq, p.nsq, g);
+      dw_plain_kernel<2, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.flip, p.sumsq, p.nsq, g);
       return 1;
     }
     return 0;
@@ -549,23 +576,27 @@ int dwconv_fast(const rcot_dw_params& p, int planes, cudaStream_t st) {
   if (rows == 2 && !dw_geom(g, grid, p.B, planes, p.H, p.W, 2)) return 0;
   if (p.mode == 1) {
     if (rows == 4)
-      dw_gate_kernel<1, 4><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
+      dw_gate_kernel<1, 4, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
     else
-      dw_gate_kernel<1, 2><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
+      dw_gate_kernel<1, 2, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
   } else {
     if (p.dg_bs % 4 != 0 || (p.g_out && p.g_bs % 4 != 0)) return 0;
     if (rows == 4)
-      dw_gate_kernel<2, 4><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, p.dg, p.dg_bs, p.g_out,
-                                                 p.g_bs, g);
+      dw_gate_kernel<2, 4, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, dg, p.dg_bs, g_out, p.g_bs, g);
     else
-      dw_gate_kernel<2, 2><<<grid, 256, 0, st>>>(p.in, p.in_bs, p.w, p.out, p.out_bs, p.hid, p.dg, p.dg_bs, p.g_out,
-                                                 p.g_bs, g);
+      dw_gate_kernel<2, 2, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, dg, p.dg_bs, g_out, p.g_bs, g);
   }
   return 1;
 }
 
-int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w, float* din,
-                    int64_t din_bs, float* dw, int B, int Cn, int H, int W, cudaStream_t st) {
+// Returns 1 if the aligned fast path handled the call, 0 if the caller must use the generic kernels.
+int dwconv_fast(const rcot_dw_params& p, int planes, cudaStream_t st) {
+  return p.bf16 ? dwconv_fast_t<__nv_bfloat16>(p, planes, st) : dwconv_fast_t<float>(p, planes, st);
+}
+
+template <typename T>
+static int dwconv_bwd_fast_t(const T* in, int64_t in_bs, const T* dout, int64_t dout_bs, const float* w, T* din,
+                             int64_t din_bs, float* dw, int B, int Cn, int H, int W, cudaStream_t st) {
   DwGeom g;
   dim3 grid;
   const int want = dw_rows_forced() ? dw_rows_forced() : 4;   // 4x4 patches: 669 vs 755 us at C=96, 128x128, B=32
@@ -582,10 +613,20 @@ int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t d
   while (ppt == 1 && ipc < 4 && (long)grid.x * grid.y * cdiv(B, ipc * 2) >= 8 * 148) ipc *= 2;
   grid.z = cdiv(B, ipc);
   if (rows == 4)
-    dw_bwd2_kernel<4><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
+    dw_bwd2_kernel<4, T><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
   else
-    dw_bwd2_kernel<2><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
+    dw_bwd2_kernel<2, T><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
   return 1;
+}
+
+int dwconv_bwd_fast(const void* in, int64_t in_bs, const void* dout, int64_t dout_bs, const float* w, void* din,
+                    int64_t din_bs, float* dw, int B, int Cn, int H, int W, int bf16, cudaStream_t st) {
+  if (bf16)
+    return dwconv_bwd_fast_t<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(in), in_bs,
+                                            reinterpret_cast<const __nv_bfloat16*>(dout), dout_bs, w,
+                                            reinterpret_cast<__nv_bfloat16*>(din), din_bs, dw, B, Cn, H, W, st);
+  return dwconv_bwd_fast_t<float>(reinterpret_cast<const float*>(in), in_bs, reinterpret_cast<const float*>(dout), dout_bs,
+                                  w, reinterpret_cast<float*>(din), din_bs, dw, B, Cn, H, W, st);
 }
 
 }  // namespace rcot

@@ -553,8 +553,8 @@ int dwconv_fast(const rcot_dw_params& p, int planes, cudaStream_t st);
 int gdfn_mid_bwd_fast(const float* u, int64_t u_bs, const float* dg, int64_t dg_bs, const float* w, float* du,
                       int64_t du_bs, float* dw, float* g_out, int64_t g_bs, int B, int hid, int H, int W,
                       cudaStream_t st);
-int dwconv_bwd_fast(const float* in, int64_t in_bs, const float* dout, int64_t dout_bs, const float* w, float* din,
-                    int64_t din_bs, float* dw, int B, int Cn, int H, int W, cudaStream_t st);
+int dwconv_bwd_fast(const void* in, int64_t in_bs, const void* dout, int64_t dout_bs, const float* w, void* din,
+                    int64_t din_bs, float* dw, int B, int Cn, int H, int W, int bf16, cudaStream_t st);
 }  // namespace rcot
 
 using namespace rcot;
@@ -614,6 +614,8 @@ extern "C" int rcot_dwconv3x3(const rcot_dw_params* pp, rcot_stream_t st) {
     planes = p.hid;
   }
   if (dwconv_fast(p, planes, (cudaStream_t)st)) return check_launch("dwconv3x3");
+  RCOT_REQUIRE(!p.bf16, "dwconv3x3: bf16 storage needs the aligned fast path (W %% 4 == 0, H even, 16-byte aligned; got %dx%d)",
+               p.H, p.W);
   if (p.W % 4 != 0 || p.H % 2 != 0) {
     RCOT_REQUIRE(p.mode != 2, "dwconv3x3: gate backward needs width %% 4 == 0 and even height, got %dx%d", p.H, p.W);
     const long tot = (long)p.B * planes * p.H * p.W;
@@ -648,7 +650,7 @@ extern "C" int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* d
                "dwconv3x3_bwd: bad arguments");
   RCOT_REQUIRE(W % 4 == 0 && H % 2 == 0 && in_bs % 4 == 0 && dout_bs % 4 == 0 && din_bs % 4 == 0,
                "dwconv3x3_bwd: width/strides must be multiples of 4 and height even");
-  if (dwconv_bwd_fast(in, in_bs, dout, dout_bs, w, din, din_bs, dw, B, Cn, H, W, (cudaStream_t)st))
+  if (dwconv_bwd_fast(in, in_bs, dout, dout_bs, w, din, din_bs, dw, B, Cn, H, W, 0, (cudaStream_t)st))
     return check_launch("dwconv3x3_bwd");
   long total = (long)B * H * W / 8;
   // enough CTAs per channel to fill the machine, at least ~4 quads per thread
@@ -658,6 +660,21 @@ extern "C" int rcot_dwconv3x3_bwd(const float* in, int64_t in_bs, const float* d
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, Cn);
   dw_bwd_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, B, H, W);
+  return check_launch("dwconv3x3_bwd");
+}
+
+extern "C" int rcot_dwconv3x3_bwd_t(const void* in, int64_t in_bs, const void* dout, int64_t dout_bs, const float* w,
+                                    void* din, int64_t din_bs, float* dw, int B, int Cn, int H, int W, int bf16,
+                                    rcot_stream_t st) {
+  if (!bf16)
+    return rcot_dwconv3x3_bwd(reinterpret_cast<const float*>(in), in_bs, reinterpret_cast<const float*>(dout), dout_bs, w,
+                              reinterpret_cast<float*>(din), din_bs, dw, B, Cn, H, W, st);
+  RCOT_REQUIRE(in && dout && w && din && dw && B > 0 && Cn > 0 && Cn <= 65535 && H > 0 && W > 0,
+               "dwconv3x3_bwd: bad arguments");
+  RCOT_REQUIRE(W % 4 == 0 && H % 2 == 0 && in_bs % 4 == 0 && dout_bs % 4 == 0 && din_bs % 4 == 0,
+               "dwconv3x3_bwd: width/strides must be multiples of 4 and height even");
+  RCOT_REQUIRE(dwconv_bwd_fast(in, in_bs, dout, dout_bs, w, din, din_bs, dw, B, Cn, H, W, 1, (cudaStream_t)st) == 1,
+               "dwconv3x3_bwd: bf16 storage needs the aligned fast path");
   return check_launch("dwconv3x3_bwd");
 }
 

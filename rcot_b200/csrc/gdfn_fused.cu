@@ -27,14 +27,15 @@ constexpr int GF_TH = 8, GF_TW = 16;                 // core tile (pixels)
 constexpr int GF_HH = GF_TH + 2, GF_HW = GF_TW + 2;  // halo tile
 constexpr int GF_NHP = GF_HH * GF_HW;                // 180 halo pixels
 constexpr int GF_RS = 20;                            // shared-memory row stride of a halo row (floats)
-constexpr int GF_CS = 208;                           // channel stride (floats) >= 10 * 20
+constexpr int GF_CS = 228;                           // channel stride (floats) >= 10 * 20 and == 4 (mod 32): the 8 pairs a
+                                                     // quarter-warp reads in one 16-byte access fall into 8 distinct bank groups
 constexpr int GF_HS = 16;                            // (a, b) pairs per hidden slice
 constexpr int GF_WORKER_WARPS = 16;                  // drain / stencil / epilogue warps
 constexpr int GF_THREADS = (GF_WORKER_WARPS + 1) * 32;   // + the issuer warp (TMA weight ring, every tcgen05.mma)
 constexpr int GF_WIN_SLOTS = 3;                      // W_in slice ring
 constexpr uint32_t GF_G_SBO = 272;                   // g operand: 8-row group stride (256 + 16 B pad against bank conflicts)
 constexpr uint32_t GF_G_TILE = 16 * GF_G_SBO;        // one term of the [128 x 16] g operand
-constexpr uint32_t GF_DW_BYTES = 32 * 9 * sizeof(float);
+constexpr uint32_t GF_DW_BYTES = 16 * 20 * sizeof(float);   // per pair: 9 a-taps, 9 b-taps, 2 pad (16-byte loads)
 
 template <int C>
 struct GfLayout {
@@ -59,6 +60,14 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
+}
+
+// 16-byte shared-memory load the compiler may not narrow (a quarter-warp phase of 8 lanes is conflict-free here; the
+// 8-byte form's half-warp phase is not).
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
 }
 
 // Named barrier among the 16 worker warps only (the issuer warp never joins it).
@@ -166,13 +175,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
       mbar_wait(&zbar, (uint32_t)ti & 1);                          // Z of this tile is in shared memory
       for (int s = 0; s < NS; ++s, ++n) {
         // ---- GEMM-1(n): needs W_in(n) and the U buffer n&1 drained (slice n-2)
-        mbar_wait(&winbar[n % GF_WIN_SLOTS], (uint32_t)(n / GF_WIN_SLOTS) & 1);
+        if (!(p.debug & 8) || n < 2) mbar_wait(&winbar[n % GF_WIN_SLOTS], (uint32_t)(n / GF_WIN_SLOTS) & 1);
         if (n >= 2) mbar_wait(&dbar[n & 1], (uint32_t)((n - 2) >> 1) & 1);
         tc_fence_after();
         if (lane == 0) issue_gemm1(n);
         __syncwarp();
         // ---- weight prefetch for slice n+2: W_in slot of slice n-1 (GEMM-1(n-1) done), W_out slot of slice n-2
-        if (n + 2 < total_slices) {
+        if (n + 2 < total_slices && !(p.debug & 8)) {
           if (n >= 1) mbar_wait(&ubar[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
           if (n >= 2) mbar_wait(&gbar[n & 1], (uint32_t)((n - 2) >> 1) & 1);
           if (lane == 0) load_slice(n + 2);
@@ -285,28 +294,31 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
           }
         }
         worker_sync();                                             // Usm complete
-        mbar_wait(&wobar[n & 3], (uint32_t)(n >> 2) & 1);          // depthwise taps of slice n
+        if (!(p.debug & 8) || n < 2) mbar_wait(&wobar[n & 3], (uint32_t)(n >> 2) & 1);   // depthwise taps of slice n
         // (g slot n&1 is free: GEMM-2(n-2) was issued before GEMM-1(n), whose completion ubar[n&1] signalled -- MMAs
         //  retire in issue order, so no separate wait on gbar is needed here)
-        // ---- stencil + gate: warp = pair j of the slice, lane = (row r, 4-pixel strip xq)
+        // ---- stencil + gate.  warp = (core row r, pair half jh); lane = (pair jj of the half, 4-pixel strip xq):
+        //      a quarter-warp reads 8 different channels at one strip (conflict-free 16-byte accesses, GF_CS) and the
+        //      8 pairs of a lane group are the 8 contiguous k values of one operand row (conflict-free 2-byte stores)
         if (!(p.debug & 2)) {
-          const int j = warp, xq = lane & 3, r = lane >> 2;
+          const int r = warp >> 1, j = (warp & 1) * 8 + (lane & 7), xq = lane >> 3;
           const float* wdw = reinterpret_cast<const float*>(smem + L::OFF_WO + (n & 3) * L::WO);
-          float wa[9], wb[9];
+          float wv[20];                    // taps of the pair: a0..a8, b0..b8 (+2 pad) as five 16-byte loads
 #pragma unroll
-          for (int i = 0; i < 9; ++i) {
-            wa[i] = wdw[j * 9 + i];
-            wb[i] = wdw[(16 + j) * 9 + i];
+          for (int i = 0; i < 5; ++i) {
+            const float4 t4 = lds128(wdw + j * 20 + 4 * i);
+            wv[4 * i] = t4.x; wv[4 * i + 1] = t4.y; wv[4 * i + 2] = t4.z; wv[4 * i + 3] = t4.w;
           }
+          const float* wa = wv;
+          const float* wb = wv + 9;
           float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
           const float* ua = Usm + j * GF_CS + r * GF_RS + 4 * xq;
           const float* ub = ua + 16 * GF_CS;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
-            const float4 a4 = *reinterpret_cast<const float4*>(ua + dy * GF_RS);
-            const float2 a2 = *reinterpret_cast<const float2*>(ua + dy * GF_RS + 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(ub + dy * GF_RS);
-            const float2 b2 = *reinterpret_cast<const float2*>(ub + dy * GF_RS + 4);
+            // columns 4xq .. 4xq+7 of the halo row (6 are used; the row stride of 20 keeps the second access in the row)
+            const float4 a4 = lds128(ua + dy * GF_RS), a2 = lds128(ua + dy * GF_RS + 4);
+            const float4 b4 = lds128(ub + dy * GF_RS), b2 = lds128(ub + dy * GF_RS + 4);
             const float va[6] = {a4.x, a4.y, a4.z, a4.w, a2.x, a2.y};
             const float vb[6] = {b4.x, b4.y, b4.z, b4.w, b2.x, b2.y};
 #pragma unroll
@@ -419,10 +431,12 @@ __global__ void gdfn_pack_kernel(const float* __restrict__ w_in, const float* __
     *reinterpret_cast<__nv_bfloat16*>(dst + 4 * L::SBOZ + off) = lo;
   }
   float* dw = reinterpret_cast<float*>(dst + L::WIN);
-  for (int e = threadIdx.x; e < 32 * 9; e += blockDim.x) {
-    const int i = e / 9, tp = e - i * 9;
-    const int pair = s * GF_HS + (i & 15);
-    dw[e] = (pair < hid) ? w_dw[(size_t)((i < 16) ? pair : hid + pair) * 9 + tp] : 0.f;
+  for (int e = threadIdx.x; e < 16 * 20; e += blockDim.x) {
+    const int jp = e / 20, tp = e - jp * 20;           // pair of the slice, slot: 0..8 a-taps, 9..17 b-taps, 18..19 pad
+    const int pair = s * GF_HS + jp;
+    float w = 0.f;
+    if (pair < hid && tp < 18) w = w_dw[(size_t)(tp < 9 ? pair : hid + pair) * 9 + (tp < 9 ? tp : tp - 9)];
+    dw[e] = w;
   }
   uint8_t* wo = dst + L::WIN + GF_DW_BYTES;
   for (int e = threadIdx.x; e < C * 16; e += blockDim.x) {

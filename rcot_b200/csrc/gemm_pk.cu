@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
 // each operand row is stored and immediately refilled with the next chunk's loads, so global latency hides behind
 // the rest of the chunk.  Rows beyond CA / columns beyond N are simply never written or read back (an accumulator
 // element depends on one A row and one B row only).
-template <int TERMS, int MT, int NBT>
+template <int TERMS, int MT, int NBT, int ABF = 0>
 __global__ void __launch_bounds__(PK_THREADS, 1)
     pk_mm_kernel(const rcot_pk_params p, const int BN, const int nt, const int cpi, const int per_cta,
                  const int total_chunks, const int stages, const uint32_t tmem_cols) {
@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
   const int HW = p.Ha * p.Wa;
   const int Ntot = p.CB1;
   const uint32_t a_tile = op_tile_bytes(128), b_tile = op_tile_bytes(BN);
-  const uint32_t stage_bytes = TA * (MT * a_tile + b_tile);
+  constexpr int TAA = ABF ? 1 : TA;           // a bf16-stored A operand is exact: no lo image
+  const uint32_t stage_bytes = TAA * MT * a_tile + TA * b_tile;
   int mt_valid = (p.CA - m0 + 127) >> 7;      // A tiles of this CTA that hold at least one row
   if (mt_valid > MT) mt_valid = MT;
 
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
     // Loads are unconditional (rows beyond CA / N are clamped to the last valid row and the walker stops at the
     // CTA's last chunk): a load whose result is merged under a predicate makes the compiler wait for it right
     // away, which exposes the full global latency every chunk (measured: 80 % long-scoreboard stalls).
-    const float* a_ptr[MT];
+    const float* a_ptr[MT];                  // element offsets are the same for a bf16 A: indexed as 2-byte below
     bool a_ok[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
@@ -387,6 +388,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       a_ok[m] = row < p.CA;
       a_ptr[m] = p.a + (size_t)(a_ok[m] ? row : p.CA - 1) * HW + k8 * 8;
     }
+    const __nv_bfloat16* a16 = reinterpret_cast<const __nv_bfloat16*>(p.a);
+    auto ld8a = [&](uint4& v16, float* v, const float* src) {
+      if (ABF) v16 = __ldg(reinterpret_cast<const uint4*>(a16 + (src - p.a)));   // 8 pixels = 16 bytes, already the operand
+      else {
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+        v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      }
+    };
+    uint4 ra16[MT];
     bool b_ok[NBT];
     const float* b_ptr[NBT];
     float ga[NBT], be[NBT];
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
     {
       const size_t ao = (size_t)nb * p.a_bs + nq0, bo = (size_t)nb * p.b_bs + nq0;
 #pragma unroll
-      for (int m = 0; m < MT; ++m) ld8(ra[m], a_ptr[m] + ao);
+      for (int m = 0; m < MT; ++m) ld8a(ra16[m], ra[m], a_ptr[m] + ao);
 #pragma unroll
       for (int j = 0; j < NBT; ++j) ld8(rb[j], b_ptr[j] + bo);
     }
@@ -432,8 +443,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       uint8_t* stg = smem + (size_t)s * stage_bytes;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        if (a_ok[m]) op_store8<TERMS>(stg + m * a_tile, stg + (MT + m) * a_tile, r0, k8, ra[m]);
-        ld8(ra[m], a_ptr[m] + ao);
+        if (a_ok[m]) {
+          if (ABF) {
+            const uint32_t pk4[4] = {ra16[m].x, ra16[m].y, ra16[m].z, ra16[m].w};
+            op_store8_bf16(stg + m * a_tile, r0, k8, pk4);
+          } else {
+            op_store8<TERMS>(stg + m * a_tile, stg + (MT + m) * a_tile, r0, k8, ra[m]);
+          }
+        }
+        ld8a(ra16[m], ra[m], a_ptr[m] + ao);
       }
       const float2 stc = st;                      // statistics of pixel q0 + lane of THIS chunk
       st = __ldg(stats + (size_t)nb * HW + nq0 + lane);   // (requesting these earlier in the iteration measured slower)
@@ -444,7 +462,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < NBT; ++j) rb[j][i] = fmaf((rb[j][i] - mu) * rv, ga[j], be[j]);
       }
-      uint8_t* b_hi = stg + TA * MT * a_tile;
+      uint8_t* b_hi = stg + TAA * MT * a_tile;
 #pragma unroll
       for (int j = 0; j < NBT; ++j) {
         if (b_ok[j]) op_store8<TERMS>(b_hi, b_hi + b_tile, r0 + 128 * j, k8, rb[j]);
@@ -468,12 +486,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       tc_fence_after();
       if (lane == 0) {
         const uint32_t stg = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_hi = stg + TA * MT * a_tile;
+        const uint32_t b_hi = stg + TAA * MT * a_tile;
 #pragma unroll
         for (int m = 0; m < MT; ++m)
           if (m < mt_valid)
-            issue_stage<TERMS>(tmem + m * BN, stg + m * a_tile, stg + (MT + m) * a_tile, b_hi, b_hi + b_tile, idesc,
-                               it == 0);
+            issue_stage<TERMS, !ABF>(tmem + m * BN, stg + m * a_tile, stg + (MT + m) * a_tile, b_hi, b_hi + b_tile, idesc,
+                                     it == 0);
         tc_commit(&empty_bar[s]);
       }
       __syncwarp();
@@ -523,8 +541,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
-template <int TERMS, int MT, int NBT>
-static int launch_pk_mm(const rcot_pk_params& p, int BN, cudaStream_t stream) {
+template <int TERMS, int MT, int NBT, int ABF = 0>
+static int launch_pk_mm_t(const rcot_pk_params& p, int BN, cudaStream_t stream) {
   const int Ntot = p.CB1;
   const int HW = p.Ha * p.Wa;
   const int nt = cdiv(Ntot, BN), mgroups = cdiv(p.CA, 128 * MT);
@@ -539,14 +557,15 @@ static int launch_pk_mm(const rcot_pk_params& p, int BN, cudaStream_t stream) {
   int per_cta = cdiv(total_chunks, S);
   S = cdiv(total_chunks, per_cta);
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const size_t stage_bytes = (size_t)TA * (MT * (size_t)op_tile_bytes(128) + (size_t)op_tile_bytes(BN));
+  constexpr int TAA = ABF ? 1 : TA;
+  const size_t stage_bytes = (size_t)TAA * MT * (size_t)op_tile_bytes(128) + (size_t)TA * (size_t)op_tile_bytes(BN);
   int stages = (int)((196 * 1024) / stage_bytes);
   if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
   RCOT_REQUIRE(stages >= 2, "pk_gemm(mm): stage of %zu bytes does not fit twice", stage_bytes);
   const size_t smem = stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pk_mm_kernel<TERMS, MT, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(pk_mm_kernel<TERMS, MT, NBT, ABF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          196 * 1024);
     if (e != cudaSuccess) {
       set_error("pk_gemm(mm): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -556,9 +575,13 @@ static int launch_pk_mm(const rcot_pk_params& p, int BN, cudaStream_t stream) {
   }
   RCOT_REQUIRE(S <= 65535, "pk_gemm(mm): grid too large");
   dim3 grid(mgroups * nt, S, 1);
-  pk_mm_kernel<TERMS, MT, NBT><<<grid, PK_THREADS, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks, stages,
-                                                                  tmem_cols_pow2(MT * BN));
+  pk_mm_kernel<TERMS, MT, NBT, ABF><<<grid, PK_THREADS, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks, stages,
+                                                                       tmem_cols_pow2(MT * BN));
   return check_launch("pk_gemm(mm)");
+}
+template <int TERMS, int MT, int NBT>
+static int launch_pk_mm(const rcot_pk_params& p, int BN, cudaStream_t stream) {
+  return p.a_bf16 ? launch_pk_mm_t<TERMS, MT, NBT, 1>(p, BN, stream) : launch_pk_mm_t<TERMS, MT, NBT, 0>(p, BN, stream);
 }
 
 // Picks (MT, NBT) for the multi-M kernel; returns -100 when the call does not qualify.
@@ -588,7 +611,7 @@ static int try_pk_mm(const rcot_pk_params& p, cudaStream_t stream) {
 // producers keep ~40 KB in flight per SM (3.1-3.4 TB/s measured); the ring holds PK_RAW chunks.
 constexpr int PK_RAW_MAX = 4;
 
-template <int TERMS>
+template <int TERMS, int ABF = 0, int BBF = 0>
 __global__ void __launch_bounds__(PK_THREADS + 32, 1)
     pk_tma_kernel(const rcot_pk_params p, const int BN, const int nt, const int cpi, const int per_cta,
                   const int total_chunks, const int stages, const int nraw, const uint32_t tmem_cols, const int tr,
@@ -606,9 +629,11 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
   const int HW = p.Ha * p.Wa;
   const int Ntot = p.CB1;
   const uint32_t a_tile = op_tile_bytes(128), b_tile = op_tile_bytes(BN);
-  const uint32_t stage_bytes = TA * (a_tile + b_tile);
-  const uint32_t rawA_bytes = 128u * KC * sizeof(float);           // 16 KB: 128 channels x 32 pixels
+  constexpr int TAA = ABF ? 1 : TA, TBB = BBF ? 1 : TA;           // bf16-stored operands are exact: no lo image
+  const uint32_t stage_bytes = TAA * a_tile + TBB * b_tile;
+  const uint32_t rawA_bytes = 128u * KC * sizeof(float);           // 16 KB: 128 channels x 32 pixels (slot stride)
   const uint32_t raw_bytes = rawA_bytes + (uint32_t)BN * KC * sizeof(float);
+  const uint32_t tx_bytes = 128u * KC * (ABF ? 2 : 4) + (uint32_t)BN * KC * (BBF ? 2 : 4);
   uint8_t* raw_ring = smem + (size_t)stages * stage_bytes;
 
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -644,7 +669,7 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
       mbar_wait(&raw_empty[rs], rph ^ 1);
       if (lane == 0) {
         uint8_t* slot = raw_ring + (size_t)rs * raw_bytes;
-        mbar_arrive_expect_tx(&raw_full[rs], raw_bytes);       // rows outside the tensors are zero-filled and counted
+        mbar_arrive_expect_tx(&raw_full[rs], tx_bytes);        // rows outside the tensors are zero-filled and counted
         tensor_g2s_3d(slot, &tmA, nq0, g * p.CA + m0, nb, &raw_full[rs]);
         tensor_g2s_3d(slot + rawA_bytes, &tmB, nq0, g * p.CB1 + n0, nb, &raw_full[rs]);
       }
@@ -670,11 +695,18 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
       mbar_wait(&raw_full[rs], rph);
       const uint8_t* slot = raw_ring + (size_t)rs * raw_bytes;
       float va[8], vb[8];
-      {
+      uint4 va16 = make_uint4(0, 0, 0, 0), vb16 = make_uint4(0, 0, 0, 0);
+      if (ABF) {                        // rows of 32 bf16 pixels (64 bytes): this thread's 8 pixels are one 16-byte word
+        va16 = *reinterpret_cast<const uint4*>(slot + (size_t)r0 * (KC * 2) + k8 * 16);
+      } else {
         const float4* ra = reinterpret_cast<const float4*>(slot + (size_t)r0 * (KC * 4) + k8 * 32);
         const float4 x0 = ra[0], x1 = ra[1];
         va[0] = x0.x; va[1] = x0.y; va[2] = x0.z; va[3] = x0.w;
         va[4] = x1.x; va[5] = x1.y; va[6] = x1.z; va[7] = x1.w;
+      }
+      if (BBF) {
+        vb16 = *reinterpret_cast<const uint4*>(slot + rawA_bytes + (size_t)(b_ok ? r0 : 0) * (KC * 2) + k8 * 16);
+      } else {
         const float4* rb = reinterpret_cast<const float4*>(slot + rawA_bytes + (size_t)(b_ok ? r0 : 0) * (KC * 4) + k8 * 32);
         const float4 y0 = rb[0], y1 = rb[1];
         vb[0] = y0.x; vb[1] = y0.y; vb[2] = y0.z; vb[3] = y0.w;
@@ -682,8 +714,22 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
       }
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* st = smem + (size_t)s * stage_bytes;
-      if (a_ok) op_store8<TERMS>(st, st + a_tile, r0, k8, va);
-      if (b_ok) op_store8<TERMS>(st + TA * a_tile, st + TA * a_tile + b_tile, r0, k8, vb);
+      if (a_ok) {
+        if (ABF) {
+          const uint32_t pk4[4] = {va16.x, va16.y, va16.z, va16.w};
+          op_store8_bf16(st, r0, k8, pk4);
+        } else {
+          op_store8<TERMS>(st, st + a_tile, r0, k8, va);
+        }
+      }
+      if (b_ok) {
+        if (BBF) {
+          const uint32_t pk4[4] = {vb16.x, vb16.y, vb16.z, vb16.w};
+          op_store8_bf16(st + TAA * a_tile, r0, k8, pk4);
+        } else {
+          op_store8<TERMS>(st + TAA * a_tile, st + TAA * a_tile + b_tile, r0, k8, vb);
+        }
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -709,7 +755,7 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
       tc_fence_after();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-        issue_stage<TERMS>(tmem, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, it == 0);
+        issue_stage<TERMS, !ABF, !BBF>(tmem, st, st + a_tile, st + TAA * a_tile, st + TAA * a_tile + b_tile, idesc, it == 0);
         tc_commit(&empty_bar[s]);
       }
       __syncwarp();
@@ -766,8 +812,8 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
 }
 
 // Returns -100 when the call does not qualify (the caller then launches the register-staged kernel).
-template <int TERMS>
-static int try_pk_tma(const rcot_pk_params& p, cudaStream_t stream, int tr) {
+template <int TERMS, int ABF = 0, int BBF = 0>
+static int try_pk_tma_t(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("RCOT_PK_TMA");      // RCOT_PK_TMA=0: A/B switch back to the register-staged kernel
@@ -791,7 +837,7 @@ static int try_pk_tma(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   int per_cta = cdiv(total_chunks, S);
   S = cdiv(total_chunks, per_cta);
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(BN));
+  const size_t stage_bytes = (size_t)(ABF ? 1 : TA) * op_tile_bytes(128) + (size_t)(BBF ? 1 : TA) * (size_t)op_tile_bytes(BN);
   const size_t raw_bytes = (size_t)(128 + BN) * KC * sizeof(float);
   int nraw = 3, stages = (int)((196 * 1024 - nraw * raw_bytes) / stage_bytes);
   if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
@@ -804,7 +850,7 @@ static int try_pk_tma(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   const size_t smem = stages * stage_bytes + nraw * raw_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pk_tma_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(pk_tma_kernel<TERMS, ABF, BBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
     if (e != cudaSuccess) {
       set_error("pk_gemm(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return RCOT_ERR_CUDA;
@@ -813,13 +859,20 @@ static int try_pk_tma(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   }
   RCOT_REQUIRE(zdim <= 65535 && S <= 65535, "pk_gemm(tma): grid too large");
   CUtensorMap tmA, tmB;
-  int rc = make_act_map(&tmA, p.a, p.a_bs, p.groups * p.CA, HW, p.B, KC, 128, "pk_gemm");
-  if (rc == RCOT_OK) rc = make_act_map(&tmB, p.b, p.b_bs, p.groups * p.CB1, HW, p.B, KC, BN, "pk_gemm");
+  int rc = make_act_map(&tmA, p.a, p.a_bs, p.groups * p.CA, HW, p.B, KC, 128, "pk_gemm", ABF);
+  if (rc == RCOT_OK) rc = make_act_map(&tmB, p.b, p.b_bs, p.groups * p.CB1, HW, p.B, KC, BN, "pk_gemm", BBF);
   if (rc != RCOT_OK) return rc;
   dim3 grid(mt * nt, S, zdim);
-  pk_tma_kernel<TERMS><<<grid, PK_THREADS + 32, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks, stages, nraw,
-                                                              tmem_cols_pow2(BN), tr, tmA, tmB);
+  pk_tma_kernel<TERMS, ABF, BBF><<<grid, PK_THREADS + 32, smem, stream>>>(p, BN, nt, cpi, per_cta, total_chunks, stages,
+                                                                        nraw, tmem_cols_pow2(BN), tr, tmA, tmB);
   return check_launch("pk_gemm(tma)");
+}
+template <int TERMS>
+static int try_pk_tma(const rcot_pk_params& p, cudaStream_t stream, int tr) {
+  if (p.a_bf16 && p.b_bf16) return try_pk_tma_t<TERMS, 1, 1>(p, stream, tr);
+  if (p.a_bf16) return try_pk_tma_t<TERMS, 1, 0>(p, stream, tr);
+  if (p.b_bf16) return try_pk_tma_t<TERMS, 0, 1>(p, stream, tr);
+  return try_pk_tma_t<TERMS, 0, 0>(p, stream, tr);
 }
 
 template <int TERMS, bool GENERAL, bool LN, int NBT>
@@ -885,6 +938,10 @@ extern "C" int rcot_pk_gemm(const rcot_pk_params* pp, rcot_stream_t stream_) {
   RCOT_REQUIRE(p.groups == 1 || p.CB2 == 0, "pk_gemm: groups and concat are exclusive");
   const bool ln = p.ln_stats != nullptr;
   const int HWa = p.Ha * p.Wa;
+  const bool any_bf16 = p.a_bf16 || p.b_bf16;
+  if (any_bf16)
+    RCOT_REQUIRE(p.ks == 1 && HWa % KC == 0 && p.b2 == nullptr && !(ln && p.b_bf16) && (p.a_bs % 8 == 0) && (p.b_bs % 8 == 0),
+                 "pk_gemm: bf16 operands need a 1x1 product on H*W %% 32 == 0 without concat (LayerNorm input stays fp32)");
   bool general = !(p.ks == 1 && p.stride == 1 && p.pad == 0 && HWa % 8 == 0 && p.a_bs % 4 == 0 && p.b_bs % 4 == 0 &&
                    (p.b2 == nullptr || p.b2_bs % 4 == 0) && ((uintptr_t)p.a % 16 == 0) && ((uintptr_t)p.b % 16 == 0) &&
                    (p.b2 == nullptr || (uintptr_t)p.b2 % 16 == 0));
@@ -894,6 +951,7 @@ extern "C" int rcot_pk_gemm(const rcot_pk_params* pp, rcot_stream_t stream_) {
     RCOT_REQUIRE(!general, "pk_gemm: LayerNorm path needs HW %% 8 == 0 and 16-byte aligned tensors");
     const int rc = p.terms == 3 ? try_pk_mm<3>(p, stream) : try_pk_mm<1>(p, stream);
     if (rc != -100) return rc;
+    RCOT_REQUIRE(!any_bf16, "pk_gemm: a bf16 operand with LayerNorm needs the multi-M kernel (CA > 128)");
     return p.terms == 3 ? launch_pk<3, false, true>(p, stream) : launch_pk<1, false, true>(p, stream);
   }
   if (general) return p.terms == 3 ? launch_pk<3, true, false>(p, stream) : launch_pk<1, true, false>(p, stream);
@@ -909,6 +967,8 @@ extern "C" int rcot_pk_gemm(const rcot_pk_params* pp, rcot_stream_t stream_) {
     q.b = p.a;
     q.b_bs = p.a_bs;
     q.CB1 = p.CA;
+    q.a_bf16 = p.b_bf16;
+    q.b_bf16 = p.a_bf16;
     p = q;
     tr = 1;
   }
@@ -916,5 +976,6 @@ extern "C" int rcot_pk_gemm(const rcot_pk_params* pp, rcot_stream_t stream_) {
     const int rc = p.terms == 3 ? try_pk_tma<3>(p, stream, tr) : try_pk_tma<1>(p, stream, tr);
     if (rc != -100) return rc;
   }
+  RCOT_REQUIRE(!any_bf16, "pk_gemm: bf16 operands need the TMA-staged kernel (N <= 128 after the operand swap)");
   return p.terms == 3 ? launch_pk<3, false, false>(p, stream, tr) : launch_pk<1, false, false>(p, stream, tr);
 }

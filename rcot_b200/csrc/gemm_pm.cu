@@ -48,7 +48,8 @@ struct PmGeom {
   uint32_t tmem_cols;
 };
 
-template <int KS, int MODE, int TERMS, bool LN, bool TMA>
+// ABF / OBF (1x1 TMA variant only): the gather source / the output is a bf16 tensor (bf16-storage mode).
+template <int KS, int MODE, int TERMS, bool LN, bool TMA, int ABF = 0, int OBF = 0>
 __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
     pm_gemm_kernel(const rcot_pm_params p, const PmGeom g, const __grid_constant__ CUtensorMap tm1,
                    const __grid_constant__ CUtensorMap tm2) {
@@ -57,6 +58,8 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
   __shared__ uint64_t raw_full[PM_RAW], raw_empty[PM_RAW];
   __shared__ uint32_t tmem_base_s;
   constexpr int TA = (TERMS > 1) ? 2 : 1;
+  constexpr int TAA = ABF ? 1 : TA;        // operand images of A: a bf16-stored A has no lo term
+  static_assert(!(ABF || OBF) || (TMA && KS == 1 && !(ABF && LN)), "bf16 storage: TMA-staged 1x1 kernels only");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HWr = p.Hr * p.Wr, HWs = p.Hs * p.Ws;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
   const uint32_t a_tile = op_tile_bytes(128);
   const uint32_t b_tile = op_tile_bytes(BN);          // this item's columns (a slice of the packed pass)
   const uint32_t b_tile_f = op_tile_bytes(g.BNf);     // the packed pass: [chunk][term][BNf x 32]
-  const uint32_t stage_bytes = TA * (a_tile + b_tile);
+  const uint32_t stage_bytes = TAA * a_tile + TA * b_tile;
   const int total_tiles = g.tiles_m * g.passes;
   // Features of the conv instantiations only, resolved at compile time so that the 1x1 kernels (the hot path: the
   // epilogue of the write-heavy shapes lost 20 % when these were run-time branches) carry none of their code:
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         if (lane == 0) {
           // channels beyond the tensor (ragged last chunk) are filled with zeros by the copy engine and still
           // count towards the transaction bytes
-          mbar_arrive_expect_tx(&raw_full[rs], PM_RAW_BYTES);
+          mbar_arrive_expect_tx(&raw_full[rs], ABF ? PM_RAW_BYTES / 2 : PM_RAW_BYTES);
           const int k = c * KC;
           const bool second = k >= p.C1;
           const CUtensorMap* tm = second ? &tm2 : &tm1;
@@ -186,11 +189,25 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
                             (size_t)pass * g.nk_full * (2 * b_tile_f);
       for (int c = 0; c < nk; ++c) {
         mbar_wait(&raw_full[rs], rph);
-        const float* raw = reinterpret_cast<const float*>(raw_ring + (size_t)rs * PM_RAW_BYTES) + (khalf * 16) * 128 + row;
         const int k0 = c * KC + khalf * 16;
         float v[16];
+        uint32_t pk[8];
+        if (ABF) {
+          // bf16 source: the 16 values ARE the operand (no split, no lo image); channels beyond the tensor were
+          // zero-filled by the copy engine
+          const unsigned short* raw =
+              reinterpret_cast<const unsigned short*>(raw_ring + (size_t)rs * PM_RAW_BYTES) + (khalf * 16) * 128 + row;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (k0 + i < g.Ktot) ? raw[i * 128] : 0.f;   // never-copied rows read as 0
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t lo16 = (k0 + 2 * i < g.Ktot) ? raw[(2 * i) * 128] : 0u;
+            const uint32_t hi16 = (k0 + 2 * i + 1 < g.Ktot) ? raw[(2 * i + 1) * 128] : 0u;
+            pk[i] = lo16 | (hi16 << 16);
+          }
+        } else {
+          const float* raw = reinterpret_cast<const float*>(raw_ring + (size_t)rs * PM_RAW_BYTES) + (khalf * 16) * 128 + row;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (k0 + i < g.Ktot) ? raw[i * 128] : 0.f;   // never-copied rows read as 0
+        }
         const int s = ps_;
         const uint32_t ph = pph_;
         if (++ps_ == stages) {
@@ -201,18 +218,24 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         uint8_t* st = smem + (size_t)s * stage_bytes;
         if (tid == 0) {
           mbar_arrive_expect_tx(&full_bar[s], TA * b_tile);
-          bulk_g2s(st + TA * a_tile, wsrc + (size_t)c * (2 * b_tile_f), TA * b_tile, &full_bar[s]);
+          bulk_g2s(st + TAA * a_tile, wsrc + (size_t)c * (2 * b_tile_f), TA * b_tile, &full_bar[s]);
         }
-        if (LN) {
-          const float* gb = ln_gb + k0 * 2;   // interleaved (gamma, beta), zero beyond Ktot
+        if (ABF) {
+          const uint32_t pa[4] = {pk[0], pk[1], pk[2], pk[3]}, pb[4] = {pk[4], pk[5], pk[6], pk[7]};
+          op_store8_bf16(st, row, khalf * 2, pa);
+          op_store8_bf16(st, row, khalf * 2 + 1, pb);
+        } else {
+          if (LN) {
+            const float* gb = ln_gb + k0 * 2;   // interleaved (gamma, beta), zero beyond Ktot
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 w2 = *reinterpret_cast<const float2*>(gb + 2 * i);
-            v[i] = (v[i] - mu) * rstd * w2.x + w2.y;
+            for (int i = 0; i < 16; ++i) {
+              const float2 w2 = *reinterpret_cast<const float2*>(gb + 2 * i);
+              v[i] = (v[i] - mu) * rstd * w2.x + w2.y;
+            }
           }
+          op_store8<TERMS>(st, st + a_tile, row, khalf * 2, v);
+          op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, v + 8);
         }
-        op_store8<TERMS>(st, st + a_tile, row, khalf * 2, v);
-        op_store8<TERMS>(st, st + a_tile, row, khalf * 2 + 1, v + 8);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -432,10 +455,10 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         }
         const uint8_t* wsrc = S.x.wsrc + (size_t)wc * (2 * b_tile_f);
         if (nslice == 1) {
-          bulk_g2s(st + TA * a_tile, wsrc, TA * b_tile, &full_bar[s]);          // hi and lo images are adjacent
+          bulk_g2s(st + TAA * a_tile, wsrc, TA * b_tile, &full_bar[s]);          // hi and lo images are adjacent
         } else {
-          bulk_g2s(st + TA * a_tile, wsrc, b_tile, &full_bar[s]);
-          if (TA > 1) bulk_g2s(st + TA * a_tile + b_tile, wsrc + b_tile_f, b_tile, &full_bar[s]);
+          bulk_g2s(st + TAA * a_tile, wsrc, b_tile, &full_bar[s]);
+          if (TA > 1) bulk_g2s(st + TAA * a_tile + b_tile, wsrc + b_tile_f, b_tile, &full_bar[s]);
         }
       }
       if (LN) {
@@ -485,7 +508,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-          issue_stage<TERMS>(d, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, c == 0);
+          issue_stage<TERMS, !ABF>(d, st, st + a_tile, st + TAA * a_tile, st + TAA * a_tile + b_tile, idesc, c == 0);
           tc_commit(&empty_bar[s]);
         }
         __syncwarp();
@@ -587,7 +610,12 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(cur[i]) + (epi_res ? q[i] : 0.f);
           }
-          if (nrem >= 16) {
+          if (OBF) {      // bf16 output tensor: same element offsets, 2-byte stores (a warp writes 64 contiguous bytes)
+            __nv_bfloat16* og16 = reinterpret_cast<__nv_bfloat16*>(p.out) + (og - p.out);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nrem) og16[(size_t)i * HWr] = __float2bfloat16_rn(y[i]);
+          } else if (nrem >= 16) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) og[(size_t)i * HWr] = y[i];
           } else {
@@ -659,7 +687,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
 
 static int g_num_sms = 0;
 
-template <int KS, int MODE, int TERMS, bool LN, bool TMA = false>
+template <int KS, int MODE, int TERMS, bool LN, bool TMA = false, int ABF = 0, int OBF = 0>
 static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   PmGeom g;
   g.Ktot = (p.C1 + p.C2) * KS * KS;
@@ -682,7 +710,8 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
     g.passes = pl.passes * g.nslice;
   }
   constexpr int TA = (TERMS > 1) ? 2 : 1;
-  const size_t stage_bytes = (size_t)TA * (op_tile_bytes(128) + (size_t)op_tile_bytes(g.BN));
+  constexpr int TAA = ABF ? 1 : TA;
+  const size_t stage_bytes = (size_t)TAA * op_tile_bytes(128) + (size_t)TA * op_tile_bytes(g.BN);
   const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
   g.c1_aligned = (p.C2 == 0 || p.C1 % 16 == 0) ? 1 : 0;
   const size_t raw_bytes = TMA ? (size_t)PM_RAW * PM_RAW_BYTES : 0;
@@ -710,7 +739,7 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   RCOT_REQUIRE(smem <= 208 * 1024, "pm_gemm: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN, TMA>,
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN, TMA, ABF, OBF>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) {
       set_error("pm_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -730,11 +759,11 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   memset(&tm1, 0, sizeof(tm1));
   memset(&tm2, 0, sizeof(tm2));
   if (TMA) {
-    int rc = make_act_map(&tm1, p.in, p.in_bs, p.C1, HWr, p.B, 128, KC, "pm_gemm");
+    int rc = make_act_map(&tm1, p.in, p.in_bs, p.C1, HWr, p.B, 128, KC, "pm_gemm", ABF);
     if (rc == RCOT_OK && p.in2) rc = make_act_map(&tm2, p.in2, p.in2_bs, p.C2, HWr, p.B, 128, KC, "pm_gemm");
     if (rc != RCOT_OK) return rc;
   }
-  pm_gemm_kernel<KS, MODE, TERMS, LN, TMA><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g, tm1, tm2);
+  pm_gemm_kernel<KS, MODE, TERMS, LN, TMA, ABF, OBF><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g, tm1, tm2);
   return check_launch("pm_gemm");
 }
 
@@ -751,6 +780,7 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
   RCOT_REQUIRE((p.C2 == 0) == (p.in2 == nullptr), "pm_gemm: in2/C2 mismatch");
   RCOT_REQUIRE(p.Hs > 0 && p.Ws > 0 && p.Hr > 0 && p.Wr > 0, "pm_gemm: bad spatial sizes");
   RCOT_REQUIRE(p.terms == 1 || p.terms == 3, "pm_gemm: terms must be 1 or 3");
+  RCOT_REQUIRE(!(p.in_bf16 || p.out_bf16) || p.ks == 1, "pm_gemm: bf16 tensors are supported by the 1x1 kernels only");
   RCOT_REQUIRE(p.mode == 0 || p.mode == 1, "pm_gemm: mode must be 0 or 1");
   const bool ln = p.ln_stats != nullptr;
   if (ln) RCOT_REQUIRE(p.ks == 1 && p.ln_gamma && p.ln_beta, "pm_gemm: LayerNorm prologue needs ks==1, gamma, beta");
@@ -777,6 +807,22 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
       const bool tma = tma_on && tensor_map_encoder() != nullptr && HW % 128 == 0 && p.in_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 &&
                        (p.in2 == nullptr || (p.C1 % 32 == 0 && p.in2_bs % 4 == 0 &&
                                              (reinterpret_cast<uintptr_t>(p.in2) & 15) == 0));
+      if (p.in_bf16 || p.out_bf16) {
+        // bf16-storage mode of the hidden tensors: TMA-staged kernels only
+        RCOT_REQUIRE(tma && p.in2 == nullptr, "pm_gemm: bf16 tensors need the TMA-staged 1x1 path (H*W %% 128 == 0, 16-byte "
+                     "aligned, no concat); got %dx%d", p.Hr, p.Wr);
+        RCOT_REQUIRE(!(p.in_bf16 && ln), "pm_gemm: LayerNorm prologue takes an fp32 input");
+        if (p.out_bf16)
+          RCOT_REQUIRE(!p.bias && !p.act && !p.mask_y && !p.accumulate && !p.residual && !p.stats_out,
+                       "pm_gemm: a bf16 output takes the plain epilogue only");
+#define PM_BF(LNF, A, O) \
+  return (p.terms == 3) ? launch_pm<1, 0, 3, LNF, true, A, O>(p, stream) : launch_pm<1, 0, 1, LNF, true, A, O>(p, stream)
+        if (p.in_bf16 && p.out_bf16) { PM_BF(false, 1, 1); }
+        if (p.in_bf16) { PM_BF(false, 1, 0); }
+        if (ln) { PM_BF(true, 0, 1); }
+        PM_BF(false, 0, 1);
+#undef PM_BF
+      }
       if (tma) {
         if (ln) return (p.terms == 3) ? launch_pm<1, 0, 3, true, true>(p, stream) : launch_pm<1, 0, 1, true, true>(p, stream);
         return (p.terms == 3) ? launch_pm<1, 0, 3, false, true>(p, stream) : launch_pm<1, 0, 1, false, true>(p, stream);

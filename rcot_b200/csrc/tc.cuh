@@ -254,9 +254,17 @@ __device__ __forceinline__ void op_store8(uint8_t* hi_tile, uint8_t* lo_tile, in
   if (TERMS > 1) *reinterpret_cast<uint4*>(lo_tile + off) = lo;
 }
 
+// Store 8 consecutive-k bf16 values (already exact) of one operand row.
+__device__ __forceinline__ void op_store8_bf16(uint8_t* hi_tile, int row, int k8, const uint32_t (&pk)[4]) {
+  const uint32_t off = (uint32_t)(row >> 3) * OP_SBO + (uint32_t)k8 * OP_LBO + (uint32_t)(row & 7) * 16u;
+  *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 // Issue the MMAs of one K stage (KC = 2 k16 steps) for one [128 x BN] accumulator.
 // TERMS==3: hi*hi + lo*hi + hi*lo (fp32-class accuracy); TERMS==1: hi*hi (bf16 compute).
-template <int TERMS>
+// ALO = false: the A operand is exact in bf16 (bf16-stored activations): its lo term does not exist.
+// BLO = false: likewise for B.
+template <int TERMS, bool ALO = true, bool BLO = true>
 __device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
                                             uint32_t b_lo, uint32_t idesc, bool first_stage) {
 #pragma unroll
@@ -266,10 +274,14 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t a_hi, uint
     uint64_t dbh = make_sdesc(b_hi + ko, OP_LBO, OP_SBO);
     tc_mma_bf16(tmem_d, dah, dbh, idesc, (first_stage && s == 0) ? 0u : 1u);
     if (TERMS > 1) {
-      uint64_t dal = make_sdesc(a_lo + ko, OP_LBO, OP_SBO);
-      uint64_t dbl = make_sdesc(b_lo + ko, OP_LBO, OP_SBO);
-      tc_mma_bf16(tmem_d, dal, dbh, idesc, 1u);
-      tc_mma_bf16(tmem_d, dah, dbl, idesc, 1u);
+      if (ALO) {
+        uint64_t dal = make_sdesc(a_lo + ko, OP_LBO, OP_SBO);
+        tc_mma_bf16(tmem_d, dal, dbh, idesc, 1u);
+      }
+      if (BLO) {
+        uint64_t dbl = make_sdesc(b_lo + ko, OP_LBO, OP_SBO);
+        tc_mma_bf16(tmem_d, dah, dbl, idesc, 1u);
+      }
     }
   }
 }

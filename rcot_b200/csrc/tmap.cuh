@@ -30,18 +30,20 @@ inline EncodeTiledFn tensor_map_encoder() {
 // Map of an activation [B, C, HW] (per-image block contiguous, batch stride bs elements) with a box of
 // box_px pixels x box_ch channels x 1 image, no swizzle: the box lands in shared memory as [channel][pixel].
 // Channels / pixels of a box that fall outside the tensor are filled with zeros.
-inline int make_act_map(CUtensorMap* tm, const float* base, int64_t bs, int C, long HW, int B, int box_px, int box_ch,
-                        const char* who) {
+inline int make_act_map(CUtensorMap* tm, const void* base, int64_t bs, int C, long HW, int B, int box_px, int box_ch,
+                        const char* who, int bf16 = 0) {
   EncodeTiledFn encode = tensor_map_encoder();
   if (!encode) {
     set_error("%s: cuTensorMapEncodeTiled is not available from this driver", who);
     return RCOT_ERR_CUDA;
   }
   const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
-  const cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)bs * sizeof(float)};
+  const size_t esz = bf16 ? 2 : sizeof(float);
+  const cuuint64_t strides[2] = {(cuuint64_t)HW * esz, (cuuint64_t)bs * esz};
   const cuuint32_t box[3] = {(cuuint32_t)box_px, (cuuint32_t)box_ch, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+  const CUresult r = encode(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                            const_cast<void*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

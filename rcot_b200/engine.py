@@ -249,6 +249,15 @@ class BlockSpec:
                 ps.add_gdfn(prefix, C, self.hid)
 
 
+def hidden_dtype(C, H, W):
+    """Storage type of a block's hidden tensors (pre, qkv, u, g and their gradients).  bf16-storage mode
+    (ops.HIDDEN_DTYPE = torch.bfloat16) applies to the levels that carry the bytes -- C <= 96 (84 % of the block traffic)
+    on maps with H*W % 128 == 0 (the TMA-staged kernels) -- the deep, tensor-bound levels keep fp32."""
+    if ops.HIDDEN_DTYPE == torch.bfloat16 and C <= 96 and (H * W) % 128 == 0 and W % 4 == 0:
+        return torch.bfloat16
+    return torch.float32
+
+
 def _stats_of(x):
     """Per-pixel LayerNorm (mean, rstd) of x: left on the tensor by the GEMM epilogue that produced it
     (pm_gemm stats_out), else one ln_stats launch."""
@@ -270,7 +279,7 @@ def mdta_fwd(bs: BlockSpec, x, norm_name, residual, need_bwd, store=None):
     st = sc if store is None else store
     stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
-    pre = ops.pm_gemm(x, ps.pack(a + "qkv.weight", "fwd"), 3 * C, ln=ln)
+    pre = ops.pm_gemm(x, ps.pack(a + "qkv.weight", "fwd"), 3 * C, ln=ln, out_dtype=hidden_dtype(C, H, W))
     ops.zero_(sc.zbuf)
     if store is not None:
         ops.zero_(store.sumsq)
@@ -314,11 +323,12 @@ def gdfn_fwd(bs: BlockSpec, x, norm_name, residual, keep=False):
     hid = bs.hid
     stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
-    if bs.pre in ps.gdfn and ops.TERMS == 3 and ops.gdfn_supported(C, x.shape[2], x.shape[3]):
+    hd = hidden_dtype(C, x.shape[2], x.shape[3])
+    if bs.pre in ps.gdfn and ops.TERMS == 3 and hd == torch.float32 and ops.gdfn_supported(C, x.shape[2], x.shape[3]):
         # one kernel, hidden tensor on chip; u / g are written out only when the backward wants them kept
         y, u, g = ops.gdfn_fwd(x, ps.gdfn[bs.pre], hid, ln=ln, residual=residual, stats_out=bool(norm_name), save=keep)
         return (y, (stats, u, g)) if keep else y
-    u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
+    u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln, out_dtype=hd)
     g = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=1)
     y = ops.pm_gemm(g, ps.pack(f + "project_out.weight", "fwd"), C, residual=x if residual else None,
                     stats_out=bool(norm_name))      # feeds LN1 of the next block
@@ -337,11 +347,12 @@ def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual, kept=None):
     else:
         stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
+    hd = hidden_dtype(C, x.shape[2], x.shape[3])
     if kept is None:
-        u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln)
-    dg = ops.pm_gemm(dy, ps.pack(f + "project_out.weight", "dgrad"), hid)
+        u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln, out_dtype=hd)
+    dg = ops.pm_gemm(dy, ps.pack(f + "project_out.weight", "dgrad"), hid, out_dtype=hd)
     g = g_kept if g_kept is not None else torch.empty_like(dg)
-    if FUSED_GDFN_MID and ops.gdfn_mid_ok(u):
+    if FUSED_GDFN_MID and hd == torch.float32 and ops.gdfn_mid_ok(u):
         # gate backward + transposed depthwise conv + its weight gradient in one pass over u (no [da; db] in HBM)
         du = ops.gdfn_mid_bwd(u, dg, ps.p[f + "dwconv.weight"], ps.g[f + "dwconv.weight"],
                               g_out=None if g_kept is not None else g)

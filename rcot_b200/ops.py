@@ -32,6 +32,7 @@ class PMParams(C.Structure):
         ("slope", C.c_float), ("accumulate", C.c_int32), ("bias", C.c_void_p),
         ("mask_y", C.c_void_p), ("mask_bs", C.c_int64), ("residual", C.c_void_p), ("res_bs", C.c_int64),
         ("stats_out", C.c_void_p), ("debug", C.c_int32), ("tap_major", C.c_int32),
+        ("in_bf16", C.c_int32), ("out_bf16", C.c_int32),
     ]
 
 
@@ -45,7 +46,7 @@ class PKParams(C.Structure):
         ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
         ("per_image", C.c_int32), ("terms", C.c_int32),
         ("out", C.c_void_p), ("out_bs", C.c_int64), ("ldo", C.c_int32), ("groups", C.c_int32),
-        ("out_gs", C.c_int64),
+        ("out_gs", C.c_int64), ("a_bf16", C.c_int32), ("b_bf16", C.c_int32),
     ]
 
 
@@ -55,7 +56,7 @@ class DWParams(C.Structure):
         ("B", C.c_int32), ("Cn", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("mode", C.c_int32), ("flip", C.c_int32), ("hid", C.c_int32), ("nsq", C.c_int32),
         ("dg", C.c_void_p), ("dg_bs", C.c_int64), ("g_out", C.c_void_p), ("g_bs", C.c_int64),
-        ("sumsq", C.c_void_p),
+        ("sumsq", C.c_void_p), ("bf16", C.c_int32),
     ]
 
 
@@ -97,9 +98,24 @@ def _f32(t, name="tensor"):
     return t
 
 
-def _img_view(t, name="tensor"):
+HIDDEN_DTYPE = torch.float32    # torch.bfloat16 = bf16-storage mode: the blocks' hidden tensors (pre, qkv, u, g and their
+                                # gradients) are stored as bf16; block inputs/outputs, weights, statistics, accumulation
+                                # and every weight gradient stay fp32 (set through rcot_b200.set_hidden_dtype)
+
+
+def _act(t, name="tensor"):
+    """A hidden activation: CUDA fp32 or bf16.  Returns 1 for bf16."""
+    if t.dtype not in (torch.float32, torch.bfloat16) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA float32 / bfloat16 tensor, got {t.dtype} on {t.device}")
+    return int(t.dtype == torch.bfloat16)
+
+
+def _img_view(t, name="tensor", any_act=False):
     """NCHW tensor whose per-image block [C,H,W] is contiguous; returns batch stride in elements."""
-    _f32(t, name)
+    if any_act:
+        _act(t, name)
+    else:
+        _f32(t, name)
     B, Cc, H, W = t.shape
     if t.stride(3) != 1 or t.stride(2) != W or t.stride(1) != H * W:
         raise ValueError(f"{name}: per-image block must be contiguous, strides={t.stride()}")
@@ -196,10 +212,11 @@ def pack_single(w: torch.Tensor, kind: str):
 # ------------------------------------------------------------------ pixel-as-M GEMM
 def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None, out_hw=None, out_coff=0,
             ln=None, bias=None, act=False, slope=0.2, mask_y=None, residual=None, accumulate=False,
-            wpack_bs=0, terms=None, debug=0, tap_major=False, stats_out=False):
-    """out[b, coff+n, p] = epi(sum_k A(b,p,k) W[n,k]).  ``ln`` = (stats[B,HW,2], gamma, beta)."""
+            wpack_bs=0, terms=None, debug=0, tap_major=False, stats_out=False, out_dtype=torch.float32):
+    """out[b, coff+n, p] = epi(sum_k A(b,p,k) W[n,k]).  ``ln`` = (stats[B,HW,2], gamma, beta).
+    x may be a bf16 tensor and/or out_dtype (or ``out``) bf16: bf16-storage mode of the hidden tensors (1x1 only)."""
     B, C1, Hs, Ws = x.shape
-    in_bs = _img_view(x, "x")
+    in_bs = _img_view(x, "x", True)
     C2 = 0 if x2 is None else x2.shape[1]
     in2_bs = 0 if x2 is None else _img_view(x2, "x2")
     if out_hw is None:
@@ -209,9 +226,10 @@ def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None
             raise ValueError("dgrad needs out_hw")
     Hr, Wr = out_hw
     if out is None:
-        out = torch.empty(B, N, Hr, Wr, device=x.device, dtype=torch.float32)
-    out_bs = _img_view(out, "out")
+        out = torch.empty(B, N, Hr, Wr, device=x.device, dtype=out_dtype)
+    out_bs = _img_view(out, "out", True)
     p = PMParams()
+    p.in_bf16, p.out_bf16 = _act(x, "x"), _act(out, "out")
     p.in_, p.in2, p.in_bs, p.in2_bs = x.data_ptr(), (None if x2 is None else x2.data_ptr()), in_bs, in2_bs
     p.C1, p.C2, p.Hs, p.Ws, p.Hr, p.Wr, p.B = C1, C2, Hs, Ws, Hr, Wr, B
     p.ks, p.stride, p.pad, p.mode = ks, stride, pad, mode
@@ -247,8 +265,9 @@ def pk_gemm(a, b, out, *, ldo, ks=1, stride=1, pad=0, b2=None, ln=None, per_imag
     B, CAf, Ha, Wa = a.shape
     _, CBf, Hb, Wb = b.shape
     p = PKParams()
-    p.a, p.a_bs, p.CA = a.data_ptr(), _img_view(a, "a"), (CAf // groups if CA is None else CA)
-    p.b, p.b_bs, p.CB1 = b.data_ptr(), _img_view(b, "b"), (CBf // groups if CB is None else CB)
+    p.a, p.a_bs, p.CA = a.data_ptr(), _img_view(a, "a", True), (CAf // groups if CA is None else CA)
+    p.b, p.b_bs, p.CB1 = b.data_ptr(), _img_view(b, "b", True), (CBf // groups if CB is None else CB)
+    p.a_bf16, p.b_bf16 = _act(a, "a"), _act(b, "b")
     if b2 is not None:
         p.b2, p.b2_bs, p.CB2 = b2.data_ptr(), _img_view(b2, "b2"), b2.shape[1]
     p.Ha, p.Wa, p.Hb, p.Wb, p.B = Ha, Wa, Hb, Wb, B
@@ -351,18 +370,24 @@ def ln_bwd(dz, x, stats, gamma, dgamma, dbeta, dy=None, dx=None):
 
 # ------------------------------------------------------------------ depthwise 3x3
 def dwconv(x, w, *, out=None, mode=0, flip=False, dg=None, g_out=None, sumsq=None, nsq=0):
+    """x (and out / dg / g_out) may be bf16 tensors (bf16-storage mode): same kernels, 2-byte loads and stores."""
     B, Cn, H, W = x.shape
     hid = Cn // 2 if mode != 0 else 0
+    bf = _act(x, "x")
     if out is None:
-        out = torch.empty(B, hid if mode == 1 else Cn, H, W, device=x.device, dtype=torch.float32)
+        out = torch.empty(B, hid if mode == 1 else Cn, H, W, device=x.device, dtype=x.dtype)
+    for t, nm in ((out, "out"), (dg, "dg"), (g_out, "g_out")):
+        if t is not None and t.dtype != x.dtype:
+            raise TypeError(f"dwconv: {nm} is {t.dtype} but x is {x.dtype}")
     p = DWParams()
-    p.in_, p.in_bs, p.w, p.out, p.out_bs = x.data_ptr(), _img_view(x, "x"), _f32(w).data_ptr(), out.data_ptr(), _img_view(out, "out")
+    p.in_, p.in_bs, p.w, p.out, p.out_bs = (x.data_ptr(), _img_view(x, "x", True), _f32(w).data_ptr(), out.data_ptr(),
+                                            _img_view(out, "out", True))
     p.B, p.Cn, p.H, p.W = B, Cn, H, W
-    p.mode, p.flip, p.hid, p.nsq = mode, int(flip), hid, nsq
+    p.mode, p.flip, p.hid, p.nsq, p.bf16 = mode, int(flip), hid, nsq, bf
     if dg is not None:
-        p.dg, p.dg_bs = dg.data_ptr(), _img_view(dg, "dg")
+        p.dg, p.dg_bs = dg.data_ptr(), _img_view(dg, "dg", True)
     if g_out is not None:
-        p.g_out, p.g_bs = g_out.data_ptr(), _img_view(g_out, "g_out")
+        p.g_out, p.g_bs = g_out.data_ptr(), _img_view(g_out, "g_out", True)
     if sumsq is not None:
         p.sumsq = sumsq.data_ptr()
     _lib.check(L().rcot_dwconv3x3(C.byref(p), _stream()), "dwconv3x3")
@@ -378,12 +403,15 @@ def dwconv_wgrad(x, dout, dw):
 
 
 def dwconv_bwd(x, dout, w, dw):
-    """din = dw^T(dout); dw += corr(x, dout)  (x = the depthwise conv's forward input)."""
+    """din = dw^T(dout); dw += corr(x, dout)  (x = the depthwise conv's forward input).  x / dout fp32 or both bf16."""
     B, Cn, H, W = x.shape
+    bf = _act(x, "x")
+    if dout.dtype != x.dtype:
+        raise TypeError(f"dwconv_bwd: dout is {dout.dtype} but x is {x.dtype}")
     din = torch.empty_like(dout)
-    _lib.check(L().rcot_dwconv3x3_bwd(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(dout),
-                                      C.c_int64(_img_view(dout, "dout")), _ptr(_f32(w)), _ptr(din),
-                                      C.c_int64(_img_view(din, "din")), _ptr(_f32(dw)), B, Cn, H, W, _stream()),
+    _lib.check(L().rcot_dwconv3x3_bwd_t(_ptr(x), C.c_int64(_img_view(x, "x", True)), _ptr(dout),
+                                        C.c_int64(_img_view(dout, "dout", True)), _ptr(_f32(w)), _ptr(din),
+                                        C.c_int64(_img_view(din, "din", True)), _ptr(_f32(dw)), B, Cn, H, W, bf, _stream()),
                "dwconv3x3_bwd")
     return din
 

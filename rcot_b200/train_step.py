@@ -121,6 +121,8 @@ class OTTrainStep:
         if save is None:
             # hidden tensors of all 102 blocks: 15 * 49.35 M floats per 128x128 image (pre, qkv, u, g, mid-block x)
             need = 15.0 * 49.35e6 * 4 * B * (P / 128.0) ** 2
+            if ops.HIDDEN_DTYPE == torch.bfloat16:
+                need *= 0.58            # levels with C <= 96 hold 84 % of it at half the size
             save = need < 0.55 * torch.cuda.get_device_properties(degraded.device).total_memory
         tape = Tape(save_hidden=bool(save))
         self._mark("T_forward")
@@ -198,7 +200,7 @@ class OTTrainStep:
         Python/driver launch rate.  Inputs are copied into static buffers; the learning rate and Adam's bias
         corrections live in a small device tensor refreshed before every replay."""
         B, _, P, _ = degraded.shape
-        key = (B, P, bool(paired))
+        key = (B, P, bool(paired), ops.HIDDEN_DTYPE)
         ent = self._graphs.get(key)
         dev = degraded.device
         if ent is None:

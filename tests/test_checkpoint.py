@@ -82,8 +82,8 @@ def test_save_load_forward_and_resume_step(tmp_path):
     T2, F2 = ck["Tnet"].cuda(), ck["Fnet"].cuda()
     assert list(T2.state_dict()) == list(T.state_dict()) and len(T2.state_dict()) == 816
     with torch.no_grad():
-        assert torch.equal(T2(x), y0)
-        assert torch.equal(F2(x), F(x))
+        torch.testing.assert_close(T2(x), y0, rtol=1e-5, atol=1e-5)      # same weights; split-K atomics order only
+        torch.testing.assert_close(F2(x), F(x), rtol=1e-5, atol=1e-6)
     # resume-then-step == step: one iteration on the original modules and on the reloaded ones (RMSprop state starts
     # at zero in both, as after the reference's --resume which carries no optimizer state)
     g = torch.Generator().manual_seed(1)

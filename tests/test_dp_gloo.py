@@ -33,7 +33,7 @@ def _worker(rank, world, port, ret):
         deg = tgt + 0.1 * torch.randn(B, 3, P, P, generator=g)
         de_id = torch.tensor([1, 4, 4, 1])
         # ---- (1) sharding in trainer.train_one
-        trainer.opt = trainer.parser.parse_args(["--batchSize", str(B), "--pairnum", "100"])
+        trainer.opt = trainer.parser.parse_args(["--batchSize", str(B), "--pairnum", "100", "--cuda_graph", "0"])
 
         class Stub:
             class T:

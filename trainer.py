@@ -59,6 +59,9 @@ parser.add_argument("--seed", type=int, default=None, help="fixed seed (default:
 parser.add_argument("--synthetic", type=int, default=0, help="train on this many seeded synthetic pairs")
 parser.add_argument("--no_dump", action="store_true", help="skip checksample PNG dumps")
 parser.add_argument("--max_iters", type=int, default=0, help="stop each epoch after this many iterations (0 = all)")
+parser.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="storage of the blocks' hidden tensors: fp32 (reference-exact class) or bf16 (half the hidden "
+                         "traffic and memory; fp32 accumulation, weights and block inputs/outputs; stated tolerance 2e-2)")
 parser.add_argument("--device_data", action="store_true",
                     help="assemble the training patches on the GPU (rcot_b200.data: crop / augmentation / uint8-grid "
                          "noise in one kernel per batch) instead of a CPU DataLoader; with --synthetic N")
@@ -299,6 +302,8 @@ def main(argv=None):
         print(opt)
     if not opt.cuda or not torch.cuda.is_available():
         raise Exception("rcot_b200 runs on a B200 only (no CPU path); the reference's CPU mode is the oracle in oracle/")
+    import rcot_b200
+    rcot_b200.set_hidden_dtype(opt.dtype)
     opt.seed = random.randint(1, 10000) if opt.seed is None else opt.seed
     if world > 1:
         # every rank must build the same weights, shuffle the same way and draw the same alpha stream: the seed
