@@ -33,28 +33,52 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
+// Row segments of PW output pixels: PW = 4 for fp32 (16 bytes), 8 for bf16 (16 bytes): one vector access per row either
+// way, so the bf16 kernels move half the bytes with the SAME number of memory instructions per byte moved.
+template <typename T> struct RowW { static constexpr int PW = 4; };
+template <> struct RowW<__nv_bfloat16> { static constexpr int PW = 8; };
+__device__ __forceinline__ void ldrow(const float* p, float (&v)[4]) {
+  const float4 m = ld4(p);
+  v[0] = m.x; v[1] = m.y; v[2] = m.z; v[3] = m.w;
+}
+__device__ __forceinline__ void ldrow(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+  v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+  v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+__device__ __forceinline__ void strow(float* p, const float (&v)[4]) { st4(p, make_float4(v[0], v[1], v[2], v[3])); }
+__device__ __forceinline__ void strow(__nv_bfloat16* p, const float (&v)[8]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  const __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                                            *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+}
+
 // the value a store of v will leave in memory (so that sums of squares match what later kernels read)
 __device__ __forceinline__ float stored(const float*, float v) { return v; }
 __device__ __forceinline__ float stored(const __nv_bfloat16*, float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-template <int ROWS>
+template <int ROWS, int PW>
 struct Patch {
-  float v[ROWS + 2][6];  // rows y-1 .. y+ROWS, columns x0-1 .. x0+4
+  float v[ROWS + 2][PW + 2];  // rows y-1 .. y+ROWS, columns x0-1 .. x0+PW
 };
 
 template <int ROWS, typename T>
-__device__ __forceinline__ void load_patch(Patch<ROWS>& P, const T* __restrict__ plane, int y, int x0, int H, int W) {
+__device__ __forceinline__ void load_patch(Patch<ROWS, RowW<T>::PW>& P, const T* __restrict__ plane, int y, int x0, int H,
+                                           int W) {
+  constexpr int PW = RowW<T>::PW;
   const T* p = plane + (y - 1) * W + x0;
-  if (y > 0 && y + ROWS < H && x0 > 0 && x0 + 4 < W) {   // interior: no predicates
+  if (y > 0 && y + ROWS < H && x0 > 0 && x0 + PW < W) {   // interior: no predicates
 #pragma unroll
     for (int r = 0; r < ROWS + 2; ++r) {
-      const float4 m = ld4(p + r * W);
+      float m[PW];
+      ldrow(p + r * W, m);
       P.v[r][0] = ld1(p + r * W - 1);
-      P.v[r][1] = m.x;
-      P.v[r][2] = m.y;
-      P.v[r][3] = m.z;
-      P.v[r][4] = m.w;
-      P.v[r][5] = ld1(p + r * W + 4);
+#pragma unroll
+      for (int i = 0; i < PW; ++i) P.v[r][1 + i] = m[i];
+      P.v[r][PW + 1] = ld1(p + r * W + PW);
     }
     return;
   }
@@ -62,26 +86,25 @@ __device__ __forceinline__ void load_patch(Patch<ROWS>& P, const T* __restrict__
   for (int r = 0; r < ROWS + 2; ++r) {
     const int yy = y - 1 + r;
     if ((unsigned)yy < (unsigned)H) {
-      const float4 m = ld4(p + r * W);
+      float m[PW];
+      ldrow(p + r * W, m);
       P.v[r][0] = x0 > 0 ? ld1(p + r * W - 1) : 0.f;
-      P.v[r][1] = m.x;
-      P.v[r][2] = m.y;
-      P.v[r][3] = m.z;
-      P.v[r][4] = m.w;
-      P.v[r][5] = x0 + 4 < W ? ld1(p + r * W + 4) : 0.f;
+#pragma unroll
+      for (int i = 0; i < PW; ++i) P.v[r][1 + i] = m[i];
+      P.v[r][PW + 1] = x0 + PW < W ? ld1(p + r * W + PW) : 0.f;
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) P.v[r][i] = 0.f;
+      for (int i = 0; i < PW + 2; ++i) P.v[r][i] = 0.f;
     }
   }
 }
 
-template <int ROWS>
-__device__ __forceinline__ void conv_patch(const Patch<ROWS>& P, const float (&w)[9], float (&o)[ROWS][4]) {
+template <int ROWS, int PW>
+__device__ __forceinline__ void conv_patch(const Patch<ROWS, PW>& P, const float (&w)[9], float (&o)[ROWS][PW]) {
 #pragma unroll
   for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < PW; ++j) {
       float acc = 0.f;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
@@ -94,7 +117,7 @@ __device__ __forceinline__ void conv_patch(const Patch<ROWS>& P, const float (&w
 // Which (image, plane, patch) a thread owns.  pshift < 0: large planes, the plane is (blockIdx.y, blockIdx.z);
 // otherwise 2^pshift (>= patches per plane) threads per plane and 256 >> pshift planes per CTA.
 struct DwGeom {
-  int H, W, pw, ppp, planes, pshift, ROWSv;
+  int H, W, pw, ppp, planes, pshift, ROWSv, PWv;   // PWv: pixels per patch row (4: fp32, 8: bf16)
 };
 struct DwThread {
   int b, ch, y, x0;
@@ -119,7 +142,7 @@ __device__ __forceinline__ DwThread dw_map(const DwGeom& g, int rows) {
   }
   const int py = patch / g.pw;
   t.y = py * rows;
-  t.x0 = (patch - py * g.pw) * 4;
+  t.x0 = (patch - py * g.pw) * g.PWv;
   return t;
 }
 __device__ __forceinline__ float warp_sum_dw(float v) {
@@ -138,18 +161,19 @@ __global__ void __launch_bounds__(256)
   float wk[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) wk[i] = __ldg(w + t.ch * 9 + (flip ? 8 - i : i));
-  float o[ROWS][4];
+  constexpr int PW = RowW<T>::PW;
+  float o[ROWS][PW];
   float sq = 0.f;
   if (t.active) {
-    Patch<ROWS> P;
-    load_patch<ROWS>(P, in + (size_t)t.b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
-    conv_patch<ROWS>(P, wk, o);
+    Patch<ROWS, PW> P;
+    load_patch<ROWS, T>(P, in + (size_t)t.b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+    conv_patch<ROWS, PW>(P, wk, o);
     T* op = out + (size_t)t.b * out_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      st4(op + r * g.W, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
+      strow(op + r * g.W, o[r]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < PW; ++j) {
         const float v = stored(op, o[r][j]);
         sq = fmaf(v, v, sq);
       }
@@ -183,32 +207,34 @@ __global__ void __launch_bounds__(256)
     w0[i] = __ldg(w + t.ch * 9 + i);
     w1[i] = __ldg(w + (t.ch + hid) * 9 + i);
   }
+  constexpr int PW = RowW<T>::PW;
   const T* inb = in + (size_t)t.b * in_bs;
-  float a[ROWS][4], gt[ROWS][4];
+  float a[ROWS][PW], gt[ROWS][PW];
   {
-    Patch<ROWS> P;
-    load_patch<ROWS>(P, inb + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
-    conv_patch<ROWS>(P, w0, a);
+    Patch<ROWS, PW> P;
+    load_patch<ROWS, T>(P, inb + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+    conv_patch<ROWS, PW>(P, w0, a);
   }
   {
-    Patch<ROWS> P;
-    load_patch<ROWS>(P, inb + (size_t)(t.ch + hid) * HW, t.y, t.x0, g.H, g.W);
-    conv_patch<ROWS>(P, w1, gt);
+    Patch<ROWS, PW> P;
+    load_patch<ROWS, T>(P, inb + (size_t)(t.ch + hid) * HW, t.y, t.x0, g.H, g.W);
+    conv_patch<ROWS, PW>(P, w1, gt);
   }
   const int pix = t.y * g.W + t.x0;
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
     const int pr = pix + r * g.W;
     if (MODE == 1) {
-      st4(out + (size_t)t.b * out_bs + (size_t)t.ch * HW + pr,
-          make_float4(gelu_fast(a[r][0]) * gt[r][0], gelu_fast(a[r][1]) * gt[r][1], gelu_fast(a[r][2]) * gt[r][2],
-                      gelu_fast(a[r][3]) * gt[r][3]));
-    } else {
-      const float4 d4 = ld4(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pr);
-      const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-      float da[4], db[4], gg[4];
+      float gv[PW];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < PW; ++j) gv[j] = gelu_fast(a[r][j]) * gt[r][j];
+      strow(out + (size_t)t.b * out_bs + (size_t)t.ch * HW + pr, gv);
+    } else {
+      float d[PW];
+      ldrow(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pr, d);
+      float da[PW], db[PW], gg[PW];
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
         float ga, dga;
         gelu_pair(a[r][j], ga, dga);
         da[j] = d[j] * gt[r][j] * dga;
@@ -216,9 +242,9 @@ __global__ void __launch_bounds__(256)
         gg[j] = ga * gt[r][j];
       }
       T* ob = out + (size_t)t.b * out_bs;
-      st4(ob + (size_t)t.ch * HW + pr, make_float4(da[0], da[1], da[2], da[3]));
-      st4(ob + (size_t)(t.ch + hid) * HW + pr, make_float4(db[0], db[1], db[2], db[3]));
-      if (g_out) st4(g_out + (size_t)t.b * g_bs + (size_t)t.ch * HW + pr, make_float4(gg[0], gg[1], gg[2], gg[3]));
+      strow(ob + (size_t)t.ch * HW + pr, da);
+      strow(ob + (size_t)(t.ch + hid) * HW + pr, db);
+      if (g_out) strow(g_out + (size_t)t.b * g_bs + (size_t)t.ch * HW + pr, gg);
     }
   }
 }
@@ -229,6 +255,7 @@ __global__ void __launch_bounds__(256)
     dw_bwd2_kernel(const T* __restrict__ in, int64_t in_bs, const T* __restrict__ dout, int64_t dout_bs,
                    const float* __restrict__ w, T* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
                    const DwGeom g, const int ppt, const int ipc, const int B) {
+  constexpr int PW = RowW<T>::PW;
   DwThread t = dw_map(g, ROWS);
   const int HW = g.H * g.W;
   float acc[9];
@@ -249,25 +276,25 @@ __global__ void __launch_bounds__(256)
       t.active = patch < g.ppp;
       const int py = (t.active ? patch : 0) / g.pw;
       t.y = py * ROWS;
-      t.x0 = ((t.active ? patch : 0) - py * g.pw) * 4;
+      t.x0 = ((t.active ? patch : 0) - py * g.pw) * PW;
     }
     if (!t.active) continue;
-    float d[ROWS][4];
+    float d[ROWS][PW];
     {
-      Patch<ROWS> P;
-      load_patch<ROWS>(P, dout + (size_t)b * dout_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
-      float o[ROWS][4];
-      conv_patch<ROWS>(P, wf, o);
+      Patch<ROWS, PW> P;
+      load_patch<ROWS, T>(P, dout + (size_t)b * dout_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+      float o[ROWS][PW];
+      conv_patch<ROWS, PW>(P, wf, o);
       T* dp = din + (size_t)b * din_bs + (size_t)t.ch * HW + t.y * g.W + t.x0;
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) {
-        st4(dp + r * g.W, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
+        strow(dp + r * g.W, o[r]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) d[r][j] = P.v[r + 1][j + 1];   // centre rows of dout
+        for (int j = 0; j < PW; ++j) d[r][j] = P.v[r + 1][j + 1];   // centre rows of dout
       }
     }
-    Patch<ROWS> Q;
-    load_patch<ROWS>(Q, in + (size_t)b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+    Patch<ROWS, PW> Q;
+    load_patch<ROWS, T>(Q, in + (size_t)b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
@@ -275,7 +302,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[ky * 3 + kx] = fmaf(d[r][j], Q.v[r + ky][j + kx], acc[ky * 3 + kx]);
+          for (int j = 0; j < PW; ++j) acc[ky * 3 + kx] = fmaf(d[r][j], Q.v[r + ky][j + kx], acc[ky * 3 + kx]);
   }
   }
   // reduce the 9 tap sums over the threads that share a channel, one atomicAdd per group
@@ -524,11 +551,12 @@ static int dw_rows_forced() {   // 0: per-kernel default
   }
   return pref;
 }
-static bool dw_geom(DwGeom& g, dim3& grid, int B, int planes, int H, int W, int rows) {
-  if (W % 4 != 0 || H % rows != 0 || B > 65535) return false;
+static bool dw_geom(DwGeom& g, dim3& grid, int B, int planes, int H, int W, int rows, int PW = 4) {
+  if (W % PW != 0 || H % rows != 0 || B > 65535) return false;
   g.H = H;
   g.W = W;
-  g.pw = W / 4;
+  g.PWv = PW;
+  g.pw = W / PW;
   g.ppp = g.pw * (H / rows);
   g.planes = planes;
   g.ROWSv = rows;
@@ -549,7 +577,9 @@ static bool dw_geom(DwGeom& g, dim3& grid, int B, int planes, int H, int W, int 
 
 template <typename T>
 static int dwconv_fast_t(const rcot_dw_params& p, int planes, cudaStream_t st) {
-  const bool al = p.in_bs % 4 == 0 && p.out_bs % 4 == 0 && ((uintptr_t)p.in % 16 == 0) && ((uintptr_t)p.out % 16 == 0);
+  constexpr int PWT = RowW<T>::PW;
+  const bool al = p.in_bs % PWT == 0 && p.out_bs % PWT == 0 && ((uintptr_t)p.in % 16 == 0) && ((uintptr_t)p.out % 16 == 0) &&
+                  (PWT == 4 || (p.dg_bs % PWT == 0 && p.g_bs % PWT == 0));
   if (!al) return 0;
   const T* in = reinterpret_cast<const T*>(p.in);
   T* out = reinterpret_cast<T*>(p.out);
@@ -558,11 +588,11 @@ static int dwconv_fast_t(const rcot_dw_params& p, int planes, cudaStream_t st) {
   DwGeom g;
   dim3 grid;
   if (p.mode == 0) {
-    if (dw_geom(g, grid, p.B, planes, p.H, p.W, 4)) {
+    if (dw_geom(g, grid, p.B, planes, p.H, p.W, 4, RowW<T>::PW)) {
       dw_plain_kernel<4, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.flip, p.sumsq, p.nsq, g);
       return 1;
     }
-    if (dw_geom(g, grid, p.B, planes, p.H, p.W, 2)) {
+    if (dw_geom(g, grid, p.B, planes, p.H, p.W, 2, RowW<T>::PW)) {
       dw_plain_kernel<2, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.flip, p.sumsq, p.nsq, g);
       return 1;
     }
@@ -572,8 +602,8 @@ static int dwconv_fast_t(const rcot_dw_params& p, int planes, cudaStream_t st) {
   // C=96, 128x128, B=32); the gate backward holds three more planes in registers and is faster with 4x2 patches
   // (557 vs 695 us).  RCOT_DW_ROWS=2|4 forces one shape for both (A/B switch).
   const int want = dw_rows_forced() ? dw_rows_forced() : (p.mode == 1 ? 4 : 2);
-  const int rows = (want == 4 && p.H % 4 == 0 && dw_geom(g, grid, p.B, planes, p.H, p.W, 4)) ? 4 : 2;
-  if (rows == 2 && !dw_geom(g, grid, p.B, planes, p.H, p.W, 2)) return 0;
+  const int rows = (want == 4 && p.H % 4 == 0 && dw_geom(g, grid, p.B, planes, p.H, p.W, 4, RowW<T>::PW)) ? 4 : 2;
+  if (rows == 2 && !dw_geom(g, grid, p.B, planes, p.H, p.W, 2, RowW<T>::PW)) return 0;
   if (p.mode == 1) {
     if (rows == 4)
       dw_gate_kernel<1, 4, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
@@ -600,8 +630,8 @@ static int dwconv_bwd_fast_t(const T* in, int64_t in_bs, const T* dout, int64_t 
   DwGeom g;
   dim3 grid;
   const int want = dw_rows_forced() ? dw_rows_forced() : 4;   // 4x4 patches: 669 vs 755 us at C=96, 128x128, B=32
-  const int rows = (want == 4 && H % 4 == 0 && dw_geom(g, grid, B, Cn, H, W, 4)) ? 4 : 2;
-  if (rows == 2 && !dw_geom(g, grid, B, Cn, H, W, 2)) return 0;
+  const int rows = (want == 4 && H % 4 == 0 && dw_geom(g, grid, B, Cn, H, W, 4, RowW<T>::PW)) ? 4 : 2;
+  if (rows == 2 && !dw_geom(g, grid, B, Cn, H, W, 2, RowW<T>::PW)) return 0;
   int ppt = 1;
   if (g.pshift < 0) {   // large planes: up to 4 patches per thread
     ppt = g.ppp / 256;

