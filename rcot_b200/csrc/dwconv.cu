@@ -33,28 +33,21 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
-// Row segments of PW output pixels: PW = 4 for fp32 (16 bytes), 8 for bf16 (16 bytes): one vector access per row either
-// way, so the bf16 kernels move half the bytes with the SAME number of memory instructions per byte moved.
+// Row segments of PW output pixels per thread and row.  PW = 4 for both storage types: 8-pixel rows for bf16 (16-byte
+// accesses) were measured SLOWER (gate forward 0.51 vs 0.45 ms, fused backward 1.08 vs 0.79 ms at C=96, 128x128, B=32:
+// the patch doubles the live registers and halves the CTAs in flight) -- these stencils sit at the CUDA-core issue limit
+// once the bytes are halved, so the bf16 mode buys memory, not time, here.
 template <typename T> struct RowW { static constexpr int PW = 4; };
-template <> struct RowW<__nv_bfloat16> { static constexpr int PW = 8; };
 __device__ __forceinline__ void ldrow(const float* p, float (&v)[4]) {
   const float4 m = ld4(p);
   v[0] = m.x; v[1] = m.y; v[2] = m.z; v[3] = m.w;
 }
-__device__ __forceinline__ void ldrow(const __nv_bfloat16* p, float (&v)[8]) {
-  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
-  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
-  v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
-  v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+__device__ __forceinline__ void ldrow(const __nv_bfloat16* p, float (&v)[4]) {
+  const float4 m = ld4(p);
+  v[0] = m.x; v[1] = m.y; v[2] = m.z; v[3] = m.w;
 }
 __device__ __forceinline__ void strow(float* p, const float (&v)[4]) { st4(p, make_float4(v[0], v[1], v[2], v[3])); }
-__device__ __forceinline__ void strow(__nv_bfloat16* p, const float (&v)[8]) {
-  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-  const __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
-                                            *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
-}
+__device__ __forceinline__ void strow(__nv_bfloat16* p, const float (&v)[4]) { st4(p, make_float4(v[0], v[1], v[2], v[3])); }
 
 // the value a store of v will leave in memory (so that sums of squares match what later kernels read)
 __device__ __forceinline__ float stored(const float*, float v) { return v; }

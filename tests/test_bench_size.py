@@ -123,23 +123,38 @@ def test_full_iteration_128(cuda_lib, paired):
                                    for k, v in gref.items()}, 3e-3, "GP (initial weights)", tol_tensor=1e-2)
     Fp.ps.flat.copy_(Ff)
     Fp.ps.repack()
-    if not paired:
-        _cmp_grads(Tp.ps, step.capture["T"], o["grads_T"], 3e-3, "T-sub (unpaired)")
-        return
-    # paired: drive our T backward (initial weights) with the oracle's dL/dout
+    # ---- T-sub.  Inside the iteration dL/dout contains dF/dout of the potential AFTER its two sign-like steps (our
+    # weights and the oracle's differ by +-10*lr on ~zero-gradient entries), so the transport gradient is checked in two
+    # exact halves instead: (a) our cost kernels + F input gradient with the ORACLE's updated potential -> dL/dout;
+    # (b) our T backward (initial weights) driven by the oracle's dL/dout -> every weight gradient.
     out_o = o["out"].clone().requires_grad_(True)
     with torch.enable_grad():
-        lossT, _ = R.transport_loss(out_o, deg, tgt, R.fnet_forward(F_sd, out_o), de_id, 1.0, 10000.0, True)
+        lossT, _ = R.transport_loss(out_o, deg, tgt, R.fnet_forward(F_sd, out_o), de_id, 1.0, 10000.0, paired)
     lossT.backward()
-    away = (o["out"] - tgt).abs() > 1e-4
-    torch.testing.assert_close(step.capture["dout"].cpu()[away], out_o.grad[away], rtol=2e-3, atol=2e-4)
+    dref = out_o.grad
+    for k, off in Fp.ps.offsets.items():
+        Fp.ps.flat[off:off + F_sd[k].numel()].copy_(F_sd[k].flatten())
+    Fp.ps.repack()
+    out_g = o["out"].cuda()
+    fv, dF = Fp.input_grad(out_g, -1.0 / B)
+    acc = torch.zeros(4, device="cuda")
+    gfou = torch.empty_like(out_g)
+    tg = tgt.cuda() if paired else None
+    ops.cost_stage1(out_g, deg.cuda(), tg, de_id.cuda(), gfou, acc)
+    dout = torch.empty_like(out_g)
+    ops.cost_stage2(out_g, deg.cuda(), tg, gfou, dF, acc, dout, 1.0, 10000.0, float(B * 3 * P * P))
+    away = ((o["out"] - tgt).abs() > 1e-4) if paired else torch.ones_like(tgt, dtype=torch.bool)
+    # (the Fourier |F| branch divides by |F|: bins with |F| ~ 0 are the only loose elements)
+    err = (dout.cpu()[away] - dref[away]).norm() / dref[away].norm()
+    print(f"dL/dout vs oracle (same potential): rel-L2 {err.item():.2e}")
+    assert err < 2e-3, err
     Tp.ps.flat.copy_(Tflat0)
     Tp.ps.repack()
     Tp.ps.zero_grad()
     tape = Tape(save_hidden=True)
     out = Tp.forward(deg.cuda(), tape)
-    tape.backward(out, out_o.grad.cuda())
-    _cmp_grads(Tp.ps, Tp.ps.grad, o["grads_T"], 3e-3, "T-sub (paired, oracle dL/dout)")
+    tape.backward(out, dref.cuda())
+    _cmp_grads(Tp.ps, Tp.ps.grad, o["grads_T"], 3e-3, f"T-sub ({'paired' if paired else 'unpaired'}, oracle dL/dout)")
 
 
 def test_batch32_equals_sum_of_shards(cuda_lib):
