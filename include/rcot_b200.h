@@ -94,6 +94,15 @@ typedef struct {
   int32_t in_bf16;      /* bf16-storage mode: `in` is a bf16 tensor (1x1, no LayerNorm, no concat, H*W % 128 == 0): the A
                            operand is exact in bf16, so its lo term and the fp32->bf16 split disappear */
   int32_t out_bf16;     /* `out` is a bf16 tensor (1x1, plain epilogue: no bias/activation/mask/residual/accumulate/stats) */
+  /* LayerNorm-BACKWARD epilogue (1x1, N = C <= 256; Net_Restormer.py:186-189 differentiated): the GEMM result is
+   * dz = dL/dLN(x); out = [residual +] LN'(dz) with x / (mean, rstd) / gamma of that LayerNorm, and
+   * lnb_dgamma += sum dz * xhat, lnb_dbeta += sum dz.  lnb_x == NULL: off. */
+  const float* lnb_x;
+  int64_t lnb_x_bs;
+  const float* lnb_stats;
+  const float* lnb_gamma;
+  float* lnb_dgamma;
+  float* lnb_dbeta;
 } rcot_pm_params;
 
 int rcot_pm_gemm(const rcot_pm_params* p, rcot_stream_t stream);

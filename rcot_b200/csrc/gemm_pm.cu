@@ -49,7 +49,10 @@ struct PmGeom {
 };
 
 // ABF / OBF (1x1 TMA variant only): the gather source / the output is a bf16 tensor (bf16-storage mode).
-template <int KS, int MODE, int TERMS, bool LN, bool TMA, int ABF = 0, int OBF = 0>
+// LNB: LayerNorm-BACKWARD epilogue (1x1, N = C <= 256 = one pass): the accumulator row of a pixel is dz = dL/dLN(x);
+// the epilogue turns it into dx = [dy +] rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dz * gamma, and accumulates
+// dgamma += sum_p dz * xhat, dbeta += sum_p dz -- the separate ln_bwd pass (read dz, x, dy; write dx) disappears.
+template <int KS, int MODE, int TERMS, bool LN, bool TMA, int ABF = 0, int OBF = 0, bool LNB = false>
 __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
     pm_gemm_kernel(const rcot_pm_params p, const PmGeom g, const __grid_constant__ CUtensorMap tm1,
                    const __grid_constant__ CUtensorMap tm2) {
@@ -57,8 +60,14 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
   __shared__ uint64_t full_bar[PM_MAX_STAGES], empty_bar[PM_MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint64_t raw_full[PM_RAW], raw_empty[PM_RAW];
   __shared__ uint32_t tmem_base_s;
+  // LNB: per epilogue warp a 32 x 33 transpose pad (column sums over the warp's 32 pixels) and 2 x 256 running sums
+  __shared__ float lnb_scr[LNB ? 4 * 32 * 33 : 1];
+  __shared__ float lnb_acc[LNB ? 4 * 512 : 1];
   constexpr int TA = (TERMS > 1) ? 2 : 1;
   constexpr int TAA = ABF ? 1 : TA;        // operand images of A: a bf16-stored A has no lo term
+  static_assert(!LNB || (KS == 1 && !LN && !OBF), "LayerNorm-backward epilogue: 1x1 kernels with an fp32 output");
+  if (LNB)
+    for (int i = threadIdx.x; i < 4 * 512; i += blockDim.x) lnb_acc[i] = 0.f;
   static_assert(!(ABF || OBF) || (TMA && KS == 1 && !(ABF && LN)), "bf16 storage: TMA-staged 1x1 kernels only");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -579,6 +588,73 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
+      if (LNB) {
+        // ---------------- LayerNorm backward on the accumulator row (single pass: nbase = 0, all N = C columns)
+        const int Cn = p.N, ng = (Cn + 15) >> 4;
+        const uint32_t tb = lane_base + buf * BN;
+        const size_t po = (size_t)b * HWr + pix;
+        float mu = 0.f, rstd = 0.f;
+        if (valid) {
+          const float2 st2 = __ldg(reinterpret_cast<const float2*>(p.lnb_stats) + po);
+          mu = st2.x;
+          rstd = st2.y;
+        }
+        const float* xr = p.lnb_x + (size_t)b * p.lnb_x_bs + pix;
+        const float* dyr = p.residual ? p.residual + (size_t)b * p.res_bs + pix : nullptr;
+        float* orow = p.out + (size_t)b * p.out_bs + pix;
+        float* scr = lnb_scr + (warp & 3) * (32 * 33);
+        float* accw = lnb_acc + (warp & 3) * 512;
+        float s1 = 0.f, s2 = 0.f;
+        for (int gi = 0; gi < ng; ++gi) {
+          float dz[16], xv[16];
+          tmem_ld16(tb + gi * 16, dz);
+          const int nrem = Cn - gi * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xv[i] = (valid && i < nrem) ? __ldg(xr + (size_t)(gi * 16 + i) * HWr) : 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool ok = valid && i < nrem;
+            const float xh = (xv[i] - mu) * rstd;
+            const float d = ok ? dz[i] : 0.f;
+            const float gq = d * (i < nrem ? __ldg(p.lnb_gamma + gi * 16 + i) : 0.f);
+            s1 += gq;
+            s2 = fmaf(gq, xh, s2);
+            scr[lane * 33 + i] = d * xh;          // -> dgamma
+            scr[lane * 33 + 16 + i] = d;          // -> dbeta
+          }
+          __syncwarp();
+          float tcol = 0.f;
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) tcol += scr[l * 33 + lane];
+          accw[gi * 32 + lane] += tcol;           // lane < 16: dgamma of channel gi*16+lane; else dbeta of gi*16+lane-16
+          __syncwarp();
+        }
+        const float invC = 1.f / (float)Cn;
+        const float m1 = s1 * invC, m2 = s2 * invC;
+        for (int gi = 0; gi < ng; ++gi) {
+          float dz[16], xv[16], dyv[16];
+          tmem_ld16(tb + gi * 16, dz);
+          const int nrem = Cn - gi * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool ok = valid && i < nrem;
+            xv[i] = ok ? __ldg(xr + (size_t)(gi * 16 + i) * HWr) : 0.f;
+            dyv[i] = (ok && dyr) ? __ldg(dyr + (size_t)(gi * 16 + i) * HWr) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (valid && i < nrem) {
+              const float xh = (xv[i] - mu) * rstd;
+              const float gq = dz[i] * __ldg(p.lnb_gamma + gi * 16 + i);
+              orow[(size_t)(gi * 16 + i) * HWr] = dyv[i] + rstd * (gq - m1 - xh * m2);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
       const int nbase = (pass / nslice) * g.BNf + (pass % nslice) * BN;
       float* o = p.out + (size_t)b * p.out_bs + (size_t)(p.out_coff + nbase) * HWr + pix;
       const float* mk = p.mask_y ? p.mask_y + (size_t)b * p.mask_bs + (size_t)nbase * HWr + pix : nullptr;
@@ -683,6 +759,15 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
+  if (LNB && warp >= PM_PROD_WARPS + 1 && warp < PM_PROD_WARPS + 5) {
+    // flush this warp's running column sums (every lane only ever touched its own slots)
+    const float* accw = lnb_acc + (warp & 3) * 512;
+    const int ng = (p.N + 15) >> 4;
+    for (int gi = 0; gi < ng; ++gi) {
+      const int ch = gi * 16 + (lane & 15);
+      if (ch < p.N) atomicAdd((lane < 16 ? p.lnb_dgamma : p.lnb_dbeta) + ch, accw[gi * 32 + lane]);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, g.tmem_cols);
@@ -690,7 +775,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
 
 static int g_num_sms = 0;
 
-template <int KS, int MODE, int TERMS, bool LN, bool TMA = false, int ABF = 0, int OBF = 0>
+template <int KS, int MODE, int TERMS, bool LN, bool TMA = false, int ABF = 0, int OBF = 0, bool LNB = false>
 static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   PmGeom g;
   g.Ktot = (p.C1 + p.C2) * KS * KS;
@@ -718,7 +803,8 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
   g.c1_aligned = (p.C2 == 0 || p.C1 % 16 == 0) ? 1 : 0;
   const size_t raw_bytes = TMA ? (size_t)PM_RAW * PM_RAW_BYTES : 0;
-  int stages = (int)((196 * 1024 - raw_bytes - ln_bytes) / stage_bytes);
+  const size_t lnb_bytes = LNB ? (4 * 32 * 33 + 4 * 512) * sizeof(float) : 0;    // static shared memory of the LNB epilogue
+  int stages = (int)((196 * 1024 - raw_bytes - ln_bytes - lnb_bytes) / stage_bytes);
   if (stages > PM_MAX_STAGES) stages = PM_MAX_STAGES;
   if (stages < 2) stages = 2;
   g.stages = stages;
@@ -742,7 +828,7 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   RCOT_REQUIRE(smem <= 208 * 1024, "pm_gemm: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN, TMA, ABF, OBF>,
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN, TMA, ABF, OBF, LNB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) {
       set_error("pm_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -766,7 +852,7 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
     if (rc == RCOT_OK && p.in2) rc = make_act_map(&tm2, p.in2, p.in2_bs, p.C2, HWr, p.B, 128, KC, "pm_gemm");
     if (rc != RCOT_OK) return rc;
   }
-  pm_gemm_kernel<KS, MODE, TERMS, LN, TMA, ABF, OBF><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g, tm1, tm2);
+  pm_gemm_kernel<KS, MODE, TERMS, LN, TMA, ABF, OBF, LNB><<<grid, PM_THREADS + (TMA ? 32 : 0), smem, stream>>>(p, g, tm1, tm2);
   return check_launch("pm_gemm");
 }
 
@@ -810,6 +896,21 @@ extern "C" int rcot_pm_gemm(const rcot_pm_params* pp, rcot_stream_t stream_) {
       const bool tma = tma_on && tensor_map_encoder() != nullptr && HW % 128 == 0 && p.in_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 &&
                        (p.in2 == nullptr || (p.C1 % 32 == 0 && p.in2_bs % 4 == 0 &&
                                              (reinterpret_cast<uintptr_t>(p.in2) & 15) == 0));
+      if (p.lnb_x) {
+        // LayerNorm-backward epilogue (the dz GEMM of a block's backward)
+        RCOT_REQUIRE(p.lnb_stats && p.lnb_gamma && p.lnb_dgamma && p.lnb_dbeta, "pm_gemm: LayerNorm-backward epilogue needs "
+                     "stats, gamma, dgamma and dbeta");
+        RCOT_REQUIRE(p.N <= 256 && !ln && !p.out_bf16 && !p.bias && !p.act && !p.mask_y && !p.accumulate && !p.stats_out &&
+                     p.out_coff == 0 && p.in2 == nullptr && p.wpack_bs == 0,
+                     "pm_gemm: LayerNorm-backward epilogue needs N <= 256 and the plain / residual epilogue");
+        RCOT_REQUIRE(!p.in_bf16 || tma, "pm_gemm: bf16 input needs the TMA-staged path");
+#define PM_LNB(T, A) \
+  return (p.terms == 3) ? launch_pm<1, 0, 3, false, T, A, 0, true>(p, stream) : launch_pm<1, 0, 1, false, T, A, 0, true>(p, stream)
+        if (tma && p.in_bf16) { PM_LNB(true, 1); }
+        if (tma) { PM_LNB(true, 0); }
+        PM_LNB(false, 0);
+#undef PM_LNB
+      }
       if (p.in_bf16 || p.out_bf16) {
         // bf16-storage mode of the hidden tensors: TMA-staged kernels only
         RCOT_REQUIRE(tma && p.in2 == nullptr, "pm_gemm: bf16 tensors need the TMA-staged 1x1 path (H*W %% 128 == 0, 16-byte "

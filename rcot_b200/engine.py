@@ -27,6 +27,9 @@ FUSED_GDFN_MID = os.environ.get("RCOT_FUSED_GDFN_MID", "0") == "1"
 # but it is bound by its per-slice synchronisation and the CUDA-core stencil, not by HBM: measured 1.46 ms vs 0.97 ms
 # for the three launches at C=96, 128x128, B=32 -- so the three-launch path stays the default.
 FUSED_GDFN = os.environ.get("RCOT_FUSED_GDFN", "0") == "1"
+# RCOT_LNB_EPILOGUE=0: LayerNorm backward as its own kernel again (A/B switch); default: inside the epilogue of the GEMM
+# that produces dL/dLN(x) (C <= 256), which drops two passes over the block tensor and one launch per sub-block.
+LNB_EPILOGUE = os.environ.get("RCOT_LNB_EPILOGUE", "1") == "1"
 
 
 # ---------------------------------------------------------------------------------- parameters
@@ -310,6 +313,10 @@ def mdta_bwd(bs: BlockSpec, x, dy, norm_name, residual, ctx):
     dpre = ops.dwconv_bwd(pre, dqkv, ps.p[a + "qkv_dwconv.weight"], ps.g[a + "qkv_dwconv.weight"])
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
     ops.pk_gemm(dpre, x, ps.g[a + "qkv.weight"], ldo=C, ln=ln)
+    if norm_name and LNB_EPILOGUE and C <= 256:
+        return ops.pm_gemm(dpre, ps.pack(a + "qkv.weight", "dgrad"), C, residual=dy if residual else None,
+                           lnb=(x, stats, ps.p[norm_name + ".body.weight"], ps.g[norm_name + ".body.weight"],
+                                ps.g[norm_name + ".body.bias"]))
     dz = ops.pm_gemm(dpre, ps.pack(a + "qkv.weight", "dgrad"), C, residual=None if norm_name or not residual else dy)
     if not norm_name:
         return dz
@@ -366,6 +373,10 @@ def gdfn_bwd(bs: BlockSpec, x, dy, norm_name, residual, kept=None):
         du = ops.dwconv_bwd(u, dab, ps.p[f + "dwconv.weight"], ps.g[f + "dwconv.weight"])
         del dab, u
     ops.pk_gemm(du, x, ps.g[f + "project_in.weight"], ldo=C, ln=ln)
+    if norm_name and LNB_EPILOGUE and C <= 256:
+        return ops.pm_gemm(du, ps.pack(f + "project_in.weight", "dgrad"), C, residual=dy if residual else None,
+                           lnb=(x, stats, ps.p[norm_name + ".body.weight"], ps.g[norm_name + ".body.weight"],
+                                ps.g[norm_name + ".body.bias"]))
     dz = ops.pm_gemm(du, ps.pack(f + "project_in.weight", "dgrad"), C,
                      residual=None if norm_name or not residual else dy)
     if not norm_name:

@@ -33,6 +33,8 @@ class PMParams(C.Structure):
         ("mask_y", C.c_void_p), ("mask_bs", C.c_int64), ("residual", C.c_void_p), ("res_bs", C.c_int64),
         ("stats_out", C.c_void_p), ("debug", C.c_int32), ("tap_major", C.c_int32),
         ("in_bf16", C.c_int32), ("out_bf16", C.c_int32),
+        ("lnb_x", C.c_void_p), ("lnb_x_bs", C.c_int64), ("lnb_stats", C.c_void_p), ("lnb_gamma", C.c_void_p),
+        ("lnb_dgamma", C.c_void_p), ("lnb_dbeta", C.c_void_p),
     ]
 
 
@@ -212,9 +214,11 @@ def pack_single(w: torch.Tensor, kind: str):
 # ------------------------------------------------------------------ pixel-as-M GEMM
 def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None, out_hw=None, out_coff=0,
             ln=None, bias=None, act=False, slope=0.2, mask_y=None, residual=None, accumulate=False,
-            wpack_bs=0, terms=None, debug=0, tap_major=False, stats_out=False, out_dtype=torch.float32):
+            wpack_bs=0, terms=None, debug=0, tap_major=False, stats_out=False, out_dtype=torch.float32, lnb=None):
     """out[b, coff+n, p] = epi(sum_k A(b,p,k) W[n,k]).  ``ln`` = (stats[B,HW,2], gamma, beta).
-    x may be a bf16 tensor and/or out_dtype (or ``out``) bf16: bf16-storage mode of the hidden tensors (1x1 only)."""
+    x may be a bf16 tensor and/or out_dtype (or ``out``) bf16: bf16-storage mode of the hidden tensors (1x1 only).
+    ``lnb`` = (x_ln, stats, gamma, dgamma, dbeta): LayerNorm-backward epilogue -- the GEMM result is dL/dLN(x_ln) and
+    out = [residual +] LN'(.) while dgamma / dbeta are accumulated (N <= 256)."""
     B, C1, Hs, Ws = x.shape
     in_bs = _img_view(x, "x", True)
     C2 = 0 if x2 is None else x2.shape[1]
@@ -248,6 +252,10 @@ def pm_gemm(x, wpack_ptr, N, *, ks=1, stride=1, pad=0, mode=0, x2=None, out=None
         st = torch.empty(B, Hr * Wr, 2, device=x.device, dtype=torch.float32)
         p.stats_out = st.data_ptr()
     p.bias = None if bias is None else _f32(bias).data_ptr()
+    if lnb is not None:
+        xl, stl, gl, dgl, dbl = lnb
+        p.lnb_x, p.lnb_x_bs, p.lnb_stats = xl.data_ptr(), _img_view(xl, "lnb x"), _f32(stl).data_ptr()
+        p.lnb_gamma, p.lnb_dgamma, p.lnb_dbeta = _f32(gl).data_ptr(), _f32(dgl).data_ptr(), _f32(dbl).data_ptr()
     if mask_y is not None:
         p.mask_y, p.mask_bs = mask_y.data_ptr(), _img_view(mask_y, "mask_y")
     if residual is not None:
@@ -621,7 +629,8 @@ def _pm_bytes(a, k, r):
     x, N = a[0], a[2]
     ks = k.get("ks", 1)
     Kdim = (x.shape[1] + (k["x2"].shape[1] if k.get("x2") is not None else 0)) * ks * ks
-    return (_nb(x, k.get("x2"), k.get("residual"), k.get("mask_y")) + r.shape[0] * N * r.shape[2] * r.shape[3] * 4 +
+    return (_nb(x, k.get("x2"), k.get("residual"), k.get("mask_y"), k["lnb"][0] if k.get("lnb") else None) +
+            r.shape[0] * N * r.shape[2] * r.shape[3] * r.element_size() +
             N * Kdim * 4 * (r.shape[0] if k.get("wpack_bs", 0) else 1))
 
 

@@ -43,13 +43,16 @@ def main():
         assert one.world == 1
         one.capture = {}
         r1 = one.iteration(deg.cuda(), tgt.cuda(), de_id.cuda(), alpha.cuda(), paired, 1e-4)
-        for k in ("loss_F", "loss_gp", "loss_T", "loss_mse"):
+        for k, tol in (("loss_F", 1e-5), ("loss_gp", 2e-3), ("loss_T", 2e-3), ("loss_mse", 1e-5)):
             a, b = r[k].item(), r1[k].item()
-            assert abs(a - b) <= 1e-5 * abs(b) + 1e-7, (k, a, b)
-        for k in ("F", "GP", "T"):
+            assert abs(a - b) <= tol * abs(b) + 1e-7, (k, a, b)
+        # F-sub is evaluated at IDENTICAL weights in both runs: sharding + all-reduce must reproduce it to fp32 summation
+        # order.  GP and T-sub are evaluated after the potential's sign-like first RMSprop step(s) (+-10*lr per weight
+        # whatever |g|: ~zero gradients flip between any two summation orders), so they carry that step's 1e-3-class noise.
+        for k, tol in (("F", 5e-5), ("GP", 1e-2), ("T", 1e-2)):
             a, b = dp.capture[k].double(), one.capture[k].double()
             err = ((a - b).norm() / b.norm()).item()
-            assert err < 2e-5, (paired, k, err)
+            assert err < tol, (paired, k, err)
             if rank == 0:
                 print(f"paired={paired} grads {k}: 2 ranks x {B // world} vs 1 x {B}: rel-L2 {err:.2e}")
         # post-step weights: identical updates up to sign flips of ~zero gradients (RMSprop's first step is sign-like)
