@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
         if (!(p.debug & 8) || n < 2) mbar_wait(&winbar[n % GF_WIN_SLOTS], (uint32_t)(n / GF_WIN_SLOTS) & 1);
         if (n >= 2) mbar_wait(&dbar[n & 1], (uint32_t)((n - 2) >> 1) & 1);
         tc_fence_after();
-        if (lane == 0) issue_gemm1(n);
+        if (elect_one()) issue_gemm1(n);
         __syncwarp();
         // ---- weight prefetch for slice n+2: W_in slot of slice n-1 (GEMM-1(n-1) done), W_out slot of slice n-2
         if (n + 2 < total_slices && !(p.debug & 8)) {
@@ -192,14 +192,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
           mbar_wait(&sbar[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
           if (s == 1 && ti > 0) mbar_wait(&ybar, (uint32_t)(ti - 1) & 1);
           tc_fence_after();
-          if (lane == 0) issue_gemm2(n - 1, s == 1);
+          if (elect_one()) issue_gemm2(n - 1, s == 1);
           __syncwarp();
         }
       }
       mbar_wait(&sbar[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
       if (NS == 1 && ti > 0) mbar_wait(&ybar, (uint32_t)(ti - 1) & 1);
       tc_fence_after();
-      if (lane == 0) issue_gemm2(n - 1, NS == 1);
+      if (elect_one()) issue_gemm2(n - 1, NS == 1);
       __syncwarp();
     }
   } else {

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
     for (int it = 0; it < nchunks; ++it) {
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
         issue_stage<TERMS>(tmem, st, st + a_tile, st + TA * a_tile, st + TA * a_tile + b_tile, idesc, it == 0);
         tc_commit(&empty_bar[s]);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         ph ^= 1;
       }
     }
-    if (lane == 0 && nchunks > 0) tc_commit(&done_bar);
+    if (elect_one() && nchunks > 0) tc_commit(&done_bar);
   }
   if (warp < PK_PROD_WARPS && nchunks > 0) {
     mbar_wait(&done_bar, 0);
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
     for (int it = 0; it < nchunks; ++it) {
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t stg = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t b_hi = stg + TAA * MT * a_tile;
 #pragma unroll
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         ph ^= 1;
       }
     }
-    if (lane == 0 && nchunks > 0) tc_commit(&done_bar);
+    if (elect_one() && nchunks > 0) tc_commit(&done_bar);
   }
   if (warp < PK_PROD_WARPS && nchunks > 0) {
     mbar_wait(&done_bar, 0);
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
     for (int it = 0; it < nchunks; ++it) {
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
         issue_stage<TERMS, !ABF, !BBF>(tmem, st, st + a_tile, st + TAA * a_tile, st + TAA * a_tile + b_tile, idesc, it == 0);
         tc_commit(&empty_bar[s]);
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(PK_THREADS + 32, 1)
         ph ^= 1;
       }
     }
-    if (lane == 0 && nchunks > 0) tc_commit(&done_bar);
+    if (elect_one() && nchunks > 0) tc_commit(&done_bar);
   }
   if (warp < PK_PROD_WARPS && nchunks > 0) {
     mbar_wait(&done_bar, 0);

@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       for (int c = 0; c < nk; ++c) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
           issue_stage<TERMS, !ABF>(d, st, st + a_tile, st + TAA * a_tile, st + TAA * a_tile + b_tile, idesc, c == 0);
           tc_commit(&empty_bar[s]);
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
           ph ^= 1;
         }
       }
-      if (lane == 0) tc_commit(&acc_full[buf]);
+      if (elect_one()) tc_commit(&acc_full[buf]);
       __syncwarp();
     }
   } else if (warp < PM_PROD_WARPS + 5) {
@@ -825,11 +825,11 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
     g.nk = 4 * (p.C1 / 32);
   }
   const size_t smem = stages * stage_bytes + ln_bytes + raw_bytes;
-  RCOT_REQUIRE(smem <= 208 * 1024, "pm_gemm: %zu bytes of shared memory needed", smem);
+  RCOT_REQUIRE(smem + lnb_bytes <= 208 * 1024, "pm_gemm: %zu bytes of shared memory needed", smem + lnb_bytes);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<KS, MODE, TERMS, LN, TMA, ABF, OBF, LNB>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024 - lnb_bytes));
     if (e != cudaSuccess) {
       set_error("pm_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return RCOT_ERR_CUDA;

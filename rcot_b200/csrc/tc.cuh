@@ -117,6 +117,18 @@ __host__ __device__ inline uint32_t tmem_cols_pow2(uint32_t n) {
   return c;
 }
 
+// True in exactly one lane of a fully active warp (elect.sync): unlike `lane == 0` the compiler KNOWS the guarded code
+// runs in a single thread, so uniform-register operands (tcgen05.mma descriptors) need no waterfall loop per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, SWIZZLE_NONE, K-major (bit layout as documented for
 // sm_100 UMMA: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48)).

@@ -27,9 +27,12 @@ FUSED_GDFN_MID = os.environ.get("RCOT_FUSED_GDFN_MID", "0") == "1"
 # but it is bound by its per-slice synchronisation and the CUDA-core stencil, not by HBM: measured 1.46 ms vs 0.97 ms
 # for the three launches at C=96, 128x128, B=32 -- so the three-launch path stays the default.
 FUSED_GDFN = os.environ.get("RCOT_FUSED_GDFN", "0") == "1"
-# RCOT_LNB_EPILOGUE=0: LayerNorm backward as its own kernel again (A/B switch); default: inside the epilogue of the GEMM
-# that produces dL/dLN(x) (C <= 256), which drops two passes over the block tensor and one launch per sub-block.
-LNB_EPILOGUE = os.environ.get("RCOT_LNB_EPILOGUE", "1") == "1"
+# RCOT_LNB_EPILOGUE=1: LayerNorm backward inside the epilogue of the GEMM that produces dL/dLN(x) (C <= 256) instead of
+# its own kernel: two passes over the block tensor and 168 launches per step fewer -- but measured SLOWER (step 246.7 ->
+# 265.3 ms at B=32: pm_gemm +32.8 ms, ln_bwd -13.3 ms): the four epilogue warps of a CTA become the bottleneck of the
+# K-heavy dz GEMMs, while the stand-alone ln_bwd kernel spreads the same work over the whole chip.  Kept as an opt-in,
+# parity-tested variant (tests/test_lnb.py).
+LNB_EPILOGUE = os.environ.get("RCOT_LNB_EPILOGUE", "0") == "1"
 
 
 # ---------------------------------------------------------------------------------- parameters
