@@ -377,7 +377,12 @@ def run_b200(args):
     if not args.no_extra_configs and B == 32 and P == 128:
         if world > 1 and 32 % world == 0:
             Bs = 32 // world
-            m, gq, fin = side_run(Bs, True)
+            try:
+                m, gq, fin = side_run(Bs, True)
+            except Exception as e:          # e.g. a collective that cannot be captured: measure without the graph
+                print(f"bench: strong-scaling side run with CUDA graph failed ({type(e).__name__}: {e}); eager retry",
+                      file=sys.stderr)
+                m, gq, fin = side_run(Bs, True, graph=False)
             extras["strong"] = {"what": "same iteration, GLOBAL batch fixed at 32 (BASELINE config c3's shape)",
                                 "global_batch": 32, "per_gpu_batch": Bs, "value": 32 / (m / 1e3), "unit": UNIT,
                                 "ms_per_step": m, "cuda_graph": gq, "scaling": "strong", "finite": fin}
