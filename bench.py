@@ -225,6 +225,17 @@ def run_eager_baseline(args):
 
 
 # ---------------------------------------------------------------------------------- B200 arm
+def _finish(world):
+    """End of a rank: with CUDA graphs that captured NCCL collectives alive, destroy_process_group() was observed to
+    hang (2-GPU run: the JSON line printed, the process never exited).  Nothing of value remains to be torn down, so
+    multi-rank processes flush and leave without running the interpreter's / NCCL's destructors."""
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_b200(args):
     import Net_Restormer as N
     import trainer
@@ -441,8 +452,7 @@ def run_b200(args):
 
     barrier()
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        _finish(world)
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -488,9 +498,8 @@ def run_b200(args):
                                             "(torch-default TF32 convs), same patch size" +
                                             ("" if eager["tf32_default"]["batch"] == B else
                                              f"; the eager run fits only batch {eager['tf32_default']['batch']}")}
-    print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _finish(world)
 
 
 def main():

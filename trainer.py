@@ -365,6 +365,14 @@ def main(argv=None):
             with open("./checksample/" + opt.type + "/validation_results.txt", "a") as f:
                 f.write(f"Patchsize {opt.patch_size} Epoch {epoch}, psnr {p:.4f}, Batchsize {opt.batchSize}\n")
             save_checkpoint(Tnet, Fnet, epoch)
+    if world > 1:
+        # CUDA graphs that captured NCCL collectives are still alive: destroy_process_group() / interpreter teardown was
+        # observed to hang with them (bench.py, 2 GPUs) -- leave without running destructors
+        import sys
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
