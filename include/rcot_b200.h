@@ -32,6 +32,9 @@ int rcot_check_device(void);
 
 /* tcgen05 bring-up: D[128 x N] = A[128 x K] * B[N x K]^T */
 int rcot_selftest_tc(const float* A, const float* B, float* D, int N, int K, int terms, rcot_stream_t stream);
+/* same product with the A operand resident in TENSOR MEMORY (tcgen05.mma "TS" form; single bf16 term): bring-up of the
+ * TMEM operand layout for fused kernels that keep a tile's A operand on chip across many small MMAs */
+int rcot_selftest_tmem_a(const float* A, const float* B, float* D, int N, int K, int variant, rcot_stream_t stream);
 
 /* ---------------------------------------------------------------- packed weights
  * B-operand image of a [N x K] matrix in the tcgen05 no-swizzle K-major layout, bf16 hi+lo,

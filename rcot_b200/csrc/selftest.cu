@@ -75,7 +75,104 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
   if (warp == 0) tmem_dealloc(tmem, cols);
 }
 
+// ------------------------------------------------------------------ A operand from TMEM (tcgen05.mma "TS" form)
+// Bring-up for keeping a resident A operand (e.g. LN(x) of a tile) in tensor memory instead of shared memory: row m of A
+// lives in TMEM lane m, two bf16 K-elements per 32-bit column (variant 0: even k in the low half), written with
+// tcgen05.st by the thread that owns the lane; each k16 step of the MMA reads 8 columns.  Single bf16 term.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128) tc_selftest_tmema_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                                float* __restrict__ D, int N, int K, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t a_col = 256;                          // A: columns [256, 256 + K/2); D: columns [0, N)
+  // A -> TMEM: this thread owns lane tid
+  const uint32_t lane_addr = tmem_lane_base(tmem) + a_col;
+  for (int c8 = 0; c8 < K / 16; ++c8) {                // 8 columns = 16 K-elements per store
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float e0 = A[(size_t)tid * K + c8 * 16 + 2 * i], e1 = A[(size_t)tid * K + c8 * 16 + 2 * i + 1];
+      const __nv_bfloat162 pk = variant == 0 ? __floats2bfloat162_rn(e0, e1) : __floats2bfloat162_rn(e1, e0);
+      r[i] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+    tmem_st8(lane_addr + c8 * 8, r);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  // B -> shared (hi term only), chunk layout of the production kernels
+  const int nchunks = K / KC;
+  const uint32_t b_tile = op_tile_bytes(256);
+  float v[8];
+  for (int c = 0; c < nchunks; ++c)
+    for (int n = tid; n < N; n += 128)
+      for (int k8 = 0; k8 < KC / 8; ++k8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = Bm[(size_t)n * K + c * KC + k8 * 8 + i];
+        op_store8<1>(smem + c * b_tile, nullptr, n, k8, v);
+      }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    for (int c = 0; c < nchunks; ++c)
+      for (int s2 = 0; s2 < KC / 16; ++s2) {
+        const uint64_t db = make_sdesc(smem_u32(smem + c * b_tile) + s2 * 2 * OP_LBO, OP_LBO, OP_SBO);
+        tc_mma_bf16_ts(tmem, tmem + a_col + (c * (KC / 16) + s2) * 8, db, idesc, (c | s2) ? 1u : 0u);
+      }
+    tc_commit(&done_bar);
+  }
+  mbar_wait(&done_bar, 0);
+  tc_fence_after();
+  const uint32_t lane_base = tmem_lane_base(tmem);
+  for (int n0 = 0; n0 < N; n0 += 8) {
+    float o[8];
+    tmem_ld8(lane_base + n0, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) D[(size_t)tid * N + n0 + i] = o[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace rcot
+
+extern "C" int rcot_selftest_tmem_a(const float* A, const float* B, float* D, int N, int K, int variant,
+                                    cudaStream_t stream) {
+  using namespace rcot;
+  RCOT_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "selftest_tmem_a: N must be a multiple of 16 in [16,256], got %d", N);
+  RCOT_REQUIRE(K >= KC && K % KC == 0 && K <= 256, "selftest_tmem_a: K must be a multiple of %d up to 256, got %d", KC, K);
+  const int smem = (K / KC) * op_tile_bytes(256);
+  cudaFuncSetAttribute(tc_selftest_tmema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  tc_selftest_tmema_kernel<<<1, 128, smem, stream>>>(A, B, D, N, K, variant);
+  return check_launch("tc_selftest_tmem_a");
+}
 
 extern "C" int rcot_selftest_tc(const float* A, const float* B, float* D, int N, int K, int terms,
                                 cudaStream_t stream) {
