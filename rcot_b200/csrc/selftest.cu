@@ -110,30 +110,40 @@ __global__ void __launch_bounds__(128) tc_selftest_tmema_kernel(const float* __r
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t a_col = 256;                          // A: columns [256, 256 + K/2); D: columns [0, N)
-  // A -> TMEM: this thread owns lane tid
   const uint32_t lane_addr = tmem_lane_base(tmem) + a_col;
-  for (int c8 = 0; c8 < K / 16; ++c8) {                // 8 columns = 16 K-elements per store
-    uint32_t r[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float e0 = A[(size_t)tid * K + c8 * 16 + 2 * i], e1 = A[(size_t)tid * K + c8 * 16 + 2 * i + 1];
-      const __nv_bfloat162 pk = variant == 0 ? __floats2bfloat162_rn(e0, e1) : __floats2bfloat162_rn(e1, e0);
-      r[i] = *reinterpret_cast<const uint32_t*>(&pk);
-    }
-    tmem_st8(lane_addr + c8 * 8, r);
-  }
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  // B -> shared (hi term only), chunk layout of the production kernels
   const int nchunks = K / KC;
   const uint32_t b_tile = op_tile_bytes(256);
-  float v[8];
-  for (int c = 0; c < nchunks; ++c)
-    for (int n = tid; n < N; n += 128)
-      for (int k8 = 0; k8 < KC / 8; ++k8) {
+  auto store_a = [&]() {                               // A -> TMEM: this thread owns lane tid
+    for (int c8 = 0; c8 < K / 16; ++c8) {              // 8 columns = 16 K-elements per store
+      uint32_t r[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = Bm[(size_t)n * K + c * KC + k8 * 8 + i];
-        op_store8<1>(smem + c * b_tile, nullptr, n, k8, v);
+      for (int i = 0; i < 8; ++i) {
+        const float e0 = A[(size_t)tid * K + c8 * 16 + 2 * i], e1 = A[(size_t)tid * K + c8 * 16 + 2 * i + 1];
+        const __nv_bfloat162 pk = (variant & 1) == 0 ? __floats2bfloat162_rn(e0, e1) : __floats2bfloat162_rn(e1, e0);
+        r[i] = *reinterpret_cast<const uint32_t*>(&pk);
       }
+      tmem_st8(lane_addr + c8 * 8, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  };
+  auto store_b = [&]() {                               // B -> shared (hi term only), chunk layout of the production kernels
+    float v[8];
+    for (int c = 0; c < nchunks; ++c)
+      for (int n = tid; n < N; n += 128)
+        for (int k8 = 0; k8 < KC / 8; ++k8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = Bm[(size_t)n * K + c * KC + k8 * 8 + i];
+          op_store8<1>(smem + c * b_tile, smem + c * b_tile, n, k8, v);
+        }
+  };
+  if (variant & 2) {
+    store_b();
+    __syncthreads();
+    store_a();
+  } else {
+    store_a();
+    store_b();
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
