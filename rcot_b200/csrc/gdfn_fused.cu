@@ -46,8 +46,8 @@ struct GfLayout {
   static constexpr uint32_t WO = GF_DW_BYTES + 2 * WOUT_T;     // dw taps + W_out slice (contiguous in the blob)
   static constexpr uint32_t SLICE = WIN + WO;
   // shared memory carve-up
-  static constexpr uint32_t OFF_Z = 0;
-  static constexpr uint32_t OFF_U = OFF_Z + 4 * ZT;
+  // (the LN(x) operand of the tile lives in TENSOR memory: columns [0, 2C) = {tile 0 hi, lo, tile 1 hi, lo})
+  static constexpr uint32_t OFF_U = 0;
   static constexpr uint32_t OFF_G = OFF_U + 32 * GF_CS * 4;
   static constexpr uint32_t OFF_WIN = OFF_G + 2 * 2 * GF_G_TILE;
   static constexpr uint32_t OFF_WO = OFF_WIN + GF_WIN_SLOTS * WIN;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
       gb[c] = __ldg(p.ln_gamma + c);
       gb[C + c] = __ldg(p.ln_beta + c);
     }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < GF_WIN_SLOTS; ++i) mbar_init(&winbar[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&wobar[i], 1);
@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tmem_y = tmem + 128;                 // U buffers: columns [0,128); Y: [128, 128 + C)
+  // TMEM columns: Z (A operand of GEMM-1) [0, 2C), U buffers [2C, 2C + 128), Y [2C + 128, 3C + 128)   (<= 416 of 512)
+  const uint32_t tmem_u = tmem + 2 * C;
+  const uint32_t tmem_y = tmem_u + 128;
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total_slices = my_tiles * NS;
 
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
     // ================================================================ issuer warp: TMA weight ring + every MMA
     const uint8_t* blob = reinterpret_cast<const uint8_t*>(p.wblob);
     const uint32_t idesc1 = make_idesc_bf16(128, 32), idesc2 = make_idesc_bf16(128, C);
-    const uint32_t z_base = smem_u32(smem + L::OFF_Z), g_base = smem_u32(smem + L::OFF_G);
+    const uint32_t g_base = smem_u32(smem + L::OFF_G);
     const uint32_t win_base = smem_u32(smem + L::OFF_WIN), wo_base = smem_u32(smem + L::OFF_WO);
     // descriptor templates: everything but the 14-bit start address
     const uint64_t dz_t = make_sdesc(0, 128, L::SBOZ), dg_t = make_sdesc(0, 128, GF_G_SBO), dw_t = make_sdesc(0, 128, 256);
@@ -139,16 +141,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
       if (!(p.debug & 1)) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t d = tmem + (uint32_t)(n & 1) * 64 + mt * 32;
-          const uint32_t ah = (z_base + (mt * 2 + 0) * L::ZT) >> 4, al = (z_base + (mt * 2 + 1) * L::ZT) >> 4;
+          const uint32_t d = tmem_u + (uint32_t)(n & 1) * 64 + mt * 32;
+          const uint32_t ah = tmem + mt * C, al = ah + C / 2;        // A operand in TMEM: 8 columns per k16 step
 #pragma unroll
           for (int ks = 0; ks < C / 16; ++ks) {
-            const uint64_t dah = dz_t | (uint64_t)((ah + ks * 16) & 0x3FFFu), dal = dz_t | (uint64_t)((al + ks * 16) & 0x3FFFu);
             const uint64_t dbh = dz_t | (uint64_t)((wb + ks * 16) & 0x3FFFu);
             const uint64_t dbl = dz_t | (uint64_t)((wb + (4 * L::SBOZ >> 4) + ks * 16) & 0x3FFFu);
-            tc_mma_bf16(d, dah, dbh, idesc1, ks == 0 ? 0u : 1u);
-            tc_mma_bf16(d, dal, dbh, idesc1, 1u);
-            tc_mma_bf16(d, dah, dbl, idesc1, 1u);
+            tc_mma_bf16_ts(d, ah + ks * 8, dbh, idesc1, ks == 0 ? 0u : 1u);
+            tc_mma_bf16_ts(d, al + ks * 8, dbh, idesc1, 1u);
+            tc_mma_bf16_ts(d, ah + ks * 8, dbl, idesc1, 1u);
           }
         }
       }
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
     }
     int n = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      mbar_wait(&zbar, (uint32_t)ti & 1);                          // Z of this tile is in shared memory
+      mbar_wait(&zbar, (uint32_t)ti & 1);                          // Z of this tile is in tensor memory
       for (int s = 0; s < NS; ++s, ++n) {
         // ---- GEMM-1(n): needs W_in(n) and the U buffer n&1 drained (slice n-2)
         if (!(p.debug & 8) || n < 2) mbar_wait(&winbar[n % GF_WIN_SLOTS], (uint32_t)(n / GF_WIN_SLOTS) & 1);
@@ -213,46 +214,43 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
       const int hy = hp / GF_HW, hx = hp - hy * GF_HW;
       const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
       const bool inimg = hp < GF_NHP && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-      const int mt = hp >> 7, row = hp & 127;
-      uint8_t* zh = smem + L::OFF_Z + (mt * 2 + 0) * L::ZT + (row >> 3) * L::SBOZ + (row & 7) * 16;
-      uint8_t* zl = zh + L::ZT;
+      const int mt = hp >> 7;                          // warp-uniform: hp = 32 * (warp & 7) + lane
+      // this warp's TMEM lanes are 32 * (warp & 3) .. +31 = rows (hp & 127) of tile mt; columns of channel group kg:
+      //   hi: mt*C + 4*kg .. +3,   lo: mt*C + C/2 + 4*kg .. +3      (8 channels = 4 packed columns)
+      const uint32_t zaddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * C);
       constexpr int NG = C / 16;                      // 8-channel groups per thread (half of the channels)
+      float v[NG][8];
       if (inimg) {
         const float* xp = p.x + (size_t)b * p.x_bs + (size_t)gy * W + gx + (size_t)(half * (C / 2)) * HWp;
-        float v[NG][8];
 #pragma unroll
         for (int g = 0; g < NG; ++g)
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[g][i] = __ldg(xp + (size_t)(g * 8 + i) * HWp);
-        float mu = 0.f, rstd = 1.f;
         if (LN) {
           const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + (size_t)b * HWp + gy * W + gx);
-          mu = st.x;
-          rstd = st.y;
-        }
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if (LN) {
+          for (int g = 0; g < NG; ++g) {
             const float* gp = gb + half * (C / 2) + g * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[g][i] = (v[g][i] - mu) * rstd * gp[i] + gp[C + i];
+            for (int i = 0; i < 8; ++i) v[g][i] = (v[g][i] - st.x) * st.y * gp[i] + gp[C + i];
           }
-          uint4 hi, lo;
-          split8(v[g], hi, lo);
-          const uint32_t ko = (uint32_t)(half * (C / 16) + g) * 128;
-          *reinterpret_cast<uint4*>(zh + ko) = hi;
-          *reinterpret_cast<uint4*>(zl + ko) = lo;
         }
-      } else {
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
+      } else {                                         // outside the image (or beyond the 180 halo pixels): zero rows
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          const uint32_t ko = (uint32_t)(half * (C / 16) + g) * 128;
-          *reinterpret_cast<uint4*>(zh + ko) = z4;
-          *reinterpret_cast<uint4*>(zl + ko) = z4;
-        }
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
       }
-      fence_async_smem();
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {                  // every lane takes part in the (warp-collective) TMEM stores
+        uint4 hi, lo;
+        split8(v[g], hi, lo);
+        const uint32_t kc = (uint32_t)(half * (C / 16) + g) * 4;
+        tmem_st4(zaddr + kc, hi.x, hi.y, hi.z, hi.w);
+        tmem_st4(zaddr + C / 2 + kc, lo.x, lo.y, lo.z, lo.w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&zbar);
     };
@@ -272,7 +270,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
           const int q = warp & 3, mt = (warp >> 2) & 1, ch0 = (warp >> 3) * 16;
           const int hp = mt * 128 + q * 32 + lane;
           uint32_t r[16];
-          tmem_ld16_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(n & 1) * 64 + mt * 32 + ch0, r);
+          tmem_ld16_nowait(tmem_u + ((uint32_t)(q * 32) << 16) + (uint32_t)(n & 1) * 64 + mt * 32 + ch0, r);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -408,7 +406,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gdfn_fwd_kernel(const rcot_gdfn
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------- weight blob

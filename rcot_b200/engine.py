@@ -22,11 +22,14 @@ from . import ops
 # It moves 13.3 instead of 29.3 C*H*W passes but is issue-bound (8 k warp-instructions per 32x32 tile, measured
 # 1.49 ms vs 1.29 ms for the two kernels at C=96, 128x128, B=32), so the two-kernel form stays the default.
 FUSED_GDFN_MID = os.environ.get("RCOT_FUSED_GDFN_MID", "0") == "1"
-# RCOT_FUSED_GDFN=1 selects the one-kernel GDFN forward (csrc/gdfn_fused.cu; C in {48, 96}, H % 8 == 0, W % 16 == 0)
-# instead of the three-launch path (pm_gemm -> dw_gate -> pm_gemm).  It is parity-green and moves ~8x fewer DRAM bytes,
-# but it is bound by its per-slice synchronisation and the CUDA-core stencil, not by HBM: measured 1.46 ms vs 0.97 ms
-# for the three launches at C=96, 128x128, B=32 -- so the three-launch path stays the default.
-FUSED_GDFN = os.environ.get("RCOT_FUSED_GDFN", "0") == "1"
+# One-kernel GDFN forward (csrc/gdfn_fused.cu; C in {48, 96}, H % 8 == 0, W % 16 == 0) instead of the three launches
+# pm_gemm -> dw_gate -> pm_gemm.  RCOT_FUSED_GDFN: "auto" (default) = wherever the hidden tensors are NOT kept for the
+# backward (inference, and the recompute mode of training), "1" = always (the kernel then also writes u and g), "0" =
+# never.  Measured at C=96, 128x128, B=32: 0.96 ms vs 0.98 ms for the three launches with 10x less DRAM traffic (0.48 vs
+# 0.50 ms at C=48), but 1.28 vs 0.98 ms when u and g must also be written -- hence "auto" (DESIGN.md section 6).
+_FG = os.environ.get("RCOT_FUSED_GDFN", "auto")
+FUSED_GDFN = _FG != "0"              # blobs are packed
+FUSED_GDFN_ALWAYS = _FG == "1"
 # RCOT_LNB_EPILOGUE=1: LayerNorm backward inside the epilogue of the GEMM that produces dL/dLN(x) (C <= 256) instead of
 # its own kernel: two passes over the block tensor and 168 launches per step fewer -- but measured SLOWER (step 246.7 ->
 # 265.3 ms at B=32: pm_gemm +32.8 ms, ln_bwd -13.3 ms): the four epilogue warps of a CTA become the bottleneck of the
@@ -91,6 +94,8 @@ class ParamSet:
         self.table = ops.PackTable(device)
         self.pack_idx = {}
         self.gdfn = {}                 # block prefix -> weight blob of the fused GDFN forward kernel
+        self.gdfn_ver = {}
+        self.weights_ver = 0
 
     def add_pack(self, name, kind):
         key = (name, kind)
@@ -106,13 +111,20 @@ class ParamSet:
     def add_gdfn(self, prefix, C, hid):
         if prefix not in self.gdfn:
             self.gdfn[prefix] = torch.empty(ops.gdfn_blob_bytes(C, hid), dtype=torch.uint8, device=self.flat.device)
+            self.gdfn_ver[prefix] = -1
 
     def repack(self):
         if self.table.entries:
             self.table.repack()
-        for pre, blob in self.gdfn.items():
-            f = pre + "ffn."
-            ops.gdfn_pack(self.p[f + "project_in.weight"], self.p[f + "dwconv.weight"], self.p[f + "project_out.weight"], blob)
+        self.weights_ver += 1          # the fused-GDFN blobs are re-packed lazily, by the first forward that uses them
+
+    def gdfn_blob(self, prefix):
+        if self.gdfn_ver[prefix] != self.weights_ver:
+            f = prefix + "ffn."
+            ops.gdfn_pack(self.p[f + "project_in.weight"], self.p[f + "dwconv.weight"], self.p[f + "project_out.weight"],
+                          self.gdfn[prefix])
+            self.gdfn_ver[prefix] = self.weights_ver
+        return self.gdfn[prefix]
 
     def pack(self, name, kind):
         return self.table.ptr(self.pack_idx[(name, kind)])
@@ -334,9 +346,10 @@ def gdfn_fwd(bs: BlockSpec, x, norm_name, residual, keep=False):
     stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
     hd = hidden_dtype(C, x.shape[2], x.shape[3])
-    if bs.pre in ps.gdfn and ops.TERMS == 3 and hd == torch.float32 and ops.gdfn_supported(C, x.shape[2], x.shape[3]):
+    if (bs.pre in ps.gdfn and (FUSED_GDFN_ALWAYS or not keep) and ops.TERMS == 3 and hd == torch.float32
+            and ops.gdfn_supported(C, x.shape[2], x.shape[3])):
         # one kernel, hidden tensor on chip; u / g are written out only when the backward wants them kept
-        y, u, g = ops.gdfn_fwd(x, ps.gdfn[bs.pre], hid, ln=ln, residual=residual, stats_out=bool(norm_name), save=keep)
+        y, u, g = ops.gdfn_fwd(x, ps.gdfn_blob(bs.pre), hid, ln=ln, residual=residual, stats_out=bool(norm_name), save=keep)
         return (y, (stats, u, g)) if keep else y
     u = ops.pm_gemm(x, ps.pack(f + "project_in.weight", "fwd"), 2 * hid, ln=ln, out_dtype=hd)
     g = ops.dwconv(u, ps.p[f + "dwconv.weight"], mode=1)

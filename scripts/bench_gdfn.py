@@ -48,6 +48,7 @@ def main():
             else:
                 ps.gdfn.clear()
             ps.finalize()
+            engine.FUSED_GDFN_ALWAYS = fused
             for keep in (False, True):
                 i = [0]
 

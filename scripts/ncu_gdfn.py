@@ -21,6 +21,8 @@ for fused in (True, False):
     bs = engine.BlockSpec(ps, "b.", C, 1, has_attn=False)
     if fused:
         ps.add_gdfn("b.", C, hid)
+    else:
+        ps.gdfn.clear()
     ps.finalize()
     for _ in range(3):
         y = engine.gdfn_fwd(bs, x, "b.norm2", True, keep=False)

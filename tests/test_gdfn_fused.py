@@ -79,8 +79,32 @@ def test_gdfn_fused_matches_unfused_block_path(cuda_lib):
         else:
             ps.gdfn.clear()
         ps.finalize()
+        engine.FUSED_GDFN_ALWAYS = fused           # the default ("auto") takes the fused kernel only when nothing is kept
         y, kept = engine.gdfn_fwd(bs, x, "b.norm2", True, keep=True)
         dx = engine.gdfn_bwd(bs, x, dy.clone(), "b.norm2", True, kept=kept)
         outs.append((y, dx, ps.grad.clone()))
+    engine.FUSED_GDFN_ALWAYS = False
     for a, b in zip(outs[0], outs[1]):
         torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4)
+
+
+def test_inference_forward_uses_fused_kernel_and_matches(cuda_lib):
+    """Default policy: a forward that keeps nothing (inference) runs GDFN as one kernel; same result as the three launches."""
+    from rcot_b200 import engine, ops
+    g = torch.Generator().manual_seed(5)
+    C = 48
+    sd, hid = _params(C, g)
+    x = torch.randn(2, C, 64, 64, generator=g).cuda()
+    ys, used = [], []
+    for fused in (True, False):
+        ps = engine.ParamSet({k: v for k, v in sd.items()}, "cuda")
+        bs = engine.BlockSpec(ps, "b.", C, 1, has_attn=False)
+        if not fused:
+            ps.gdfn.clear()
+        ps.finalize()
+        ops.PROF = ops.Profiler()
+        ys.append(engine.gdfn_fwd(bs, x, "b.norm2", True, keep=False))
+        used.append("gdfn_fwd" in ops.PROF.summary())
+        ops.PROF = None
+    assert used == [True, False]
+    torch.testing.assert_close(ys[0], ys[1], rtol=2e-4, atol=2e-4)
