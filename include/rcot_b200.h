@@ -181,13 +181,16 @@ typedef struct {
   int64_t g_bs;
   int32_t B, C, H, W, hid;
   int32_t residual;          /* y = x + out                                                   */
-  int32_t debug;             /* measurement knobs (0 in production): 1 skip MMAs, 2 skip stencil, 4 skip drain stores */
+  int32_t debug;             /* measurement knobs (0 in production): 1 skip MMAs, 2 skip stencil, 4 skip drain stores, 16 cycle counters */
 } rcot_gdfn_params;
 int rcot_gdfn_supported(int C, int H, int W);
 size_t rcot_gdfn_blob_bytes(int C, int hid);
 int rcot_gdfn_pack(const float* w_in, const float* w_dw, const float* w_out, void* blob, int C, int hid,
                    rcot_stream_t stream);
 int rcot_gdfn_fwd(const rcot_gdfn_params* p, rcot_stream_t stream);
+/* Measurement aid (not part of the reference surface): per-warp wait / section cycle counters of CTA 0 of the last
+ * rcot_gdfn_fwd launched with debug & 16, as [22 warps][8] uint64 (n = 176).  Synchronises the device. */
+int rcot_gdfn_profile_read(unsigned long long* out, int n);
 
 /* ---------------------------------------------------------------- LayerNorm over channels
  * Net_Restormer.py:173-200 (WithBias_LayerNorm on the 'b (h w) c' view): stats[b, p] = (mean, rstd)

@@ -346,6 +346,14 @@ def gdfn_fwd(x, blob, hid, ln=None, residual=True, stats_out=False, save=False):
     return y, u, g
 
 
+def gdfn_profile_read():
+    """Cycle counters of CTA 0 of the last gdfn_fwd launched with RCOT_GDFN_DEBUG & 16: [22 warps][8] (measurement aid)."""
+    import numpy as np
+    out = np.zeros(22 * 8, dtype=np.uint64)
+    _lib.check(L().rcot_gdfn_profile_read(out.ctypes.data_as(C.c_void_p), out.size), "gdfn_profile_read")
+    return out.reshape(22, 8)
+
+
 # ------------------------------------------------------------------ LayerNorm
 def ln_stats(x, out=None):
     B, Cc, H, W = x.shape
