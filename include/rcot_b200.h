@@ -192,6 +192,37 @@ int rcot_gdfn_fwd(const rcot_gdfn_params* p, rcot_stream_t stream);
  * rcot_gdfn_fwd launched with debug & 16, as [22 warps][8] uint64 (n = 176).  Synchronises the device. */
 int rcot_gdfn_profile_read(unsigned long long* out, int n);
 
+/* ---------------------------------------------------------------- MDTA phase 1 as ONE kernel (csrc/mdta_fused.cu)
+ * Net_Restormer.py:29-41 (qkv 1x1 conv of LN(x), depthwise 3x3, q k^T and the row norms of F.normalize) with pre, q
+ * and k kept on chip: per 8x16-pixel tile (+1-pixel halo) the 3C channels are walked in slices of 32 (tcgen05 GEMM from
+ * a TMEM-resident LN(x) operand -> shared-memory stencil), v goes to HBM, q / k become bf16 hi/lo operand rows of a
+ * per-tile Gram MMA that accumulates in TMEM across the tiles of an image.  Built for C in {48, 96}, H % 8 == 0,
+ * W % 16 == 0.  G [B, heads, c, c] and sumsq [B, 2C] are ACCUMULATED (zero them first); they and v are exactly what
+ * rcot_attn_fwd and the y = x + M v GEMM consume.  Weights: one blob made by rcot_mdta_p1_pack from qkv.weight [3C, C]
+ * and qkv_dwconv.weight [3C, 9].  Optional save_pre [B, 3C, H, W] / save_qk [B, 2C, H, W] feed the unfused backward. */
+typedef struct {
+  const float* x;            /* [B, C, H, W], per-image block contiguous                     */
+  int64_t x_bs;
+  const float* ln_stats;     /* [B, H*W, 2] (mean, rstd) or NULL = no LayerNorm              */
+  const float* ln_gamma;
+  const float* ln_beta;
+  const void* wblob;         /* rcot_mdta_p1_pack output                                     */
+  float* v;                  /* [B, C, H, W] (16-byte aligned; may be the v part of a qkv tensor) */
+  int64_t v_bs;
+  float* G;                  /* [B, heads, c, c]  +=                                         */
+  float* sumsq;              /* [B, 2C]           +=  (q channels then k channels)           */
+  float* save_pre;           /* optional                                                     */
+  int64_t pre_bs;
+  float* save_qk;            /* optional (may be the q, k part of a qkv tensor)              */
+  int64_t qk_bs;
+  int32_t B, C, H, W, heads;
+  int32_t debug;             /* measurement knobs (0 in production): 1 skip MMAs, 2 skip stencil, 4 skip drain stores */
+} rcot_mdta_p1_params;
+int rcot_mdta_p1_supported(int C, int H, int W, int heads);
+size_t rcot_mdta_p1_blob_bytes(int C);
+int rcot_mdta_p1_pack(const float* w_qkv, const float* w_dw, void* blob, int C, rcot_stream_t stream);
+int rcot_mdta_p1(const rcot_mdta_p1_params* p, rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- LayerNorm over channels
  * Net_Restormer.py:173-200 (WithBias_LayerNorm on the 'b (h w) c' view): stats[b, p] = (mean, rstd)
  * with biased variance and eps 1e-5; the normalisation itself is applied as a GEMM prologue. */

@@ -346,6 +346,61 @@ def gdfn_fwd(x, blob, hid, ln=None, residual=True, stats_out=False, save=False):
     return y, u, g
 
 
+class MdtaP1Params(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_bs", C.c_int64), ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p),
+                ("ln_beta", C.c_void_p), ("wblob", C.c_void_p), ("v", C.c_void_p), ("v_bs", C.c_int64),
+                ("G", C.c_void_p), ("sumsq", C.c_void_p), ("save_pre", C.c_void_p), ("pre_bs", C.c_int64),
+                ("save_qk", C.c_void_p), ("qk_bs", C.c_int64), ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32),
+                ("W", C.c_int32), ("heads", C.c_int32), ("debug", C.c_int32)]
+
+
+def mdta_p1_supported(Cc, H, W, heads):
+    return bool(L().rcot_mdta_p1_supported(Cc, H, W, heads))
+
+
+def mdta_p1_blob_bytes(Cc):
+    L().rcot_mdta_p1_blob_bytes.restype = C.c_size_t
+    return int(L().rcot_mdta_p1_blob_bytes(Cc))
+
+
+def mdta_p1_pack(w_qkv, w_dw, blob):
+    """Weight blob of the fused MDTA phase-1 kernel from qkv.weight [3C,C,1,1] and qkv_dwconv.weight [3C,1,3,3]."""
+    global LAUNCHES
+    LAUNCHES += 1
+    Cc = w_qkv.shape[1]
+    _lib.check(L().rcot_mdta_p1_pack(_ptr(_f32(w_qkv)), _ptr(_f32(w_dw)), _ptr(blob), Cc, _stream()), "mdta_p1_pack")
+    return blob
+
+
+def mdta_p1(x, blob, heads, G, sumsq, ln=None, save=False):
+    """One-kernel MDTA phase 1: accumulates the per-head Grams into ``G`` [B, heads, c, c] and the row sums of squares
+    into ``sumsq`` [B, 2C] (both zeroed by the caller) and returns (v, pre, qkv): ``v`` [B, C, H, W] alone when
+    ``save`` is false (pre = qkv = None), else a view of the v part of the saved ``qkv`` tensor."""
+    B, Cc, H, W = x.shape
+    p = MdtaP1Params()
+    p.x, p.x_bs = x.data_ptr(), _img_view(x, "x")
+    if ln is not None:
+        stats, gamma, beta = ln
+        p.ln_stats, p.ln_gamma, p.ln_beta = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    p.wblob = blob.data_ptr()
+    pre = qkv = None
+    if save:
+        pre = torch.empty(B, 3 * Cc, H, W, device=x.device, dtype=torch.float32)
+        qkv = torch.empty(B, 3 * Cc, H, W, device=x.device, dtype=torch.float32)
+        v = qkv[:, 2 * Cc:]
+        p.save_pre, p.pre_bs = pre.data_ptr(), _img_view(pre, "pre")
+        p.save_qk, p.qk_bs = qkv.data_ptr(), 3 * Cc * H * W
+        p.v, p.v_bs = v.data_ptr(), 3 * Cc * H * W
+    else:
+        v = torch.empty(B, Cc, H, W, device=x.device, dtype=torch.float32)
+        p.v, p.v_bs = v.data_ptr(), _img_view(v, "v")
+    p.G, p.sumsq = G.data_ptr(), sumsq.data_ptr()
+    p.B, p.C, p.H, p.W, p.heads = B, Cc, H, W, heads
+    p.debug = int(os.environ.get("RCOT_MDTA_DEBUG", "0"))
+    _lib.check(L().rcot_mdta_p1(C.byref(p), _stream()), "mdta_p1")
+    return v, pre, qkv
+
+
 def gdfn_profile_read():
     """Cycle counters of CTA 0 of the last gdfn_fwd launched with RCOT_GDFN_DEBUG & 16: [22 warps][8] (measurement aid)."""
     import numpy as np
@@ -645,6 +700,7 @@ def _pm_bytes(a, k, r):
 pm_gemm = _instrument("pm_gemm", _pm_bytes)(pm_gemm)
 pk_gemm = _instrument("pk_gemm", lambda a, k, r: _nb(a[0], a[1], k.get("b2"), a[2]))(pk_gemm)
 gdfn_fwd = _instrument("gdfn_fwd", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(gdfn_fwd)
+mdta_p1 = _instrument("mdta_p1", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(mdta_p1)
 ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
 ln_fwd = _instrument("ln_fwd", lambda a, k, r: _nb(a[0], r[0]))(ln_fwd)
 ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)
