@@ -25,11 +25,18 @@ FUSED_GDFN_MID = os.environ.get("RCOT_FUSED_GDFN_MID", "0") == "1"
 # One-kernel GDFN forward (csrc/gdfn_fused.cu; C in {48, 96}, H % 8 == 0, W % 16 == 0) instead of the three launches
 # pm_gemm -> dw_gate -> pm_gemm.  RCOT_FUSED_GDFN: "auto" (default) = wherever the hidden tensors are NOT kept for the
 # backward (inference, and the recompute mode of training), "1" = always (the kernel then also writes u and g), "0" =
-# never.  Measured at C=96, 128x128, B=32: 0.96 ms vs 0.98 ms for the three launches with 10x less DRAM traffic (0.48 vs
-# 0.50 ms at C=48), but 1.28 vs 0.98 ms when u and g must also be written -- hence "auto" (DESIGN.md section 6).
+# never.  Measured at C=96, 128x128, B=32 (version 6 of the kernel): 0.73 ms vs 0.98 ms for the three launches with 10x
+# less DRAM traffic (0.39 vs 0.50 ms at C=48), but 1.01 vs 0.98 ms when u and g must also be written -- hence "auto".
 _FG = os.environ.get("RCOT_FUSED_GDFN", "auto")
 FUSED_GDFN = _FG != "0"              # blobs are packed
 FUSED_GDFN_ALWAYS = _FG == "1"
+# One-kernel MDTA phase 1 (csrc/mdta_fused.cu: qkv GEMM -> depthwise stencil -> Gram + row norms, pre / q / k on chip)
+# instead of pm_gemm -> dw_plain -> pk_gemm.  RCOT_FUSED_MDTA: "auto" (default) = wherever pre and qkv are not kept for
+# the backward, "1" = always (the kernel then also writes pre, q and k), "0" = never.  Measured at C=96, 128x128, B=32:
+# 0.47 vs 0.56 ms (0.23 vs 0.33 ms at C=48); 0.82 vs 0.56 ms when pre and qkv must also be written -- hence "auto".
+_FM = os.environ.get("RCOT_FUSED_MDTA", "auto")
+FUSED_MDTA = _FM != "0"
+FUSED_MDTA_ALWAYS = _FM == "1"
 # RCOT_LNB_EPILOGUE=1: LayerNorm backward inside the epilogue of the GEMM that produces dL/dLN(x) (C <= 256) instead of
 # its own kernel: two passes over the block tensor and 168 launches per step fewer -- but measured SLOWER (step 246.7 ->
 # 265.3 ms at B=32: pm_gemm +32.8 ms, ln_bwd -13.3 ms): the four epilogue warps of a CTA become the bottleneck of the
@@ -95,6 +102,8 @@ class ParamSet:
         self.pack_idx = {}
         self.gdfn = {}                 # block prefix -> weight blob of the fused GDFN forward kernel
         self.gdfn_ver = {}
+        self.mdta = {}                 # block prefix -> weight blob of the fused MDTA phase-1 kernel
+        self.mdta_ver = {}
         self.weights_ver = 0
 
     def add_pack(self, name, kind):
@@ -112,6 +121,18 @@ class ParamSet:
         if prefix not in self.gdfn:
             self.gdfn[prefix] = torch.empty(ops.gdfn_blob_bytes(C, hid), dtype=torch.uint8, device=self.flat.device)
             self.gdfn_ver[prefix] = -1
+
+    def add_mdta(self, prefix, C):
+        if prefix not in self.mdta:
+            self.mdta[prefix] = torch.empty(ops.mdta_p1_blob_bytes(C), dtype=torch.uint8, device=self.flat.device)
+            self.mdta_ver[prefix] = -1
+
+    def mdta_blob(self, prefix):
+        if self.mdta_ver[prefix] != self.weights_ver:
+            a = prefix + "attn."
+            ops.mdta_p1_pack(self.p[a + "qkv.weight"], self.p[a + "qkv_dwconv.weight"], self.mdta[prefix])
+            self.mdta_ver[prefix] = self.weights_ver
+        return self.mdta[prefix]
 
     def repack(self):
         if self.table.entries:
@@ -257,6 +278,8 @@ class BlockSpec:
             a = prefix + "attn."
             ps.add_pack(a + "qkv.weight", "fwd")
             ps.add_pack(a + "qkv.weight", "dgrad")
+            if FUSED_MDTA and C in (48, 96):
+                ps.add_mdta(prefix, C)
         if has_ffn:
             f = prefix + "ffn."
             self.hid = ps.p[f + "project_out.weight"].shape[1]
@@ -297,16 +320,26 @@ def mdta_fwd(bs: BlockSpec, x, norm_name, residual, need_bwd, store=None):
     st = sc if store is None else store
     stats = _stats_of(x) if norm_name else None
     ln = _ln_args(ps, norm_name, stats) if norm_name else None
-    pre = ops.pm_gemm(x, ps.pack(a + "qkv.weight", "fwd"), 3 * C, ln=ln, out_dtype=hidden_dtype(C, H, W))
+    c = C // h
+    fused = (bs.pre in ps.mdta and (FUSED_MDTA_ALWAYS or not need_bwd) and ops.TERMS == 3
+             and hidden_dtype(C, H, W) == torch.float32 and ops.mdta_p1_supported(C, H, W, h))
+    if not fused:
+        pre = ops.pm_gemm(x, ps.pack(a + "qkv.weight", "fwd"), 3 * C, ln=ln, out_dtype=hidden_dtype(C, H, W))
     ops.zero_(sc.zbuf)
     if store is not None:
         ops.zero_(store.sumsq)
-    qkv = ops.dwconv(pre, ps.p[a + "qkv_dwconv.weight"], sumsq=st.sumsq, nsq=2 * C)
-    c = C // h
-    ops.pk_gemm(qkv[:, :C], qkv[:, C:2 * C], sc.G, ldo=c, per_image=True, groups=h, out_gs=c * c)
+    if fused:
+        # one kernel: pre, q and k stay on chip (written out only when the backward wants them kept)
+        v, pre, qkv = ops.mdta_p1(x, ps.mdta_blob(bs.pre), h, sc.G, st.sumsq, ln=ln, save=need_bwd)
+        if qkv is None:
+            qkv = v.new_empty(0)                       # nothing kept: only v exists
+    else:
+        qkv = ops.dwconv(pre, ps.p[a + "qkv_dwconv.weight"], sumsq=st.sumsq, nsq=2 * C)
+        ops.pk_gemm(qkv[:, :C], qkv[:, C:2 * C], sc.G, ldo=c, per_image=True, groups=h, out_gs=c * c)
+        v = qkv[:, 2 * C:]
     ops.attn_fwd(sc.G, st.sumsq, ps.p[a + "temperature"], ps.p[a + "project_out.weight"], st.A, st.Gt, sc.Mpack,
                  st.MTpack if need_bwd else None, B, C, h)
-    y = ops.pm_gemm(qkv[:, 2 * C:], sc.Mpack.data_ptr(), C, wpack_bs=sc.pb, residual=x if residual else None,
+    y = ops.pm_gemm(v, sc.Mpack.data_ptr(), C, wpack_bs=sc.pb, residual=x if residual else None,
                     stats_out=bool(norm_name))      # feeds LN2 of the same block
     return y, (stats, pre, qkv, sc, st)
 

@@ -61,3 +61,43 @@ def test_mdta_phase1(cuda_lib, C, heads, B, H, W, ln):
         if save:
             _close("pre", pre, pre64)
             _close("qkv", qkv, qkv64)
+
+
+@pytest.mark.parametrize("C,heads,H,W", [(96, 2, 32, 32), (48, 1, 16, 48), (96, 4, 24, 16)])
+def test_mdta_forward_fused_matches_unfused_and_oracle(cuda_lib, C, heads, H, W):
+    """engine.mdta_fwd takes the one-kernel phase 1 when nothing is kept for the backward; its block output must agree
+    with the three-launch path on the same weights and with the oracle's MDTA (Net_Restormer.py:29-50)."""
+    from oracle import restormer_ref as R
+    from rcot_b200 import engine
+    g = torch.Generator().manual_seed(7 + C + heads)
+    sd = _params(C, heads, g)
+    x = torch.randn(2, C, H, W, generator=g)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    x64 = x.double()
+    y64 = x64 + R.mdta(R.layer_norm_c(x64, sd64["b.norm1.body.weight"], sd64["b.norm1.body.bias"]), sd64, "b.attn.", heads)
+    outs = []
+    for fused in (True, False):
+        ps = engine.ParamSet(dict(sd), "cuda")
+        bs = engine.BlockSpec(ps, "b.", C, heads, has_ffn=False)
+        if fused:
+            ps.add_mdta("b.", C)
+        else:
+            ps.mdta.clear()
+        ps.finalize()
+        y, _ = engine.mdta_fwd(bs, x.cuda(), "b.norm1", True, False)
+        outs.append(y)
+        _close("y vs oracle", y, y64)
+        if fused:                                     # "always" mode: the kept tensors feed the unfused backward
+            engine.FUSED_MDTA_ALWAYS = True
+            try:
+                y2, ctx = engine.mdta_fwd(bs, x.cuda(), "b.norm1", True, True)
+            finally:
+                engine.FUSED_MDTA_ALWAYS = False
+            _close("y (keep)", y2, y64)
+            dx = engine.mdta_bwd(bs, x.cuda(), torch.ones_like(y2), "b.norm1", True, ctx)
+            outs.append(dx)
+        else:
+            y3, ctx = engine.mdta_fwd(bs, x.cuda(), "b.norm1", True, True)
+            outs.append(engine.mdta_bwd(bs, x.cuda(), torch.ones_like(y3), "b.norm1", True, ctx))
+    torch.testing.assert_close(outs[0], outs[2], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(outs[1], outs[3], rtol=2e-3, atol=2e-4)
