@@ -253,6 +253,15 @@ class OTTrainStep:
         ops.LAUNCHES += st["launches"]
         return out
 
+    def release_graphs(self):
+        """Drop every captured iteration together with its private memory pool (at batch 32 a captured iteration pins
+        ~98 GB of saved hidden tensors: an eager iteration next to it does not fit 180 GB)."""
+        import gc
+        self._graphs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
     def _snapshot(self):
         """Weights + optimizer state, so the warm-up iteration before a capture leaves no trace."""
         return (self.T.ps.flat.clone(), self.F.ps.flat.clone(), self.T_opt.sq.clone(), self.F_opt.sq.clone(),
