@@ -422,6 +422,18 @@ def run_b200(args):
             m, gq, fin = side_run(4, True)
             extras["c3_shape_fp32"] = {"what": "BASELINE config c3's per-GPU share (4 images, paired) at fp32 storage",
                                        "value": 4 / (m / 1e3), "unit": UNIT, "ms_per_step": m, "cuda_graph": gq, "finite": fin}
+            # recompute mode: only the block inputs are kept (6 GB instead of ~98 GB at batch 32); the forward then runs
+            # on the one-kernel GDFN / MDTA-phase-1 kernels, the backward recomputes each block's hidden tensors
+            step.save_hidden = False
+            try:
+                torch.cuda.reset_peak_memory_stats()
+                m, gq, fin = side_run(32, True)
+                extras["recompute_mode"] = {"what": "the headline step (batch 32, paired) keeping only the block inputs for the "
+                                                    "backward: fused forward kernels + per-block recompute",
+                                            "value": 32 / (m / 1e3), "unit": UNIT, "ms_per_step": m, "cuda_graph": gq,
+                                            "finite": fin, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
+            finally:
+                step.save_hidden = None
             # c5: T_net forward only, 256x256, 8 images per GPU (64 global on 8 GPUs)
             x5 = torch.rand(8, 3, 256, 256, device="cuda")
             with torch.no_grad():

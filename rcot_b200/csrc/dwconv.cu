@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------ fused backward: din and dW
-template <int ROWS, typename T>
-__global__ void __launch_bounds__(256)
+template <int ROWS, typename T, int MINB = 1, bool EARLYQ = false>
+__global__ void __launch_bounds__(256, MINB)
     dw_bwd2_kernel(const T* __restrict__ in, int64_t in_bs, const T* __restrict__ dout, int64_t dout_bs,
                    const float* __restrict__ w, T* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
                    const DwGeom g, const int ppt, const int ipc, const int B) {
@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(256)
     }
     if (!t.active) continue;
     float d[ROWS][PW];
+    Patch<ROWS, PW> Q;
+    if (EARLYQ) load_patch<ROWS, T>(Q, in + (size_t)b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
     {
       Patch<ROWS, PW> P;
       load_patch<ROWS, T>(P, dout + (size_t)b * dout_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
@@ -286,8 +288,7 @@ __global__ void __launch_bounds__(256)
         for (int j = 0; j < PW; ++j) d[r][j] = P.v[r + 1][j + 1];   // centre rows of dout
       }
     }
-    Patch<ROWS, PW> Q;
-    load_patch<ROWS, T>(Q, in + (size_t)b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+    if (!EARLYQ) load_patch<ROWS, T>(Q, in + (size_t)b * in_bs + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
@@ -635,8 +636,28 @@ static int dwconv_bwd_fast_t(const T* in, int64_t in_bs, const T* dout, int64_t 
   int ipc = 1;          // small planes: up to 4 images per thread while >= 8 CTAs per SM remain
   while (ppt == 1 && ipc < 4 && (long)grid.x * grid.y * cdiv(B, ipc * 2) >= 8 * 148) ipc *= 2;
   grid.z = cdiv(B, ipc);
-  if (rows == 4)
-    dw_bwd2_kernel<4, T><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
+  // Measured at 510 x 128 x 128, B=32 (scripts/bench_dw.py): the kernel is latency-bound (ncu: 24 % warps active at 95
+  // registers, 41 % long-scoreboard stalls), so occupancy pays: __launch_bounds__(256, 3) = 80 registers, three CTAs
+  // per SM: 662 -> 593 us (5.4 TB/s); four CTAs (64 registers, spills) 691 us; loading both patches up front 860 us.
+  static int variant = -1;            // A/B switch: RCOT_DW_BWD_VAR = 10 * MINB + EARLYQ  (default 30)
+  if (variant < 0) {
+    const char* e = getenv("RCOT_DW_BWD_VAR");
+    variant = e ? atoi(e) : 30;
+  }
+#define RCOT_BWD2(MB, EQ) dw_bwd2_kernel<4, T, MB, EQ><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B)
+  if (rows == 4) {
+    switch (variant) {
+      case 11: RCOT_BWD2(1, true); break;
+      case 20: RCOT_BWD2(2, false); break;
+      case 21: RCOT_BWD2(2, true); break;
+      case 31: RCOT_BWD2(3, true); break;
+      case 40: RCOT_BWD2(4, false); break;
+      case 41: RCOT_BWD2(4, true); break;
+      case 10: RCOT_BWD2(1, false); break;
+      default: RCOT_BWD2(3, false); break;
+    }
+  }
+#undef RCOT_BWD2
   else
     dw_bwd2_kernel<2, T><<<grid, 256, 0, st>>>(in, in_bs, dout, dout_bs, w, din, din_bs, dw, g, ppt, ipc, B);
   return 1;

@@ -6,6 +6,7 @@
 // Layout everywhere: fp32 NCHW, per-image block contiguous, `*_bs` = batch stride in elements.
 #include "../../include/rcot_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace rcot {
 
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(256)
 // so the per-channel sums over pixels are warp shuffles into shared slots no other warp touches; the
 // per-pixel sums over channels are combined across the 8 warps through shared memory.  A CTA walks
 // `groups` consecutive 32-pixel groups before it flushes its channel sums with one atomicAdd each.
-template <int NCH>   // NCH > 0: C == 8*NCH and the (dz, xhat) values of the first sweep stay in registers
-__global__ void __launch_bounds__(256)
+template <int NCH, int MINB = 2, bool EARLYDY = false>   // NCH > 0: C == 8*NCH and the (dz, xhat) values of the first sweep stay in registers
+__global__ void __launch_bounds__(256, MINB)
     ln_bwd_kernel(const float* __restrict__ dz, int64_t dz_bs, const float* __restrict__ x, int64_t x_bs,
                   const float2* __restrict__ stats, const float* __restrict__ gamma, const float* dy, int64_t dy_bs,
                   float* dx, int64_t dx_bs, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int HW,
@@ -142,6 +143,12 @@ __global__ void __launch_bounds__(256)
         }
       }
     }
+    float ry[R];
+    if (NCH > 0 && EARLYDY) {          // the residual rows travel while the CTA meets at the barrier below
+      const float* dyp = (dy && valid) ? dy + (size_t)b * dy_bs + p : nullptr;
+#pragma unroll
+      for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + 8 * k) * HW] : 0.f;
+    }
     spix[wy * 32 + lane] = sg;
     spix[256 + wy * 32 + lane] = sgx;
     __syncthreads();
@@ -158,9 +165,10 @@ __global__ void __launch_bounds__(256)
       const float* dyp = dy ? dy + (size_t)b * dy_bs + p : nullptr;
       float* dxp = dx + (size_t)b * dx_bs + p;
       if (NCH > 0) {
-        float ry[R];
+        if (!EARLYDY) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + 8 * k) * HW] : 0.f;
+          for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + 8 * k) * HW] : 0.f;
+        }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const int c = wy + 8 * k;
@@ -589,14 +597,34 @@ extern "C" int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64
   dim3 grid(cdiv(pg, groups), B);
   const size_t sm = (2 * C + 512) * sizeof(float);
   const float2* st2 = reinterpret_cast<const float2*>(stats);
-#define LNB(NCH)                                                                                                  \
-  ln_bwd_kernel<NCH><<<grid, 256, sm, (cudaStream_t)st>>>(dz, dz_bs, x, x_bs, st2, gamma, dy, dy_bs, dx, dx_bs, \
-                                                          dgamma, dbeta, C, HW, groups)
-  if (C == 48) LNB(6);
-  else if (C == 96) LNB(12);
-  else if (C == 192) LNB(24);
-  else LNB(0);
+  // Measured (scripts/bench_ln.py, B=32): the kernel is latency-bound (ncu at C=96: 128 registers, 24 % warps active,
+  // 55 % long-scoreboard stalls).  At C=48 three CTAs per SM (80 registers) with the residual rows requested before the
+  // CTA barrier give 136 -> 82 us (4.9 TB/s); at C=96 / 192 the same limits spill and lose (184 -> 193 / 47 -> 98 us),
+  // so those keep two CTAs per SM.  A/B switch: RCOT_LN_BWD_VAR = 10 * MINB + EARLYDY.
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("RCOT_LN_BWD_VAR");
+    forced = e ? atoi(e) : 0;
+  }
+  const int variant = forced ? forced : (C == 48 ? 31 : 20);
+#define LNBV(NCH, MB, ED)                                                                                                  \
+  ln_bwd_kernel<NCH, MB, ED><<<grid, 256, sm, (cudaStream_t)st>>>(dz, dz_bs, x, x_bs, st2, gamma, dy, dy_bs, dx, dx_bs, \
+                                                                  dgamma, dbeta, C, HW, groups)
+#define LNB(NCH)                          \
+  switch (variant) {                      \
+    case 21: LNBV(NCH, 2, true); break;   \
+    case 30: LNBV(NCH, 3, false); break;  \
+    case 31: LNBV(NCH, 3, true); break;   \
+    case 40: LNBV(NCH, 4, false); break;  \
+    case 41: LNBV(NCH, 4, true); break;   \
+    default: LNBV(NCH, 2, false); break;  \
+  }
+  if (C == 48) { LNB(6) }
+  else if (C == 96) { LNB(12) }
+  else if (C == 192) { LNB(24) }
+  else LNBV(0, 2, false);
 #undef LNB
+#undef LNBV
   return check_launch("ln_bwd");
 }
 
