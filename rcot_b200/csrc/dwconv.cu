@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------ GELU gate: forward / backward
 // mode 1: out[j] = gelu(dw(in[j])) * dw(in[j+hid])
 // mode 2: a = dw(in[j]), b = dw(in[j+hid]); out[j] = dg*b*gelu'(a); out[j+hid] = dg*gelu(a); g_out[j] = gelu(a)*b
-template <int MODE, int ROWS, typename T>
-__global__ void __launch_bounds__(256)
+template <int MODE, int ROWS, typename T, int MINB = 0, bool EARLY = false>
+__global__ void __launch_bounds__(256, MINB)
     dw_gate_kernel(const T* __restrict__ in, int64_t in_bs, const float* __restrict__ w, T* __restrict__ out,
                    int64_t out_bs, int hid, const T* __restrict__ dg, int64_t dg_bs, T* __restrict__ g_out,
                    int64_t g_bs, const DwGeom g) {
@@ -203,17 +203,31 @@ __global__ void __launch_bounds__(256)
   constexpr int PW = RowW<T>::PW;
   const T* inb = in + (size_t)t.b * in_bs;
   float a[ROWS][PW], gt[ROWS][PW];
-  {
-    Patch<ROWS, PW> P;
-    load_patch<ROWS, T>(P, inb + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
-    conv_patch<ROWS, PW>(P, w0, a);
-  }
-  {
-    Patch<ROWS, PW> P;
-    load_patch<ROWS, T>(P, inb + (size_t)(t.ch + hid) * HW, t.y, t.x0, g.H, g.W);
-    conv_patch<ROWS, PW>(P, w1, gt);
-  }
   const int pix = t.y * g.W + t.x0;
+  float dgr[ROWS][PW];
+  if (EARLY) {
+    // every global request of the thread first (both patches, then the dg rows): more bytes in flight per warp
+    Patch<ROWS, PW> P, Q;
+    load_patch<ROWS, T>(P, inb + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+    load_patch<ROWS, T>(Q, inb + (size_t)(t.ch + hid) * HW, t.y, t.x0, g.H, g.W);
+    if (MODE == 2) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) ldrow(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pix + r * g.W, dgr[r]);
+    }
+    conv_patch<ROWS, PW>(P, w0, a);
+    conv_patch<ROWS, PW>(Q, w1, gt);
+  } else {
+    {
+      Patch<ROWS, PW> P;
+      load_patch<ROWS, T>(P, inb + (size_t)t.ch * HW, t.y, t.x0, g.H, g.W);
+      conv_patch<ROWS, PW>(P, w0, a);
+    }
+    {
+      Patch<ROWS, PW> P;
+      load_patch<ROWS, T>(P, inb + (size_t)(t.ch + hid) * HW, t.y, t.x0, g.H, g.W);
+      conv_patch<ROWS, PW>(P, w1, gt);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
     const int pr = pix + r * g.W;
@@ -224,7 +238,12 @@ __global__ void __launch_bounds__(256)
       strow(out + (size_t)t.b * out_bs + (size_t)t.ch * HW + pr, gv);
     } else {
       float d[PW];
-      ldrow(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pr, d);
+      if (EARLY) {
+#pragma unroll
+        for (int j = 0; j < PW; ++j) d[j] = dgr[r][j];
+      } else {
+        ldrow(dg + (size_t)t.b * dg_bs + (size_t)t.ch * HW + pr, d);
+      }
       float da[PW], db[PW], gg[PW];
 #pragma unroll
       for (int j = 0; j < PW; ++j) {
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------ fused backward: din and dW
-template <int ROWS, typename T, int MINB = 1, bool EARLYQ = false>
+template <int ROWS, typename T, int MINB = 0, bool EARLYQ = false>
 __global__ void __launch_bounds__(256, MINB)
     dw_bwd2_kernel(const T* __restrict__ in, int64_t in_bs, const T* __restrict__ dout, int64_t dout_bs,
                    const float* __restrict__ w, T* __restrict__ din, int64_t din_bs, float* __restrict__ dw,
@@ -599,16 +618,49 @@ static int dwconv_fast_t(const rcot_dw_params& p, int planes, cudaStream_t st) {
   const int rows = (want == 4 && p.H % 4 == 0 && dw_geom(g, grid, p.B, planes, p.H, p.W, 4, RowW<T>::PW)) ? 4 : 2;
   if (rows == 2 && !dw_geom(g, grid, p.B, planes, p.H, p.W, 2, RowW<T>::PW)) return 0;
   if (p.mode == 1) {
-    if (rows == 4)
-      dw_gate_kernel<1, 4, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
+    // gate forward: four CTAs per SM (64 registers) 376 -> 366 us at 510x128x128; requesting both patches up front LOSES
+    // (448 us: more registers, fewer resident warps) -- scripts/bench_dw.py
+    static int variant1 = -1;         // A/B switch: RCOT_DW_GATE1_VAR = 10 * MINB + EARLY (default 40)
+    if (variant1 < 0) {
+      const char* e = getenv("RCOT_DW_GATE1_VAR");
+      variant1 = e ? atoi(e) : 40;
+    }
+#define RCOT_GATE1(MB, EA) dw_gate_kernel<1, 4, T, MB, EA><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g)
+    if (rows == 4) {
+      switch (variant1) {
+        case 11: RCOT_GATE1(1, true); break;
+        case 21: RCOT_GATE1(2, true); break;
+        case 30: RCOT_GATE1(3, false); break;
+        case 31: RCOT_GATE1(3, true); break;
+        case 10: RCOT_GATE1(0, false); break;
+        default: RCOT_GATE1(4, false); break;
+      }
+    }
+#undef RCOT_GATE1
     else
       dw_gate_kernel<1, 2, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, nullptr, 0, nullptr, 0, g);
   } else {
     if (p.dg_bs % 4 != 0 || (p.g_out && p.g_bs % 4 != 0)) return 0;
+    static int variant = -1;          // A/B switch: RCOT_DW_GATE_VAR = 10 * MINB + EARLY (default 10)
+    if (variant < 0) {
+      const char* e = getenv("RCOT_DW_GATE_VAR");
+      variant = e ? atoi(e) : 10;
+    }
+#define RCOT_GATE2(MB, EA) dw_gate_kernel<2, 2, T, MB, EA><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, dg, p.dg_bs, g_out, p.g_bs, g)
     if (rows == 4)
       dw_gate_kernel<2, 4, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, dg, p.dg_bs, g_out, p.g_bs, g);
-    else
-      dw_gate_kernel<2, 2, T><<<grid, 256, 0, st>>>(in, p.in_bs, p.w, out, p.out_bs, p.hid, dg, p.dg_bs, g_out, p.g_bs, g);
+    else {
+      switch (variant) {
+        case 11: RCOT_GATE2(1, true); break;
+        case 21: RCOT_GATE2(2, true); break;
+        case 31: RCOT_GATE2(3, true); break;
+        case 41: RCOT_GATE2(4, true); break;
+        case 50: RCOT_GATE2(5, false); break;
+        case 51: RCOT_GATE2(5, true); break;
+        default: RCOT_GATE2(0, false); break;
+      }
+    }
+#undef RCOT_GATE2
   }
   return 1;
 }
@@ -653,7 +705,7 @@ static int dwconv_bwd_fast_t(const T* in, int64_t in_bs, const T* dout, int64_t 
       case 31: RCOT_BWD2(3, true); break;
       case 40: RCOT_BWD2(4, false); break;
       case 41: RCOT_BWD2(4, true); break;
-      case 10: RCOT_BWD2(1, false); break;
+      case 10: RCOT_BWD2(0, false); break;
       default: RCOT_BWD2(3, false); break;
     }
   }

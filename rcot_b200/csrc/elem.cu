@@ -75,13 +75,13 @@ __global__ void __launch_bounds__(256)
 // so the per-channel sums over pixels are warp shuffles into shared slots no other warp touches; the
 // per-pixel sums over channels are combined across the 8 warps through shared memory.  A CTA walks
 // `groups` consecutive 32-pixel groups before it flushes its channel sums with one atomicAdd each.
-template <int NCH, int MINB = 2, bool EARLYDY = false>   // NCH > 0: C == 8*NCH and the (dz, xhat) values of the first sweep stay in registers
-__global__ void __launch_bounds__(256, MINB)
+template <int NCH, int MINB = 2, bool EARLYDY = false, int NW = 8>   // NCH > 0: C == NW*NCH and the (dz, xhat) values of the first sweep stay in registers
+__global__ void __launch_bounds__(32 * NW, MINB)
     ln_bwd_kernel(const float* __restrict__ dz, int64_t dz_bs, const float* __restrict__ x, int64_t x_bs,
                   const float2* __restrict__ stats, const float* __restrict__ gamma, const float* dy, int64_t dy_bs,
                   float* dx, int64_t dx_bs, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int HW,
                   int groups) {
-  extern __shared__ float sacc[];  // [2*C] channel sums, then [2][8][32] pixel partials
+  extern __shared__ float sacc[];  // [2*C] channel sums, then [2][NW][32] pixel partials
   float* spix = sacc + 2 * C;
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -110,13 +110,13 @@ __global__ void __launch_bounds__(256, MINB)
     if (NCH > 0) {
 #pragma unroll
       for (int k = 0; k < R; ++k) {   // all loads first: 2*NCH independent requests per thread
-        const int c = wy + 8 * k;
+        const int c = wy + NW * k;
         rd[k] = valid ? __ldg(dzp + (size_t)c * HW) : 0.f;
         rx[k] = valid ? __ldg(xp + (size_t)c * HW) : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        const int c = wy + 8 * k;
+        const int c = wy + NW * k;
         const float xh = valid ? (rx[k] - mu) * rstd : 0.f;
         rx[k] = xh;
         const float g = rd[k] * __ldg(gamma + c);
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, MINB)
         ab[k] += rd[k];
       }
     } else {
-      for (int c = wy; c < C; c += 8) {
+      for (int c = wy; c < C; c += NW) {
         float d = 0.f, xh = 0.f;
         if (valid) {
           d = __ldg(dzp + (size_t)c * HW);
@@ -147,16 +147,16 @@ __global__ void __launch_bounds__(256, MINB)
     if (NCH > 0 && EARLYDY) {          // the residual rows travel while the CTA meets at the barrier below
       const float* dyp = (dy && valid) ? dy + (size_t)b * dy_bs + p : nullptr;
 #pragma unroll
-      for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + 8 * k) * HW] : 0.f;
+      for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + NW * k) * HW] : 0.f;
     }
     spix[wy * 32 + lane] = sg;
-    spix[256 + wy * 32 + lane] = sgx;
+    spix[NW * 32 + wy * 32 + lane] = sgx;
     __syncthreads();
     float mg = 0.f, mgx = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < NW; ++w) {
       mg += spix[w * 32 + lane];
-      mgx += spix[256 + w * 32 + lane];
+      mgx += spix[NW * 32 + w * 32 + lane];
     }
     const float inv = 1.f / (float)C;
     mg *= inv;
@@ -167,15 +167,15 @@ __global__ void __launch_bounds__(256, MINB)
       if (NCH > 0) {
         if (!EARLYDY) {
 #pragma unroll
-          for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + 8 * k) * HW] : 0.f;
+          for (int k = 0; k < R; ++k) ry[k] = dyp ? dyp[(size_t)(wy + NW * k) * HW] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-          const int c = wy + 8 * k;
+          const int c = wy + NW * k;
           dxp[(size_t)c * HW] = rstd * (rd[k] * __ldg(gamma + c) - mg - rx[k] * mgx) + ry[k];
         }
       } else {
-        for (int c = wy; c < C; c += 8) {
+        for (int c = wy; c < C; c += NW) {
           const float d = __ldg(dzp + (size_t)c * HW);
           const float xh = (__ldg(xp + (size_t)c * HW) - mu) * rstd;
           float r = rstd * (d * __ldg(gamma + c) - mg - xh * mgx);
@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(256, MINB)
     for (int k = 0; k < R; ++k) {
       const float wg = warp_sum(ag[k]);
       const float wb = warp_sum(ab[k]);
-      if (lane == 0) {          // channel wy + 8k belongs to this warp alone
-        sacc[wy + 8 * k] = wg;
-        sacc[C + wy + 8 * k] = wb;
+      if (lane == 0) {          // channel wy + NW k belongs to this warp alone
+        sacc[wy + NW * k] = wg;
+        sacc[C + wy + NW * k] = wb;
       }
     }
     __syncthreads();
@@ -595,35 +595,34 @@ extern "C" int rcot_ln_bwd(const float* dz, int64_t dz_bs, const float* x, int64
   if (groups < 1) groups = 1;
   if (groups > 8) groups = 8;
   dim3 grid(cdiv(pg, groups), B);
-  const size_t sm = (2 * C + 512) * sizeof(float);
   const float2* st2 = reinterpret_cast<const float2*>(stats);
-  // Measured (scripts/bench_ln.py, B=32): the kernel is latency-bound (ncu at C=96: 128 registers, 24 % warps active,
-  // 55 % long-scoreboard stalls).  At C=48 three CTAs per SM (80 registers) with the residual rows requested before the
-  // CTA barrier give 136 -> 82 us (4.9 TB/s); at C=96 / 192 the same limits spill and lose (184 -> 193 / 47 -> 98 us),
-  // so those keep two CTAs per SM.  A/B switch: RCOT_LN_BWD_VAR = 10 * MINB + EARLYDY.
+  // Measured (scripts/bench_ln.py, B=32): the kernel is latency-bound (ncu at C=96, 8 warps x 12 channels per thread:
+  // 128 registers, 24 % warps active, 55 % long-scoreboard stalls).  What paid, per width:
+  //   C=48 : 3 CTAs per SM (80 registers) + residual rows requested before the CTA barrier      136 -> 82 us (4.9 TB/s)
+  //   C=192: 32 warps x 6 channels per thread (64 registers, no spills; 8 x 24 spilled)          48 -> 44 us
+  //   C=384: 32 warps x 12 channels in registers instead of the generic re-reading loop           50 -> 32 us
+  //   C=96 : unchanged (8 warps x 12); 16 warps x 6 measured 213 vs 186 us, 3 CTAs per SM spill: 193 us
+  // A/B switch RCOT_LN_BWD_VAR=1: the round-1 shapes (8 warps, NCH = C/8) everywhere.
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("RCOT_LN_BWD_VAR");
     forced = e ? atoi(e) : 0;
   }
-  const int variant = forced ? forced : (C == 48 ? 31 : 20);
-#define LNBV(NCH, MB, ED)                                                                                                  \
-  ln_bwd_kernel<NCH, MB, ED><<<grid, 256, sm, (cudaStream_t)st>>>(dz, dz_bs, x, x_bs, st2, gamma, dy, dy_bs, dx, dx_bs, \
-                                                                  dgamma, dbeta, C, HW, groups)
-#define LNB(NCH)                          \
-  switch (variant) {                      \
-    case 21: LNBV(NCH, 2, true); break;   \
-    case 30: LNBV(NCH, 3, false); break;  \
-    case 31: LNBV(NCH, 3, true); break;   \
-    case 40: LNBV(NCH, 4, false); break;  \
-    case 41: LNBV(NCH, 4, true); break;   \
-    default: LNBV(NCH, 2, false); break;  \
+#define LNBV(NCH, MB, ED, NW_)                                                                                   \
+  ln_bwd_kernel<NCH, MB, ED, NW_><<<grid, 32 * NW_, (2 * C + 64 * NW_) * sizeof(float), (cudaStream_t)st>>>(     \
+      dz, dz_bs, x, x_bs, st2, gamma, dy, dy_bs, dx, dx_bs, dgamma, dbeta, C, HW, groups)
+  if (forced == 1) {
+    if (C == 48) LNBV(6, 2, false, 8);
+    else if (C == 96) LNBV(12, 2, false, 8);
+    else if (C == 192) LNBV(24, 2, false, 8);
+    else LNBV(0, 2, false, 8);
+  } else {
+    if (C == 48) LNBV(6, 3, true, 8);
+    else if (C == 96) LNBV(12, 2, false, 8);
+    else if (C == 192) LNBV(6, 1, true, 32);
+    else if (C == 384) LNBV(12, 1, true, 32);
+    else LNBV(0, 2, false, 8);
   }
-  if (C == 48) { LNB(6) }
-  else if (C == 96) { LNB(12) }
-  else if (C == 192) { LNB(24) }
-  else LNBV(0, 2, false);
-#undef LNB
 #undef LNBV
   return check_launch("ln_bwd");
 }
