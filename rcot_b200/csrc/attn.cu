@@ -114,13 +114,17 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const rcot_attn_params p,
     const int col = t / c4, j0 = (t - col * c4) * 4;
     const float* wrow = p.w_out + (size_t)(co_begin + col) * C + h * c;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = 0; i < c; ++i) {
-      const float w = __ldg(wrow + i);
-      const float4 a = *reinterpret_cast<const float4*>(sA + i * c + j0);
-      acc.x = fmaf(w, a.x, acc.x);
-      acc.y = fmaf(w, a.y, acc.y);
-      acc.z = fmaf(w, a.z, acc.z);
-      acc.w = fmaf(w, a.w, acc.w);
+    for (int i = 0; i < c; i += 4) {                       // c % 8 == 0: one 16-byte load of W_out per four rows of A
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + i));
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(sA + (i + k) * c + j0);
+        acc.x = fmaf(wv[k], a.x, acc.x);
+        acc.y = fmaf(wv[k], a.y, acc.y);
+        acc.z = fmaf(wv[k], a.z, acc.z);
+        acc.w = fmaf(wv[k], a.w, acc.w);
+      }
     }
     *reinterpret_cast<float4*>(sM + col * c + j0) = acc;
   }
@@ -153,6 +157,7 @@ constexpr int AB_T = 6;    // largest register tile edge: ceil(96 / 16)
 // T = ceil(c/16); partial over this CTA's rows -> atomics into the zeroed scratch dA) and
 // dW_out[co,(h,i)] += sum_j P[co,(h,j)] A[i,j]  (2 x T outputs per thread, complete for these rows).
 // One CTA per (head, image) for all of it ran at < 1 IPC on 32 SMs; split by rows it fills the machine.
+template <int AB_TT>   // register tile edge ceil(c / 16), compile time: 2 (c <= 32), 3 (c <= 48), 6 (c <= 96)
 __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params p, const int ipc) {
   extern __shared__ __align__(16) float sm[];
   const int h = blockIdx.x, c = p.C / p.heads, C = p.C;
@@ -163,22 +168,22 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
   float* sW = sA + c * ca;      // [AB_CH*c] rows of W_out[:, head block]
   float* sP = sW + AB_CH * c;   // [AB_CH*c] rows of P[:, head block] of the current image
   const int tid = threadIdx.x;
-  const int T = (c + 15) >> 4;            // register tile edge (<= AB_T)
+  constexpr int T = AB_TT;               // register tile edge: T * 16 >= c
   const int nt = (c + T - 1) / T;         // tiles per dimension (<= 16)
   // dA role: thread (ti, tj) owns rows ti*T.., columns tj*T.. of dA
   const int ti = tid / nt, tj = tid - ti * nt;
   const bool da_on = ti < nt;
-  int ia[AB_T], ja[AB_T];
+  int ia[AB_TT], ja[AB_TT];
 #pragma unroll
-  for (int q = 0; q < AB_T; ++q) {
+  for (int q = 0; q < AB_TT; ++q) {
     ia[q] = min(ti * T + q, c - 1);       // clamped: duplicates are never stored
     ja[q] = min(tj * T + q, c - 1);
   }
   // dW_out role: thread (rg, ig) owns staged rows 2rg, 2rg+1 and head columns ig*T..
   const int rg = tid >> 4, ig = tid & 15;
-  int iw[AB_T];
+  int iw[AB_TT];
 #pragma unroll
-  for (int q = 0; q < AB_T; ++q) iw[q] = min(ig * T + q, c - 1) * ca;
+  for (int q = 0; q < AB_TT; ++q) iw[q] = min(ig * T + q, c - 1) * ca;
   for (int r = tid / c, i = tid - (tid / c) * c; r < AB_CH;) {   // (r, i) walk without a division per element
     sW[r * c + i] = (co0 + r < C) ? __ldg(p.w_out + (size_t)(co0 + r) * C + h * c + i) : 0.f;   // partial chunk: zeros
     i += 256;
@@ -187,9 +192,9 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
       ++r;
     }
   }
-  float aw[2][AB_T];            // dW_out partial sums, accumulated over this CTA's images: one atomic per entry
+  float aw[2][AB_TT];            // dW_out partial sums, accumulated over this CTA's images: one atomic per entry
 #pragma unroll
-  for (int q = 0; q < AB_T; ++q) aw[0][q] = aw[1][q] = 0.f;
+  for (int q = 0; q < AB_TT; ++q) aw[0][q] = aw[1][q] = 0.f;
   for (int bi = 0; bi < ipc; ++bi) {
     const int b = b0 + bi;
     if (b >= p.B) break;
@@ -214,31 +219,31 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
     }
     __syncthreads();
     if (da_on) {
-      float acc[AB_T][AB_T];
+      float acc[AB_TT][AB_TT];
 #pragma unroll
-      for (int x = 0; x < AB_T; ++x)
+      for (int x = 0; x < AB_TT; ++x)
 #pragma unroll
-        for (int y = 0; y < AB_T; ++y) acc[x][y] = 0.f;
+        for (int y = 0; y < AB_TT; ++y) acc[x][y] = 0.f;
 #pragma unroll 4
       for (int r = 0; r < AB_CH; ++r) {
-        float wv[AB_T], pv[AB_T];
+        float wv[AB_TT], pv[AB_TT];
 #pragma unroll
-        for (int q = 0; q < AB_T; ++q)
+        for (int q = 0; q < AB_TT; ++q)
           if (q < T) {
             wv[q] = sW[r * c + ia[q]];
             pv[q] = sP[r * c + ja[q]];
           }
 #pragma unroll
-        for (int x = 0; x < AB_T; ++x)
+        for (int x = 0; x < AB_TT; ++x)
 #pragma unroll
-          for (int y = 0; y < AB_T; ++y)
+          for (int y = 0; y < AB_TT; ++y)
             if (x < T && y < T) acc[x][y] = fmaf(wv[x], pv[y], acc[x][y]);
       }
       float* dA = p.dA + hb;
 #pragma unroll
-      for (int x = 0; x < AB_T; ++x)
+      for (int x = 0; x < AB_TT; ++x)
 #pragma unroll
-        for (int y = 0; y < AB_T; ++y)
+        for (int y = 0; y < AB_TT; ++y)
           if (x < T && y < T && ti * T + x < c && tj * T + y < c) atomicAdd(dA + (ti * T + x) * c + tj * T + y, acc[x][y]);
     }
     const float* p0 = sP + (2 * rg) * c;
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
     for (int j = 0; j < c; ++j) {
       const float x0 = p0[j], x1 = p1[j];
 #pragma unroll
-      for (int q = 0; q < AB_T; ++q)
+      for (int q = 0; q < AB_TT; ++q)
         if (q < T) {
           const float a = sA[iw[q] + j];
           aw[0][q] = fmaf(x0, a, aw[0][q]);
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(256) attn_bwd_p1_kernel(const rcot_attn_params
     const int co = co0 + 2 * rg + k;
     if (co < C) {
 #pragma unroll
-      for (int q = 0; q < AB_T; ++q)
+      for (int q = 0; q < AB_TT; ++q)
         if (q < T && ig * T + q < c) atomicAdd(p.dw_out + (size_t)co * C + h * c + ig * T + q, aw[k][q]);
     }
   }
@@ -375,7 +380,12 @@ extern "C" int rcot_attn_fwd(const rcot_attn_params* pp, rcot_stream_t st) {
   const int c = p.C / p.heads;
   RCOT_REQUIRE(c % 8 == 0 && p.C % 8 == 0, "attn_fwd: channels per head must be a multiple of 8");
   // rows of M per CTA: enough CTAs to cover the 148 SMs, a multiple of 8 rows each (packed 16-byte stores)
-  int nsplit = cdiv(148, (long)p.heads * p.B);
+  static int target = -1;             // A/B switch RCOT_ATTN_FWD_CTAS: CTAs the grid should reach (default 592 = 4 per SM)
+  if (target < 0) {
+    const char* e = getenv("RCOT_ATTN_FWD_CTAS");
+    target = e ? atoi(e) : 592;
+  }
+  int nsplit = cdiv(target, (long)p.heads * p.B);
   if (nsplit > p.C / 8) nsplit = p.C / 8;
   if (nsplit < 1) nsplit = 1;
   const int nco = round_up(cdiv(p.C, nsplit), 8);
@@ -407,7 +417,9 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
   const size_t smem2 = ((size_t)3 * c * c + 4 * c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_p1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_p1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_p1_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     if (e != cudaSuccess) {
@@ -427,7 +439,14 @@ extern "C" int rcot_attn_bwd(const rcot_attn_params* pp, rcot_stream_t st) {
   const int chunks = cdiv(p.C, AB_CH);
   const int ipc = ipc_env > 0 ? ipc_env : 1;
   dim3 grid1(p.heads, cdiv(p.B, ipc), chunks);
-  attn_bwd_p1_kernel<<<grid1, 256, smem1, (cudaStream_t)st>>>(p, ipc);
+  // the tile edge is a compile-time constant: at c = 48 (every level but two block kinds) the 6 x 6 register tile of the
+  // generic form carried 27 predicated-off FMAs per step and 128 registers
+  if (c <= 32)
+    attn_bwd_p1_kernel<2><<<grid1, 256, smem1, (cudaStream_t)st>>>(p, ipc);
+  else if (c <= 48)
+    attn_bwd_p1_kernel<3><<<grid1, 256, smem1, (cudaStream_t)st>>>(p, ipc);
+  else
+    attn_bwd_p1_kernel<6><<<grid1, 256, smem1, (cudaStream_t)st>>>(p, ipc);
   rc = check_launch("attn_bwd(p1)");
   if (rc) return rc;
   dim3 grid2(p.heads, p.B);
