@@ -541,6 +541,41 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
+
+// Split-K factor.  These kernels fill an SM's shared memory, so their CTAs are resident ONE per SM and a grid runs in
+// rounds of 148: 297 CTAs (what "two per SM, rounded up" gave for the 1x1 weight gradients with three tiles) take three
+// rounds, the last one for a single CTA -- ncu showed such launches at 2.7 TB/s.  Cost model: rounds x (chunks per CTA +
+// a fixed per-CTA cost of ~8 chunk times for TMEM allocation, pipeline fill and the atomic epilogue); the smallest
+// cost wins.  RCOT_PK_SPLIT=0 restores the round-1 rule (A/B switch).
+static int pick_split(long tiles, int total_chunks, int maxS, int old_target) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("RCOT_PK_SPLIT");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (maxS < 1) maxS = 1;
+  if (!enabled) {
+    int S = (int)((old_target + tiles - 1) / tiles);
+    if (S > maxS) S = maxS;
+    if (S < 1) S = 1;
+    return cdiv(total_chunks, cdiv(total_chunks, S));
+  }
+  const int sms = 148, fixed = 8;
+  long best_cost = -1;
+  int best = 1;
+  for (int S = 1; S <= maxS && (S == 1 || tiles * S <= 4L * sms); ++S) {
+    const int per = cdiv(total_chunks, S);
+    const int Se = cdiv(total_chunks, per);
+    const long rounds = (tiles * Se + sms - 1) / sms;
+    const long cost = rounds * (per + fixed);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = Se;
+    }
+  }
+  return best;
+}
+
 template <int TERMS, int MT, int NBT, int ABF = 0>
 static int launch_pk_mm_t(const rcot_pk_params& p, int BN, cudaStream_t stream) {
   const int Ntot = p.CB1;
@@ -549,11 +584,7 @@ static int launch_pk_mm_t(const rcot_pk_params& p, int BN, cudaStream_t stream) 
   const int cpi = HW / KC;
   const int total_chunks = cpi * p.B;
   const long tiles = (long)mgroups * nt;
-  int S = (int)((148 + tiles - 1) / tiles);     // one CTA per SM: every split adds CA x N atomics to the epilogue
-  int maxS = total_chunks / 4;
-  if (maxS < 1) maxS = 1;
-  if (S > maxS) S = maxS;
-  if (S < 1) S = 1;
+  int S = pick_split(tiles, total_chunks, total_chunks / 4, 148);   // every split adds CA x N atomics to the epilogue
   int per_cta = cdiv(total_chunks, S);
   S = cdiv(total_chunks, per_cta);
   constexpr int TA = (TERMS > 1) ? 2 : 1;
@@ -829,11 +860,7 @@ static int try_pk_tma_t(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   const int total_chunks = p.per_image ? cpi : cpi * p.B;
   const int zdim = p.groups * (p.per_image ? p.B : 1);
   const long tiles = (long)mt * nt * zdim;
-  int S = (int)((2 * 148 + tiles - 1) / tiles);
-  int maxS = total_chunks / 4;
-  if (maxS < 1) maxS = 1;
-  if (S > maxS) S = maxS;
-  if (S < 1) S = 1;
+  int S = pick_split(tiles, total_chunks, total_chunks / 4, 2 * 148);
   int per_cta = cdiv(total_chunks, S);
   S = cdiv(total_chunks, per_cta);
   constexpr int TA = (TERMS > 1) ? 2 : 1;
@@ -886,11 +913,7 @@ static int launch_pk_n(const rcot_pk_params& p, cudaStream_t stream, int tr) {
   const int total_chunks = p.per_image ? cpi : cpi * p.B;
   const int zdim = p.groups * (p.per_image ? p.B : 1);
   const long tiles = (long)mt * nt * zdim;
-  int S = (int)((2 * 148 + tiles - 1) / tiles);
-  int maxS = total_chunks / 4;
-  if (maxS < 1) maxS = 1;
-  if (S > maxS) S = maxS;
-  if (S < 1) S = 1;
+  int S = pick_split(tiles, total_chunks, total_chunks / 4, 2 * 148);
   int per_cta = cdiv(total_chunks, S);
   S = cdiv(total_chunks, per_cta);
   constexpr int TA = (TERMS > 1) ? 2 : 1;
