@@ -192,6 +192,14 @@ int rcot_gdfn_fwd(const rcot_gdfn_params* p, rcot_stream_t stream);
  * rcot_gdfn_fwd launched with debug & 16, as [22 warps][8] uint64 (n = 176).  Synchronises the device. */
 int rcot_gdfn_profile_read(unsigned long long* out, int n);
 
+/* ---------------------------------------------------------------- convolutions that END in three channels
+ * Direct FP32 kernel (csrc/conv3.cu) for Net_Restormer.py:326 (output conv 96 -> 3, forward: weight [3, Cin, k, k]) and
+ * for the data gradient of a conv that STARTS from three channels (:117 patch_embed, :443 F_net features.0; dgrad = 1:
+ * `in` is dL/dy with Cin = the conv's Cout channels, weight [Cin, 3, k, k], taps flipped).  Stride 1, pad (k-1)/2,
+ * k in {3, 5}; optional residual [B, 3, H, W] added to the result (the `+ inp_img` of T_net.forward). */
+int rcot_conv_to3(const float* in, int64_t in_bs, const float* weight, int dgrad, float* out, int64_t out_bs,
+                  const float* residual, int64_t res_bs, int B, int Cin, int H, int W, int ks, rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- MDTA phase 1 as ONE kernel (csrc/mdta_fused.cu)
  * Net_Restormer.py:29-41 (qkv 1x1 conv of LN(x), depthwise 3x3, q k^T and the row norms of F.normalize) with pre, q
  * and k kept on chip: per 8x16-pixel tile (+1-pixel halo) the 3C channels are walked in slices of 32 (tcgen05 GEMM from

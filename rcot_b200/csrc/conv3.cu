@@ -1,0 +1,155 @@
+// conv3.cu -- direct CUDA-core kernels for the convolutions with THREE channels on one side
+// (Net_Restormer.py:117 patch_embed 3->48, :326 output 96->3, :443 F_net features.0 3->64 k5, and their gradients).
+// As implicit GEMMs on tcgen05 these are the worst launches of a training step: N = 3 is padded to 16 accumulator
+// columns while the producers still gather Cin*k*k im2col columns per pixel tile (the 64 -> 3, 5x5 data gradient of
+// F_net's first layer took 1.02 ms, the 96 -> 3 output conv 0.54 ms at 128x128, batch 32: 4-7 % of either roofline).
+// The arithmetic is small (<= 5 GFLOP), so a register-tiled FP32 kernel is the right tool:
+//
+//   conv_to3: out[b, c, y, x] = sum_{ci, ky, kx} in[b, ci, y + ky - p, x + kx - p] * Wf[c, ci, ky, kx],  c < 3
+//     forward  (output conv):            Wf[c, ci, ky, kx] = weight[c, ci, ky, kx]
+//     data gradient of a 3 -> Cout conv: Wf[c, o, ky, kx]  = weight[o, c, k-1-ky, k-1-kx]      (stride 1, pad (k-1)/2)
+//   A CTA owns a 64 x 16-pixel tile of one image, a thread a 1 x 4 strip and all three outputs; the input tile (+halo)
+//   goes through shared memory in chunks of 8 channels, the whole (re-laid-out) weight tensor sits in shared memory:
+//   per (channel, ky) a thread issues 2 + 4 16-byte shared loads for 60 FMAs (k = 5; 2 + 3 for 36 at k = 3).
+#include "../../include/rcot_b200.h"
+#include "common.cuh"
+
+namespace rcot {
+
+constexpr int C3_TW = 64, C3_TH = 16;   // pixel tile
+constexpr int C3_CC = 8;                // channels per shared-memory chunk
+
+template <int KS>
+struct C3Geom {
+  static constexpr int P = (KS - 1) / 2;
+  static constexpr int ROWS = C3_TH + KS - 1;
+  static constexpr int TWP = 72;                          // row stride (floats): >= 64 + KS - 1, multiple of 4
+  static constexpr int WROW = (3 * KS + 3) / 4 * 4;       // taps of one (channel, ky): [kx][c], padded to 16 bytes
+  static constexpr int CHUNK = C3_CC * ROWS * TWP;        // floats of one data chunk
+};
+
+template <int KS>
+__global__ void __launch_bounds__(256) conv_to3_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ w,
+                                                       int w_sc, int w_sci, int flip, float* __restrict__ out, int64_t out_bs,
+                                                       const float* __restrict__ res, int64_t res_bs, int Cin, int H, int W) {
+  using G = C3Geom<KS>;
+  extern __shared__ __align__(16) float c3sm[];
+  float* wS = c3sm;                                   // [Cin][KS][WROW]
+  float* dS = c3sm + (size_t)Cin * KS * G::WROW;      // [C3_CC][ROWS][TWP]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, y0 = blockIdx.y * C3_TH, x0 = blockIdx.x * C3_TW;
+  const int HW = H * W;
+  for (int e = tid; e < Cin * KS * G::WROW; e += 256) {
+    const int ci = e / (KS * G::WROW), r = e - ci * (KS * G::WROW);
+    const int ky = r / G::WROW, t = r - ky * G::WROW;
+    float v = 0.f;
+    if (t < 3 * KS) {
+      const int kx = t / 3, c = t - kx * 3;
+      const int wy = flip ? KS - 1 - ky : ky, wx = flip ? KS - 1 - kx : kx;
+      v = __ldg(w + (size_t)c * w_sc + (size_t)ci * w_sci + wy * KS + wx);
+    }
+    wS[e] = v;
+  }
+  const int sx = tid & 15, ry = tid >> 4;             // strip of 4 pixels, row of the tile
+  float acc[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+  const float* inb = in + (size_t)b * in_bs;
+  for (int c0 = 0; c0 < Cin; c0 += C3_CC) {
+    __syncthreads();                                  // previous chunk consumed (and, first time, wS complete)
+    for (int e = tid; e < C3_CC * G::ROWS * (C3_TW + KS - 1); e += 256) {
+      const int cc = e / (G::ROWS * (C3_TW + KS - 1)), r = e - cc * (G::ROWS * (C3_TW + KS - 1));
+      const int yy = r / (C3_TW + KS - 1), xx = r - yy * (C3_TW + KS - 1);
+      const int gy = y0 + yy - G::P, gx = x0 + xx - G::P, ci = c0 + cc;
+      float v = 0.f;
+      if (ci < Cin && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) v = __ldg(inb + (size_t)ci * HW + (size_t)gy * W + gx);
+      dS[(cc * G::ROWS + yy) * G::TWP + xx] = v;
+    }
+    __syncthreads();
+    const int nc = min(C3_CC, Cin - c0);
+    for (int cc = 0; cc < nc; ++cc) {
+      const float* wrow = wS + (size_t)(c0 + cc) * KS * G::WROW;
+      const float* drow = dS + (cc * G::ROWS + ry) * G::TWP + 4 * sx;
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        float d[8];
+        const float4 d0 = *reinterpret_cast<const float4*>(drow + ky * G::TWP);
+        const float4 d1 = *reinterpret_cast<const float4*>(drow + ky * G::TWP + 4);
+        d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+        float wv[G::WROW];
+#pragma unroll
+        for (int q = 0; q < G::WROW / 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(wrow + ky * G::WROW + 4 * q);
+          wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[c][i] = fmaf(wv[kx * 3 + c], d[i + kx], acc[c][i]);
+      }
+    }
+  }
+  const int y = y0 + ry, xs = x0 + 4 * sx;
+  if (y >= H || xs >= W) return;
+  const bool vec = (W % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                   (res == nullptr || (res_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const size_t o = (size_t)c * HW + (size_t)y * W + xs;
+    float* op = out + (size_t)b * out_bs + o;
+    const float* rp = res ? res + (size_t)b * res_bs + o : nullptr;
+    if (vec) {                                        // W % 4 == 0 and xs % 4 == 0: the whole strip is inside the row
+      float4 v = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+      if (rp) {
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp));
+        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+      }
+      *reinterpret_cast<float4*>(op) = v;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (xs + i < W) op[i] = acc[c][i] + (rp ? __ldg(rp + i) : 0.f);
+    }
+  }
+}
+
+template <int KS>
+static int launch_conv_to3(const float* in, int64_t in_bs, const float* w, int w_sc, int w_sci, int flip, float* out, int64_t out_bs,
+                           const float* res, int64_t res_bs, int B, int Cin, int H, int W, cudaStream_t st) {
+  using G = C3Geom<KS>;
+  const size_t smem = ((size_t)Cin * KS * G::WROW + G::CHUNK) * sizeof(float);
+  RCOT_REQUIRE(smem <= 200 * 1024, "conv_to3: %d input channels need %zu bytes of shared memory", Cin, smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_to3_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv_to3: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
+      return RCOT_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  dim3 grid(cdiv(W, C3_TW), cdiv(H, C3_TH), B);
+  conv_to3_kernel<KS><<<grid, 256, smem, st>>>(in, in_bs, w, w_sc, w_sci, flip, out, out_bs, res, res_bs, Cin, H, W);
+  return check_launch("conv_to3");
+}
+
+}  // namespace rcot
+
+using namespace rcot;
+
+extern "C" int rcot_conv_to3(const float* in, int64_t in_bs, const float* weight, int dgrad, float* out, int64_t out_bs,
+                             const float* residual, int64_t res_bs, int B, int Cin, int H, int W, int ks, rcot_stream_t st) {
+  RCOT_REQUIRE(in && weight && out && B > 0 && B <= 65535 && Cin > 0 && H > 0 && W > 0, "conv_to3: bad arguments");
+  RCOT_REQUIRE(ks == 3 || ks == 5, "conv_to3: kernel size 3 or 5 (got %d)", ks);
+  RCOT_REQUIRE(cdiv(H, C3_TH) <= 65535, "conv_to3: image too tall");
+  // forward: weight [3, Cin, k, k]; data gradient: weight [Cin(= the conv's Cout), 3, k, k], taps flipped
+  const int kk = ks * ks;
+  const int w_sc = dgrad ? kk : Cin * kk, w_sci = dgrad ? 3 * kk : kk;
+  if (ks == 3)
+    return launch_conv_to3<3>(in, in_bs, weight, w_sc, w_sci, dgrad ? 1 : 0, out, out_bs, residual, res_bs, B, Cin, H, W, (cudaStream_t)st);
+  return launch_conv_to3<5>(in, in_bs, weight, w_sc, w_sci, dgrad ? 1 : 0, out, out_bs, residual, res_bs, B, Cin, H, W, (cudaStream_t)st);
+}

@@ -34,6 +34,10 @@ FUSED_GDFN_ALWAYS = _FG == "1"
 # instead of pm_gemm -> dw_plain -> pk_gemm.  RCOT_FUSED_MDTA: "auto" (default) = wherever pre and qkv are not kept for
 # the backward, "1" = always (the kernel then also writes pre, q and k), "0" = never.  Measured at C=96, 128x128, B=32:
 # 0.47 vs 0.56 ms (0.23 vs 0.33 ms at C=48); 0.82 vs 0.56 ms when pre and qkv must also be written -- hence "auto".
+# Direct FP32 kernels (csrc/conv3.cu) for the convs that end in three channels (output conv, data gradients of
+# patch_embed and of F_net's first layer) instead of the implicit GEMM with N = 3 padded to 16: RCOT_DIRECT_CONV3=0 is
+# the A/B switch back.
+DIRECT_CONV3 = os.environ.get("RCOT_DIRECT_CONV3", "1") != "0"
 _FM = os.environ.get("RCOT_FUSED_MDTA", "auto")
 FUSED_MDTA = _FM != "0"
 FUSED_MDTA_ALWAYS = _FM == "1"
@@ -482,15 +486,22 @@ class ConvSpec:
 def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True, need_res_grad=True):
     """Dense conv (stride 1, no bias), optional concat input [x, x2] and residual epilogue."""
     ps = cs.ps
-    y = ops.pm_gemm(x, ps.pack(cs.name, cs.kf), cs.Cout, ks=cs.ks, pad=cs.pad, x2=x2, residual=residual,
-                    tap_major=cs.kf.endswith("_tap"))
+    direct3 = DIRECT_CONV3 and cs.ks in (3, 5) and cs.pad == cs.ks // 2 and x2 is None and ops.TERMS == 3
+    if direct3 and cs.Cout == 3 and x.dtype == torch.float32:
+        y = ops.conv_to3(x, ps.p[cs.name], residual=residual)           # output conv 96 -> 3: direct FP32 kernel
+    else:
+        y = ops.pm_gemm(x, ps.pack(cs.name, cs.kf), cs.Cout, ks=cs.ks, pad=cs.pad, x2=x2, residual=residual,
+                        tap_major=cs.kf.endswith("_tap"))
     if tape is not None and tape.enabled:
         def bwd(dy):
             Cin = cs.Cin
             ops.pk_gemm(dy, x, ps.g[cs.name].view(cs.Cout, -1), ldo=Cin * cs.ks * cs.ks, ks=cs.ks, pad=cs.pad, b2=x2)
             if need_dx:
-                dx = ops.pm_gemm(dy, ps.pack(cs.name, cs.kd), Cin, ks=cs.ks, pad=cs.pad, mode=1,
-                                 out_hw=(x.shape[2], x.shape[3]), tap_major=cs.kd.endswith("_tap"))
+                if direct3 and Cin == 3 and dy.dtype == torch.float32:
+                    dx = ops.conv_to3(dy, ps.p[cs.name], dgrad=True)    # patch_embed's data gradient (3 channels)
+                else:
+                    dx = ops.pm_gemm(dy, ps.pack(cs.name, cs.kd), Cin, ks=cs.ks, pad=cs.pad, mode=1,
+                                     out_hw=(x.shape[2], x.shape[3]), tap_major=cs.kd.endswith("_tap"))
                 if x2 is None:
                     tape.add_grad(x, dx)
                 else:

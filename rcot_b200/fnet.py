@@ -117,8 +117,12 @@ class FnetProgram:
                                     out_hw=(src.shape[2], src.shape[3]), mask_y=src, slope=SLOPE,
                                     tap_major=self.kd[idx].endswith("_tap"))
             elif need_dx:
-                dx = ops.pm_gemm(delta, ps.pack(w + "weight", self.kd[idx]), cin, ks=k, stride=s, pad=p, mode=1,
-                                 out_hw=(src.shape[2], src.shape[3]), tap_major=self.kd[idx].endswith("_tap"))
+                from . import engine
+                if engine.DIRECT_CONV3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3:
+                    dx = ops.conv_to3(delta, ps.p[w + "weight"], dgrad=True)   # 64 -> 3, 5x5: direct FP32 kernel
+                else:
+                    dx = ops.pm_gemm(delta, ps.pack(w + "weight", self.kd[idx]), cin, ks=k, stride=s, pad=p, mode=1,
+                                     out_hw=(src.shape[2], src.shape[3]), tap_major=self.kd[idx].endswith("_tap"))
         return dx, (deltas + [d_h1, d_h2, d_f] if keep_deltas else None)
 
     # ------------------------------------------------------------------ the three uses

@@ -346,6 +346,21 @@ def gdfn_fwd(x, blob, hid, ln=None, residual=True, stats_out=False, save=False):
     return y, u, g
 
 
+def conv_to3(x, weight, dgrad=False, residual=None):
+    """Direct kernel for a stride-1 'same' conv that ends in 3 channels: forward with ``weight`` [3, Cin, k, k], or
+    (dgrad) the data gradient of a 3 -> Cout conv given dL/dy and its ``weight`` [Cout, 3, k, k].  k in {3, 5}."""
+    B, Cin, H, W = x.shape
+    ks = weight.shape[2]
+    if (weight.shape[1] if dgrad else weight.shape[0]) != 3 or (weight.shape[0] if dgrad else weight.shape[1]) != Cin:
+        raise ValueError(f"conv_to3: weight {tuple(weight.shape)} does not match x {tuple(x.shape)} (dgrad={dgrad})")
+    out = torch.empty(B, 3, H, W, device=x.device, dtype=torch.float32)
+    _lib.check(L().rcot_conv_to3(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(_f32(weight)), int(bool(dgrad)), _ptr(out),
+                                 C.c_int64(3 * H * W), _ptr(residual),
+                                 C.c_int64(_img_view(residual, "residual") if residual is not None else 0),
+                                 B, Cin, H, W, ks, _stream()), "conv_to3")
+    return out
+
+
 class MdtaP1Params(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_bs", C.c_int64), ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p),
                 ("ln_beta", C.c_void_p), ("wblob", C.c_void_p), ("v", C.c_void_p), ("v_bs", C.c_int64),
@@ -701,6 +716,7 @@ pm_gemm = _instrument("pm_gemm", _pm_bytes)(pm_gemm)
 pk_gemm = _instrument("pk_gemm", lambda a, k, r: _nb(a[0], a[1], k.get("b2"), a[2]))(pk_gemm)
 gdfn_fwd = _instrument("gdfn_fwd", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(gdfn_fwd)
 mdta_p1 = _instrument("mdta_p1", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(mdta_p1)
+conv_to3 = _instrument("conv_to3", lambda a, k, r: _nb(a[0], a[1], r, k.get("residual")))(conv_to3)
 ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
 ln_fwd = _instrument("ln_fwd", lambda a, k, r: _nb(a[0], r[0]))(ln_fwd)
 ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)

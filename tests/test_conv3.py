@@ -1,0 +1,35 @@
+"""Direct FP32 kernels for the convolutions that end in three channels (csrc/conv3.cu) against fp64 F.conv2d:
+the output conv (Net_Restormer.py:326, with the `+ inp_img` residual), the data gradient of patch_embed (:117) and of
+F_net's first layer (:443, 5x5), at ragged sizes (tiles cut by the image border, widths that are not multiples of 4)
+and at the benchmarked 128x128."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, rtol=1e-4, atol=1e-5):
+    got = got.detach().cpu().double()
+    err = (got - ref).abs()
+    tol = atol * max(1.0, ref.abs().max().item()) + rtol * ref.abs()
+    assert (err > tol).sum().item() == 0, f"max err {err.max().item():.3e} at scale {ref.abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("B,Cin,H,W,ks", [(2, 96, 128, 128, 3), (3, 96, 24, 40, 3), (1, 20, 17, 30, 3), (2, 64, 128, 128, 5),
+                                          (2, 64, 32, 32, 5), (1, 7, 19, 70, 5)])
+@pytest.mark.parametrize("dgrad", [False, True])
+def test_conv_to3(cuda_lib, B, Cin, H, W, ks, dgrad):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(B + Cin + H + ks)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    res = torch.randn(B, 3, H, W, generator=g)
+    if dgrad:
+        w = torch.randn(Cin, 3, ks, ks, generator=g) / (Cin * ks * ks) ** 0.5       # the conv maps 3 -> Cin channels
+        ref = F.conv_transpose2d(x.double(), w.double(), padding=ks // 2)          # = its data gradient
+        got = ops.conv_to3(x.cuda(), w.cuda(), dgrad=True)
+    else:
+        w = torch.randn(3, Cin, ks, ks, generator=g) / (Cin * ks * ks) ** 0.5
+        ref = F.conv2d(x.double(), w.double(), padding=ks // 2) + res.double()
+        got = ops.conv_to3(x.cuda(), w.cuda(), residual=res.cuda())
+    _close(got, ref)
