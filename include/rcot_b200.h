@@ -200,6 +200,14 @@ int rcot_gdfn_profile_read(unsigned long long* out, int n);
 int rcot_conv_to3(const float* in, int64_t in_bs, const float* weight, int dgrad, float* out, int64_t out_bs,
                   const float* residual, int64_t res_bs, int B, int Cin, int H, int W, int ks, rcot_stream_t stream);
 
+/* Direct FP32 kernel for a conv that STARTS from three channels (Net_Restormer.py:117 patch_embed 3 -> 48 k3, :443 F_net
+ * features.0 3 -> 64 k5): weight [Cout, 3, k, k], stride 1, pad (k-1)/2, k in {3, 5}; optional bias [Cout] and
+ * LeakyReLU(slope) (act = 1), or -- the bias-free tangent pass of the gradient penalty -- the LeakyReLU-derivative mask
+ * of a previous forward's output mask_y [B, Cout, H, W]: out *= (mask_y > 0 ? 1 : slope). */
+int rcot_conv_from3(const float* in, int64_t in_bs, const float* weight, const float* bias, float* out, int64_t out_bs,
+                    const float* mask_y, int64_t mask_bs, int act, float slope, int B, int Cout, int H, int W, int ks,
+                    rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- MDTA phase 1 as ONE kernel (csrc/mdta_fused.cu)
  * Net_Restormer.py:29-41 (qkv 1x1 conv of LN(x), depthwise 3x3, q k^T and the row norms of F.normalize) with pre, q
  * and k kept on chip: per 8x16-pixel tile (+1-pixel halo) the 3C channels are walked in slices of 32 (tcgen05 GEMM from

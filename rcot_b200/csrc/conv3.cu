@@ -137,6 +137,127 @@ static int launch_conv_to3(const float* in, int64_t in_bs, const float* w, int w
   return check_launch("conv_to3");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv_from3: out[b, o, y, x] = act( sum_{c < 3, ky, kx} in[b, c, y + ky - p, x + kx - p] * W[o, c, ky, kx] + bias[o] )
+// (patch_embed 3 -> 48 k3, F_net features.0 3 -> 64 k5 with bias + LeakyReLU, or its bias-free tangent pass with the
+// LeakyReLU-derivative mask of a previous forward).  K = 27 / 75 is two or three tcgen05 K chunks of mostly padding; here
+// a thread keeps the 3 x k x (4 + k - 1) input window of its 1 x 4 pixel strip in REGISTERS and walks the output
+// channels: per channel 3k^2 broadcast weights from shared memory, 12 k^2 FMAs, one 16-byte store.
+template <int KS>
+__global__ void __launch_bounds__(256) conv_from3_kernel(const float* __restrict__ in, int64_t in_bs, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int64_t out_bs,
+                                                         const float* __restrict__ mask_y, int64_t mask_bs, int act, float slope,
+                                                         int Cout, int H, int W) {
+  using G = C3Geom<KS>;
+  constexpr int WIN = 4 + KS - 1;                     // window columns of a strip
+  constexpr int WPO = (3 * KS * KS + 3) / 4 * 4;      // weights per output channel, padded to 16 bytes
+  extern __shared__ __align__(16) float c3sm[];
+  float* wS = c3sm;                                   // [Cout][WPO]
+  float* dS = c3sm + (size_t)Cout * WPO;              // [3][ROWS][TWP]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, y0 = blockIdx.y * C3_TH, x0 = blockIdx.x * C3_TW;
+  const int HW = H * W;
+  for (int e = tid; e < Cout * WPO; e += 256) {
+    const int o = e / WPO, t = e - o * WPO;
+    wS[e] = t < 3 * KS * KS ? __ldg(w + (size_t)o * 3 * KS * KS + t) : 0.f;
+  }
+  const float* inb = in + (size_t)b * in_bs;
+  for (int e = tid; e < 3 * G::ROWS * (C3_TW + KS - 1); e += 256) {
+    const int c = e / (G::ROWS * (C3_TW + KS - 1)), r = e - c * (G::ROWS * (C3_TW + KS - 1));
+    const int yy = r / (C3_TW + KS - 1), xx = r - yy * (C3_TW + KS - 1);
+    const int gy = y0 + yy - G::P, gx = x0 + xx - G::P;
+    float v = 0.f;
+    if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) v = __ldg(inb + (size_t)c * HW + (size_t)gy * W + gx);
+    dS[(c * G::ROWS + yy) * G::TWP + xx] = v;
+  }
+  __syncthreads();
+  const int sx = tid & 15, ry = tid >> 4;
+  float d[3][KS][WIN];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const float* drow = dS + (c * G::ROWS + ry + ky) * G::TWP + 4 * sx;
+      const float4 d0 = *reinterpret_cast<const float4*>(drow);
+      const float4 d1 = *reinterpret_cast<const float4*>(drow + 4);
+      const float t8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int i = 0; i < WIN; ++i) d[c][ky][i] = t8[i];
+    }
+  const int y = y0 + ry, xs = x0 + 4 * sx;
+  if (y >= H || xs >= W) return;
+  const bool vec = (W % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                   (mask_y == nullptr || (mask_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(mask_y) & 15) == 0));
+  const size_t pix = (size_t)y * W + xs;
+  for (int o = 0; o < Cout; ++o) {
+    const float* wo = wS + (size_t)o * WPO;
+    float acc[4];
+    const float bv = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = bv;
+#pragma unroll
+    for (int q = 0; q < WPO / 4; ++q) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wo + 4 * q);
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = 4 * q + k;                      // compile time: (c, ky, kx) of this weight
+        if (t < 3 * KS * KS) {
+          const int c = t / (KS * KS), ky = (t / KS) % KS, kx = t % KS;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv[k], d[c][ky][i + kx], acc[i]);
+        }
+      }
+    }
+    float* op = out + (size_t)b * out_bs + (size_t)o * HW + pix;
+    const float* mp = mask_y ? mask_y + (size_t)b * mask_bs + (size_t)o * HW + pix : nullptr;
+    if (vec) {
+      float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (mp) {
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mp));
+        v.x *= m4.x > 0.f ? 1.f : slope; v.y *= m4.y > 0.f ? 1.f : slope;
+        v.z *= m4.z > 0.f ? 1.f : slope; v.w *= m4.w > 0.f ? 1.f : slope;
+      } else if (act) {
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+      }
+      *reinterpret_cast<float4*>(op) = v;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (xs + i < W) {
+          float v = acc[i];
+          if (mp) v *= __ldg(mp + i) > 0.f ? 1.f : slope;
+          else if (act) v = v > 0.f ? v : v * slope;
+          op[i] = v;
+        }
+    }
+  }
+}
+
+template <int KS>
+static int launch_conv_from3(const float* in, int64_t in_bs, const float* w, const float* bias, float* out, int64_t out_bs,
+                             const float* mask_y, int64_t mask_bs, int act, float slope, int B, int Cout, int H, int W,
+                             cudaStream_t st) {
+  using G = C3Geom<KS>;
+  constexpr int WPO = (3 * KS * KS + 3) / 4 * 4;
+  const size_t smem = ((size_t)Cout * WPO + 3 * G::ROWS * G::TWP) * sizeof(float);
+  RCOT_REQUIRE(smem <= 200 * 1024, "conv_from3: %d output channels need %zu bytes of shared memory", Cout, smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_from3_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv_from3: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
+      return RCOT_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  dim3 grid(cdiv(W, C3_TW), cdiv(H, C3_TH), B);
+  conv_from3_kernel<KS><<<grid, 256, smem, st>>>(in, in_bs, w, bias, out, out_bs, mask_y, mask_bs, act, slope, Cout, H, W);
+  return check_launch("conv_from3");
+}
+
 }  // namespace rcot
 
 using namespace rcot;
@@ -152,4 +273,16 @@ extern "C" int rcot_conv_to3(const float* in, int64_t in_bs, const float* weight
   if (ks == 3)
     return launch_conv_to3<3>(in, in_bs, weight, w_sc, w_sci, dgrad ? 1 : 0, out, out_bs, residual, res_bs, B, Cin, H, W, (cudaStream_t)st);
   return launch_conv_to3<5>(in, in_bs, weight, w_sc, w_sci, dgrad ? 1 : 0, out, out_bs, residual, res_bs, B, Cin, H, W, (cudaStream_t)st);
+}
+
+extern "C" int rcot_conv_from3(const float* in, int64_t in_bs, const float* weight, const float* bias, float* out, int64_t out_bs,
+                               const float* mask_y, int64_t mask_bs, int act, float slope, int B, int Cout, int H, int W, int ks,
+                               rcot_stream_t st) {
+  RCOT_REQUIRE(in && weight && out && B > 0 && B <= 65535 && Cout > 0 && H > 0 && W > 0, "conv_from3: bad arguments");
+  RCOT_REQUIRE(ks == 3 || ks == 5, "conv_from3: kernel size 3 or 5 (got %d)", ks);
+  RCOT_REQUIRE(!(mask_y && (bias || act)), "conv_from3: the mask epilogue (tangent pass) takes neither bias nor activation");
+  RCOT_REQUIRE(cdiv(H, C3_TH) <= 65535, "conv_from3: image too tall");
+  if (ks == 3)
+    return launch_conv_from3<3>(in, in_bs, weight, bias, out, out_bs, mask_y, mask_bs, act, slope, B, Cout, H, W, (cudaStream_t)st);
+  return launch_conv_from3<5>(in, in_bs, weight, bias, out, out_bs, mask_y, mask_bs, act, slope, B, Cout, H, W, (cudaStream_t)st);
 }

@@ -31,11 +31,11 @@ constexpr int PM_THREADS = (PM_PROD_WARPS + 1 + 4) * 32;  // producers, MMA warp
 // from there.  The ring holds 64 KB in flight per SM -- with register prefetch the producers keep 32 KB in flight,
 // which caps a 1 us-latency stream at ~60 % of the HBM rate.  (32 separate 512-byte cp.async.bulk copies per chunk
 // were measured SLOWER than the register path: the copy engine is request-bound at that size.)
-constexpr int PM_RAW = 4;
+constexpr int PM_RAW = 8;                                       // most slots of the raw ring (g.nraw are used: 4 by default)
 constexpr uint32_t PM_RAW_BYTES = KC * 128 * sizeof(float);   // 16 KB: 32 channels x 128 pixels
 
 struct PmGeom {
-  int Ktot, nk, BN, passes, stages, tiles_m, tiles_per_img, flat, c1_aligned;
+  int Ktot, nk, BN, passes, stages, tiles_m, tiles_per_img, flat, c1_aligned, nraw;
   // parity classes of a stride-2 transposed conv (dgrad of the 4x4 stride-2 convs): an output pixel only sees the
   // taps with ky = (y + pad) mod 2 (+2), kx likewise -- 4 of 16 -- so tiles hold pixels of ONE (y&1, x&1) class and
   // the K loop runs over that class's 4 taps only (nk = 4 * C1/32 chunks) instead of multiplying 75 % zeros.
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
       mbar_init(&acc_empty[i], 4);                  // one arrival per epilogue warp
     }
     if (TMA) {
-      for (int i = 0; i < PM_RAW; ++i) {
+      for (int i = 0; i < g.nraw; ++i) {
         mbar_init(&raw_full[i], 1);                 // the loader's expect_tx arrival (+ the copies' bytes)
         mbar_init(&raw_empty[i], PM_PROD_WARPS);    // one arrival per producer warp
       }
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
           tensor_g2s_3d(raw_ring + (size_t)rs * PM_RAW_BYTES, tm, pix0, kc, b, &raw_full[rs]);
         }
         __syncwarp();
-        if (++rs == PM_RAW) {
+        if (++rs == g.nraw) {
           rs = 0;
           rph ^= 1;
         }
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(PM_THREADS + (TMA ? 32 : 0), 1)
           mbar_arrive(&full_bar[s]);
           mbar_arrive(&raw_empty[rs]);       // every lane's raw values have been consumed (stored) by now
         }
-        if (++rs == PM_RAW) {
+        if (++rs == g.nraw) {
           rs = 0;
           rph ^= 1;
         }
@@ -802,7 +802,15 @@ static int launch_pm(const rcot_pm_params& p, cudaStream_t stream) {
   const size_t stage_bytes = (size_t)TAA * op_tile_bytes(128) + (size_t)TA * op_tile_bytes(g.BN);
   const size_t ln_bytes = LN ? (size_t)g.nk * KC * 2 * sizeof(float) : 0;
   g.c1_aligned = (p.C2 == 0 || p.C1 % 16 == 0) ? 1 : 0;
-  const size_t raw_bytes = TMA ? (size_t)PM_RAW * PM_RAW_BYTES : 0;
+  static int nraw_env = -1;           // A/B switch RCOT_PM_RAW: slots of the raw fp32 ring (16 KB each; default 4)
+  if (nraw_env < 0) {
+    const char* e = getenv("RCOT_PM_RAW");
+    nraw_env = e ? atoi(e) : 4;
+    if (nraw_env < 2) nraw_env = 2;
+    if (nraw_env > PM_RAW) nraw_env = PM_RAW;
+  }
+  g.nraw = nraw_env;
+  const size_t raw_bytes = TMA ? (size_t)g.nraw * PM_RAW_BYTES : 0;
   const size_t lnb_bytes = LNB ? (4 * 32 * 33 + 4 * 512) * sizeof(float) : 0;    // static shared memory of the LNB epilogue
   int stages = (int)((196 * 1024 - raw_bytes - ln_bytes - lnb_bytes) / stage_bytes);
   if (stages > PM_MAX_STAGES) stages = PM_MAX_STAGES;

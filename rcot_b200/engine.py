@@ -489,6 +489,8 @@ def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True, need_r
     direct3 = DIRECT_CONV3 and cs.ks in (3, 5) and cs.pad == cs.ks // 2 and x2 is None and ops.TERMS == 3
     if direct3 and cs.Cout == 3 and x.dtype == torch.float32:
         y = ops.conv_to3(x, ps.p[cs.name], residual=residual)           # output conv 96 -> 3: direct FP32 kernel
+    elif direct3 and cs.Cin == 3 and residual is None and x.dtype == torch.float32:
+        y = ops.conv_from3(x, ps.p[cs.name])                            # patch_embed 3 -> 48
     else:
         y = ops.pm_gemm(x, ps.pack(cs.name, cs.kf), cs.Cout, ks=cs.ks, pad=cs.pad, x2=x2, residual=residual,
                         tap_major=cs.kf.endswith("_tap"))

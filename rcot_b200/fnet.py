@@ -62,7 +62,15 @@ class FnetProgram:
         t = x
         for li, (idx, cin, cout, k, s, p, has_b) in enumerate(CONVS):
             w = f"features.{idx}."
-            if masks is None:
+            from . import engine
+            if (li == 0 and engine.DIRECT_CONV3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3
+                    and t.dtype == torch.float32):
+                # features.0 (3 -> 64, 5x5): direct FP32 kernel instead of an implicit GEMM with K = 75
+                if masks is None:
+                    t = ops.conv_from3(t, ps.p[w + "weight"], bias=ps.p[w + "bias"] if has_b else None, act=True, slope=SLOPE)
+                else:
+                    t = ops.conv_from3(t, ps.p[w + "weight"], mask_y=masks[li + 1], slope=SLOPE)
+            elif masks is None:
                 t = ops.pm_gemm(t, ps.pack(w + "weight", self.kf[idx]), cout, ks=k, stride=s, pad=p,
                                 bias=ps.p[w + "bias"] if has_b else None, act=True, slope=SLOPE,
                                 tap_major=self.kf[idx].endswith("_tap"))

@@ -361,6 +361,21 @@ def conv_to3(x, weight, dgrad=False, residual=None):
     return out
 
 
+def conv_from3(x, weight, bias=None, act=False, slope=0.2, mask_y=None):
+    """Direct kernel for a stride-1 'same' conv that starts from 3 channels (``weight`` [Cout, 3, k, k], k in {3, 5}):
+    optional bias + LeakyReLU, or the LeakyReLU-derivative mask of a previous forward (tangent pass)."""
+    B, Cin, H, W = x.shape
+    Cout, ks = weight.shape[0], weight.shape[2]
+    if Cin != 3 or weight.shape[1] != 3:
+        raise ValueError(f"conv_from3: weight {tuple(weight.shape)} / x {tuple(x.shape)} are not a 3-channel conv")
+    out = torch.empty(B, Cout, H, W, device=x.device, dtype=torch.float32)
+    _lib.check(L().rcot_conv_from3(_ptr(x), C.c_int64(_img_view(x, "x")), _ptr(_f32(weight)), _ptr(bias), _ptr(out),
+                                   C.c_int64(Cout * H * W), _ptr(mask_y),
+                                   C.c_int64(_img_view(mask_y, "mask_y") if mask_y is not None else 0), int(bool(act)),
+                                   C.c_float(slope), B, Cout, H, W, ks, _stream()), "conv_from3")
+    return out
+
+
 class MdtaP1Params(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_bs", C.c_int64), ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p),
                 ("ln_beta", C.c_void_p), ("wblob", C.c_void_p), ("v", C.c_void_p), ("v_bs", C.c_int64),
@@ -717,6 +732,7 @@ pk_gemm = _instrument("pk_gemm", lambda a, k, r: _nb(a[0], a[1], k.get("b2"), a[
 gdfn_fwd = _instrument("gdfn_fwd", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(gdfn_fwd)
 mdta_p1 = _instrument("mdta_p1", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(mdta_p1)
 conv_to3 = _instrument("conv_to3", lambda a, k, r: _nb(a[0], a[1], r, k.get("residual")))(conv_to3)
+conv_from3 = _instrument("conv_from3", lambda a, k, r: _nb(a[0], a[1], r, k.get("mask_y")))(conv_from3)
 ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
 ln_fwd = _instrument("ln_fwd", lambda a, k, r: _nb(a[0], r[0]))(ln_fwd)
 ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)

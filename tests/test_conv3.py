@@ -33,3 +33,25 @@ def test_conv_to3(cuda_lib, B, Cin, H, W, ks, dgrad):
         ref = F.conv2d(x.double(), w.double(), padding=ks // 2) + res.double()
         got = ops.conv_to3(x.cuda(), w.cuda(), residual=res.cuda())
     _close(got, ref)
+
+
+@pytest.mark.parametrize("B,Cout,H,W,ks", [(2, 64, 128, 128, 5), (3, 48, 24, 40, 3), (1, 20, 17, 30, 3), (2, 64, 32, 32, 5),
+                                           (1, 7, 19, 70, 5), (2, 48, 128, 128, 3)])
+@pytest.mark.parametrize("mode", ["plain", "bias_act", "mask"])
+def test_conv_from3(cuda_lib, B, Cout, H, W, ks, mode):
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(B + Cout + H + ks)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(Cout, 3, ks, ks, generator=g) / (3 * ks * ks) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    my = torch.randn(B, Cout, H, W, generator=g)
+    ref = F.conv2d(x.double(), w.double(), padding=ks // 2)
+    if mode == "bias_act":
+        ref = F.leaky_relu(ref + bias.double().view(1, -1, 1, 1), 0.2)
+        got = ops.conv_from3(x.cuda(), w.cuda(), bias=bias.cuda(), act=True, slope=0.2)
+    elif mode == "mask":
+        ref = ref * torch.where(my.double() > 0, 1.0, 0.2)
+        got = ops.conv_from3(x.cuda(), w.cuda(), mask_y=my.cuda(), slope=0.2)
+    else:
+        got = ops.conv_from3(x.cuda(), w.cuda())
+    _close(got, ref)
