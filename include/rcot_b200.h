@@ -208,6 +208,12 @@ int rcot_conv_from3(const float* in, int64_t in_bs, const float* weight, const f
                     const float* mask_y, int64_t mask_bs, int act, float slope, int B, int Cout, int H, int W, int ks,
                     rcot_stream_t stream);
 
+/* Weight gradient of a stride-1 'same' conv with three channels on one side (k in {3, 5}), ACCUMULATED into dw:
+ * from3 = 0: the conv ends in 3 channels (weight / dw [3, Cm, k, k]): many = its input [B, Cm, H, W], three = dL/dy;
+ * from3 = 1: the conv starts from 3 channels (weight / dw [Cm, 3, k, k]): many = dL/dy [B, Cm, H, W], three = its input. */
+int rcot_conv3_wgrad(const float* many, int64_t many_bs, const float* three, int64_t three_bs, float* dw, int from3, int B,
+                     int Cm, int H, int W, int ks, rcot_stream_t stream);
+
 /* ---------------------------------------------------------------- MDTA phase 1 as ONE kernel (csrc/mdta_fused.cu)
  * Net_Restormer.py:29-41 (qkv 1x1 conv of LN(x), depthwise 3x3, q k^T and the row norms of F.normalize) with pre, q
  * and k kept on chip: per 8x16-pixel tile (+1-pixel halo) the 3C channels are walked in slices of 32 (tcgen05 GEMM from

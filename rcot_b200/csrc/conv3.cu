@@ -258,6 +258,111 @@ static int launch_conv_from3(const float* in, int64_t in_bs, const float* w, con
   return check_launch("conv_from3");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv3_wgrad: weight gradient of a conv with three channels on one side (stride 1, pad (k-1)/2):
+//     acc(cm, c, ty, tx) = sum_{b, y, x} three[b, c, y, x] * many[b, cm, y + ty - p, x + tx - p]
+//   conv that ENDS in 3 channels (output conv; weight [3, Cm, k, k]):  many = the conv's input, three = dL/dy,
+//       dW[c, cm, ty, tx] += acc(cm, c, ty, tx)
+//   conv that STARTS from 3 channels (patch_embed, F_net features.0; weight [Cm, 3, k, k]):  many = dL/dy, three = the input,
+//       dW[cm, c, k-1-ty, k-1-tx] += acc(cm, c, ty, tx)
+// As a pixel-as-K GEMM the 3-channel operand was padded to a 128-row MMA tile (0.6 ms for the output conv at 128x128,
+// batch 32).  Here a CTA owns (32 channels of `many`, one image, a band of 32 rows); thread = (channel, ty) keeps its
+// 3k sums in registers and walks the band row by row: the k rows of `many` it needs live in a rolling shared-memory
+// buffer (one new row per step, odd row stride = conflict-free across channels), the three-channel row as one float4 per
+// pixel (broadcast loads); per pixel 1 + 1 shared loads for 3k FMAs.  One atomicAdd per sum and CTA at the end.
+constexpr int W3_CH = 32, W3_BAND = 32;
+
+template <int KS>
+__global__ void __launch_bounds__(W3_CH* KS) conv3_wgrad_kernel(const float* __restrict__ many, int64_t many_bs,
+                                                                const float* __restrict__ three, int64_t three_bs,
+                                                                float* __restrict__ dw, int from3, int Cm, int H, int W) {
+  constexpr int P = (KS - 1) / 2;
+  extern __shared__ __align__(16) float w3sm[];
+  const int RS = (W + 2 * P) | 1;                      // odd row stride (floats)
+  float* mS = w3sm;                                    // [KS slots][W3_CH][RS]
+  float4* tS = reinterpret_cast<float4*>(w3sm + ((size_t)KS * W3_CH * RS + 3) / 4 * 4);   // [W] (t0, t1, t2, 0)
+  const int tid = threadIdx.x, nthr = W3_CH * KS;
+  const int cm_l = tid % W3_CH, ty = tid / W3_CH;
+  const int c0 = blockIdx.x * W3_CH, b = blockIdx.y, y0 = blockIdx.z * W3_BAND;
+  const int HW = H * W;
+  const float* mb = many + (size_t)b * many_bs;
+  const float* tb = three + (size_t)b * three_bs;
+  auto load_row = [&](int yy) {                        // row yy of the 32 channels into slot yy mod KS (zeros outside)
+    const int slot = ((yy % KS) + KS) % KS;
+    float* dst = mS + (size_t)slot * W3_CH * RS;
+    const bool in_y = (unsigned)yy < (unsigned)H;
+    for (int e = tid; e < W3_CH * (W + 2 * P); e += nthr) {
+      const int ch = e / (W + 2 * P), xx = e - ch * (W + 2 * P);
+      const int gx = xx - P, cm = c0 + ch;
+      float v = 0.f;
+      if (in_y && cm < Cm && (unsigned)gx < (unsigned)W) v = __ldg(mb + (size_t)cm * HW + (size_t)yy * W + gx);
+      dst[ch * RS + xx] = v;
+    }
+  };
+  float acc[KS][3];
+#pragma unroll
+  for (int i = 0; i < KS; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+  for (int yy = y0 - P; yy < y0 + P; ++yy) load_row(yy);          // rows y0-P .. y0+P-1
+  const int yend = min(y0 + W3_BAND, H);
+  for (int y = y0; y < yend; ++y) {
+    __syncthreads();                                   // previous row consumed
+    load_row(y + P);
+    for (int x = tid; x < W; x += nthr)
+      tS[x] = make_float4(__ldg(tb + (size_t)y * W + x), __ldg(tb + (size_t)HW + (size_t)y * W + x),
+                          __ldg(tb + 2 * (size_t)HW + (size_t)y * W + x), 0.f);
+    __syncthreads();
+    const int yy = y + ty - P;
+    const float* mrow = mS + (size_t)(((yy % KS) + KS) % KS) * W3_CH * RS + cm_l * RS;   // index xx = x + tx
+    float win[KS];
+#pragma unroll
+    for (int i = 0; i < KS - 1; ++i) win[i + 1] = mrow[i];
+    for (int x = 0; x < W; ++x) {
+#pragma unroll
+      for (int i = 0; i < KS - 1; ++i) win[i] = win[i + 1];
+      win[KS - 1] = mrow[x + KS - 1];
+      const float4 t4 = tS[x];
+#pragma unroll
+      for (int tx = 0; tx < KS; ++tx) {
+        acc[tx][0] = fmaf(t4.x, win[tx], acc[tx][0]);
+        acc[tx][1] = fmaf(t4.y, win[tx], acc[tx][1]);
+        acc[tx][2] = fmaf(t4.z, win[tx], acc[tx][2]);
+      }
+    }
+  }
+  const int cm = c0 + cm_l;
+  if (cm >= Cm) return;
+#pragma unroll
+  for (int tx = 0; tx < KS; ++tx)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t o = from3 ? (((size_t)cm * 3 + c) * KS + (KS - 1 - ty)) * KS + (KS - 1 - tx)
+                             : (((size_t)c * Cm + cm) * KS + ty) * KS + tx;
+      atomicAdd(dw + o, acc[tx][c]);
+    }
+}
+
+template <int KS>
+static int launch_conv3_wgrad(const float* many, int64_t many_bs, const float* three, int64_t three_bs, float* dw, int from3, int B,
+                              int Cm, int H, int W, cudaStream_t st) {
+  constexpr int P = (KS - 1) / 2;
+  const int RS = (W + 2 * P) | 1;
+  const size_t smem = (((size_t)KS * W3_CH * RS + 3) / 4 * 4) * sizeof(float) + (size_t)W * sizeof(float4);
+  RCOT_REQUIRE(smem <= 200 * 1024, "conv3_wgrad: rows of %d pixels need %zu bytes of shared memory", W, smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv3_wgrad: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
+      return RCOT_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  dim3 grid(cdiv(Cm, W3_CH), B, cdiv(H, W3_BAND));
+  conv3_wgrad_kernel<KS><<<grid, W3_CH * KS, smem, st>>>(many, many_bs, three, three_bs, dw, from3, Cm, H, W);
+  return check_launch("conv3_wgrad");
+}
+
 }  // namespace rcot
 
 using namespace rcot;
@@ -285,4 +390,13 @@ extern "C" int rcot_conv_from3(const float* in, int64_t in_bs, const float* weig
   if (ks == 3)
     return launch_conv_from3<3>(in, in_bs, weight, bias, out, out_bs, mask_y, mask_bs, act, slope, B, Cout, H, W, (cudaStream_t)st);
   return launch_conv_from3<5>(in, in_bs, weight, bias, out, out_bs, mask_y, mask_bs, act, slope, B, Cout, H, W, (cudaStream_t)st);
+}
+
+extern "C" int rcot_conv3_wgrad(const float* many, int64_t many_bs, const float* three, int64_t three_bs, float* dw, int from3,
+                                int B, int Cm, int H, int W, int ks, rcot_stream_t st) {
+  RCOT_REQUIRE(many && three && dw && B > 0 && B <= 65535 && Cm > 0 && H > 0 && W > 0, "conv3_wgrad: bad arguments");
+  RCOT_REQUIRE(ks == 3 || ks == 5, "conv3_wgrad: kernel size 3 or 5 (got %d)", ks);
+  RCOT_REQUIRE(cdiv(H, W3_BAND) <= 65535, "conv3_wgrad: image too tall");
+  if (ks == 3) return launch_conv3_wgrad<3>(many, many_bs, three, three_bs, dw, from3 ? 1 : 0, B, Cm, H, W, (cudaStream_t)st);
+  return launch_conv3_wgrad<5>(many, many_bs, three, three_bs, dw, from3 ? 1 : 0, B, Cm, H, W, (cudaStream_t)st);
 }

@@ -497,7 +497,13 @@ def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True, need_r
     if tape is not None and tape.enabled:
         def bwd(dy):
             Cin = cs.Cin
-            ops.pk_gemm(dy, x, ps.g[cs.name].view(cs.Cout, -1), ldo=Cin * cs.ks * cs.ks, ks=cs.ks, pad=cs.pad, b2=x2)
+            w3 = direct3 and dy.dtype == torch.float32 and x.dtype == torch.float32 and x.shape[3] <= 256
+            if w3 and cs.Cout == 3:
+                ops.conv3_wgrad(x, dy, ps.g[cs.name], from3=False)      # output conv: three = dL/dy
+            elif w3 and Cin == 3:
+                ops.conv3_wgrad(dy, x, ps.g[cs.name], from3=True)       # patch_embed: three = the image
+            else:
+                ops.pk_gemm(dy, x, ps.g[cs.name].view(cs.Cout, -1), ldo=Cin * cs.ks * cs.ks, ks=cs.ks, pad=cs.pad, b2=x2)
             if need_dx:
                 if direct3 and Cin == 3 and dy.dtype == torch.float32:
                     dx = ops.conv_to3(dy, ps.p[cs.name], dgrad=True)    # patch_embed's data gradient (3 channels)

@@ -117,7 +117,12 @@ class FnetProgram:
             src = acts[li]
             deltas[li] = delta
             if wgrad:
-                ops.pk_gemm(delta, src, ps.g[w + "weight"].view(cout, -1), ldo=cin * k * k, ks=k, stride=s, pad=p)
+                from . import engine
+                if (li == 0 and engine.DIRECT_CONV3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3
+                        and src.shape[3] <= 256):
+                    ops.conv3_wgrad(delta, src, ps.g[w + "weight"], from3=True)     # features.0: direct FP32 kernel
+                else:
+                    ops.pk_gemm(delta, src, ps.g[w + "weight"].view(cout, -1), ldo=cin * k * k, ks=k, stride=s, pad=p)
                 if has_b:
                     ops.channel_sum(delta, ps.g[w + "bias"])
             if li > 0:
@@ -160,7 +165,12 @@ class FnetProgram:
         ops.gp_coef(sumsq, coef, loss, Bg)
         u0 = ops.axpby(g, None, a_vec=coef)
         _, tang = self.forward(u0, masks=acts)
+        from . import engine
         for li, (idx, cin, cout, k, s, p, has_b) in enumerate(CONVS):
+            if (li == 0 and engine.DIRECT_CONV3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3
+                    and tang[li].shape[3] <= 256):
+                ops.conv3_wgrad(deltas[li], tang[li], ps.g[f"features.{idx}.weight"], from3=True)
+                continue
             ops.pk_gemm(deltas[li], tang[li], ps.g[f"features.{idx}.weight"].view(cout, -1), ldo=cin * k * k, ks=k,
                         stride=s, pad=p)
         d_h1, d_h2, d_f = deltas[10], deltas[11], deltas[12]

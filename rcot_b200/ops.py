@@ -376,6 +376,21 @@ def conv_from3(x, weight, bias=None, act=False, slope=0.2, mask_y=None):
     return out
 
 
+def conv3_wgrad(many, three, dw, from3):
+    """dw += weight gradient of a stride-1 'same' conv with 3 channels on one side.  ``from3``: the conv maps 3 -> Cm
+    channels (dw [Cm, 3, k, k]; many = dL/dy, three = the conv's input); else Cm -> 3 (dw [3, Cm, k, k]; many = the conv's
+    input, three = dL/dy)."""
+    B, Cm, H, W = many.shape
+    ks = dw.shape[2]
+    want = (Cm, 3, ks, ks) if from3 else (3, Cm, ks, ks)
+    if tuple(dw.shape) != want or tuple(three.shape) != (B, 3, H, W):
+        raise ValueError(f"conv3_wgrad: dw {tuple(dw.shape)} / three {tuple(three.shape)} do not match many {tuple(many.shape)}")
+    _lib.check(L().rcot_conv3_wgrad(_ptr(many), C.c_int64(_img_view(many, "many")), _ptr(three),
+                                    C.c_int64(_img_view(three, "three")), _ptr(_f32(dw)), int(bool(from3)), B, Cm, H, W, ks,
+                                    _stream()), "conv3_wgrad")
+    return dw
+
+
 class MdtaP1Params(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_bs", C.c_int64), ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p),
                 ("ln_beta", C.c_void_p), ("wblob", C.c_void_p), ("v", C.c_void_p), ("v_bs", C.c_int64),
@@ -733,6 +748,7 @@ gdfn_fwd = _instrument("gdfn_fwd", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(
 mdta_p1 = _instrument("mdta_p1", lambda a, k, r: _nb(a[0], r[0], r[1], r[2]))(mdta_p1)
 conv_to3 = _instrument("conv_to3", lambda a, k, r: _nb(a[0], a[1], r, k.get("residual")))(conv_to3)
 conv_from3 = _instrument("conv_from3", lambda a, k, r: _nb(a[0], a[1], r, k.get("mask_y")))(conv_from3)
+conv3_wgrad = _instrument("conv3_wgrad", lambda a, k, r: _nb(a[0], a[1]))(conv3_wgrad)
 ln_stats = _instrument("ln_stats", lambda a, k, r: _nb(a[0], r))(ln_stats)
 ln_fwd = _instrument("ln_fwd", lambda a, k, r: _nb(a[0], r[0]))(ln_fwd)
 ln_bwd = _instrument("ln_bwd", lambda a, k, r: _nb(a[0], a[1], k.get("dy"), r))(ln_bwd)

@@ -55,3 +55,22 @@ def test_conv_from3(cuda_lib, B, Cout, H, W, ks, mode):
     else:
         got = ops.conv_from3(x.cuda(), w.cuda())
     _close(got, ref)
+
+
+@pytest.mark.parametrize("B,Cm,H,W,ks", [(2, 96, 128, 128, 3), (3, 48, 24, 40, 3), (1, 20, 17, 30, 3), (2, 64, 128, 128, 5),
+                                         (2, 64, 32, 32, 5), (1, 7, 19, 70, 5), (2, 40, 72, 16, 5)])
+@pytest.mark.parametrize("from3", [False, True])
+def test_conv3_wgrad(cuda_lib, B, Cm, H, W, ks, from3):
+    """dW of a conv with three channels on one side vs fp64 autograd; accumulates onto a non-zero buffer."""
+    from rcot_b200 import ops
+    g = torch.Generator().manual_seed(B + Cm + H + ks + int(from3))
+    cin, cout = (3, Cm) if from3 else (Cm, 3)
+    x = torch.randn(B, cin, H, W, generator=g).double()
+    dy = torch.randn(B, cout, H, W, generator=g).double()
+    w = torch.randn(cout, cin, ks, ks, generator=g).double().requires_grad_(True)
+    (F.conv2d(x, w, padding=ks // 2) * dy).sum().backward()
+    dw0 = torch.randn(cout, cin, ks, ks, generator=g)
+    dw = dw0.clone().cuda()
+    many, three = (dy, x) if from3 else (x, dy)
+    ops.conv3_wgrad(many.float().cuda(), three.float().cuda(), dw, from3=from3)
+    _close(dw, dw0.double() + w.grad, rtol=2e-4, atol=2e-5)
