@@ -38,6 +38,10 @@ FUSED_GDFN_ALWAYS = _FG == "1"
 # patch_embed and of F_net's first layer) instead of the implicit GEMM with N = 3 padded to 16: RCOT_DIRECT_CONV3=0 is
 # the A/B switch back.
 DIRECT_CONV3 = os.environ.get("RCOT_DIRECT_CONV3", "1") != "0"
+# The matching direct WEIGHT-gradient kernel (rcot_conv3_wgrad: rolling shared-memory rows, 3k register sums per thread)
+# is parity-tested but measured SLOWER than the pixel-as-K GEMMs it would replace: 6 launches = 2.66 ms against 1.81 ms
+# per step at 128x128, batch 32 (96/160-thread CTAs walking a serial 128-pixel loop are latency-bound) -> opt-in.
+DIRECT_WGRAD3 = os.environ.get("RCOT_DIRECT_WGRAD3", "0") == "1"
 _FM = os.environ.get("RCOT_FUSED_MDTA", "auto")
 FUSED_MDTA = _FM != "0"
 FUSED_MDTA_ALWAYS = _FM == "1"
@@ -497,7 +501,7 @@ def conv_fwd(cs: ConvSpec, x, tape, x2=None, residual=None, need_dx=True, need_r
     if tape is not None and tape.enabled:
         def bwd(dy):
             Cin = cs.Cin
-            w3 = direct3 and dy.dtype == torch.float32 and x.dtype == torch.float32 and x.shape[3] <= 256
+            w3 = DIRECT_WGRAD3 and direct3 and dy.dtype == torch.float32 and x.dtype == torch.float32 and x.shape[3] <= 256
             if w3 and cs.Cout == 3:
                 ops.conv3_wgrad(x, dy, ps.g[cs.name], from3=False)      # output conv: three = dL/dy
             elif w3 and Cin == 3:

@@ -118,7 +118,7 @@ class FnetProgram:
             deltas[li] = delta
             if wgrad:
                 from . import engine
-                if (li == 0 and engine.DIRECT_CONV3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3
+                if (li == 0 and engine.DIRECT_WGRAD3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3
                         and src.shape[3] <= 256):
                     ops.conv3_wgrad(delta, src, ps.g[w + "weight"], from3=True)     # features.0: direct FP32 kernel
                 else:
@@ -167,7 +167,7 @@ class FnetProgram:
         _, tang = self.forward(u0, masks=acts)
         from . import engine
         for li, (idx, cin, cout, k, s, p, has_b) in enumerate(CONVS):
-            if (li == 0 and engine.DIRECT_CONV3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3
+            if (li == 0 and engine.DIRECT_WGRAD3 and cin == 3 and s == 1 and k in (3, 5) and p == k // 2 and ops.TERMS == 3
                     and tang[li].shape[3] <= 256):
                 ops.conv3_wgrad(deltas[li], tang[li], ps.g[f"features.{idx}.weight"], from3=True)
                 continue
