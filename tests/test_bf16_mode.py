@@ -155,7 +155,7 @@ def test_full_iteration_bf16_mode(cuda_lib, bf16_mode):
     # tensors T(x) is perturbed ~100x more (1e-3 instead of 1e-5 relative), more near-zero gradients of the potential
     # flip sign, and -- because an fp32-level change of summation order (split-K atomics) can move a stored value to the
     # neighbouring bf16 -- the SAME binary on the SAME inputs spreads: seven runs on a B200 gave 624.6 ... 644.8 against
-    # the oracle's 638.3 (-2.1 % ... +1.0 %, sigma 1.2 %; scripts/gpu/call_bf16rep2.sh). 5e-2 is 4 sigma of that spread.
+    # the oracle's 638.3 (-2.1 % ... +1.0 %, sigma 1.2 %; scripts/gpu/diag_bf16_spread.sh). 5e-2 is 4 sigma of that spread.
     assert abs(r["loss_T"].item() - o["loss_T"]) <= 5e-2 * abs(o["loss_T"]), (r["loss_T"].item(), o["loss_T"])
     # Flat T gradient.  Inside the iteration dL/dout carries dF/dout of the potential after its two sign-like steps (see
     # above), so -- like tests/test_bench_size.py -- the mode's 5e-2 is asserted on the exact half: the bf16-mode T
