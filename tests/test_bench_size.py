@@ -88,7 +88,9 @@ def test_full_iteration_128(cuda_lib, paired):
     # moves by +-10*lr whatever |g|; ~zero gradients flip sign under any change of summation order), so it carries
     # that step's noise: an absolute +-1..2 at P=128 whatever the size of the other terms (2e-4 relative at P=32,
     # tests/test_train_step.py)
-    assert abs(got[2] - want[2]) <= 5e-3 * abs(want[2])
+    # (seven B200 runs per mode: paired 1704.9 -0.6 ... +0.8, unpaired 638.3 -1.5 ... +0.9 -- the noise is absolute, so
+    # the bound is too: 5 is > 5 sigma of it and still 0.3 % / 0.8 % of the loss)
+    assert abs(got[2] - want[2]) <= max(5e-3 * abs(want[2]), 5.0)
     # F-sub inside the iteration: L_F = mean f(fake) - mean f(real) ~ 5e-5 at initialisation -- its gradient is a ~1 %
     # residue of two cancelling terms, so the 1e-5-level difference between our T(x) and the oracle's shows up as ~1e-2
     _cmp_grads(Fp.ps, step.capture["F"], o["grads_F"], 3e-2, "F-sub (own T output)", tol_tensor=6e-2)
@@ -201,7 +203,11 @@ def test_batch32_equals_sum_of_shards(cuda_lib):
     for name, a, b in (("T", gT, sT), ("F", gF, sF), ("GP", gGP, sGP)):
         errs[name] = ((a - b).double().norm() / b.double().norm()).item()
         print(f"batch-32 vs 16 x batch-2, {name}: rel-L2 {errs[name]:.3e}")
-    assert errs["T"] < 5e-5, errs
+    # Summation order is the only difference, but it is not a fixed one: the weight gradients and MDTA's Grams are
+    # accumulated with atomics, so the figure moves from run to run (1.9e-5 and 4.3e-5 in two runs of the same binary).
+    # A wrong tile loop / N slice / saved tensor shows up as O(1e-2..1); the bounds leave 4x over the largest value seen.
+    assert errs["T"] < 2e-4, errs
     # the critic gradient is a ~1 % residue of the cancelling real / fake contributions (L_F ~ 5e-5 at initialisation):
-    # fp32 summation-order noise of either term shows up amplified by that ratio
-    assert errs["F"] < 2e-2 and errs["GP"] < 2e-3, errs
+    # fp32 summation-order noise of either term shows up amplified by that ratio; the penalty gradient passes through
+    # LeakyReLU sign masks, where ONE flipped element of a delta tensor moves that tensor by 1.6e-3 (scripts/diag_fnet.py)
+    assert errs["F"] < 2e-2 and errs["GP"] < 5e-3, errs
