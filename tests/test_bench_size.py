@@ -204,10 +204,11 @@ def test_batch32_equals_sum_of_shards(cuda_lib):
         errs[name] = ((a - b).double().norm() / b.double().norm()).item()
         print(f"batch-32 vs 16 x batch-2, {name}: rel-L2 {errs[name]:.3e}")
     # Summation order is the only difference, but it is not a fixed one: the weight gradients and MDTA's Grams are
-    # accumulated with atomics, so the figure moves from run to run (1.9e-5 and 4.3e-5 in two runs of the same binary).
+    # accumulated with atomics, so the figure moves from run to run (1.9e-5, 4.3e-5, 4.4e-5 in three runs of the same binary).
     # A wrong tile loop / N slice / saved tensor shows up as O(1e-2..1); the bounds leave 4x over the largest value seen.
     assert errs["T"] < 2e-4, errs
     # the critic gradient is a ~1 % residue of the cancelling real / fake contributions (L_F ~ 5e-5 at initialisation):
     # fp32 summation-order noise of either term shows up amplified by that ratio; the penalty gradient passes through
     # LeakyReLU sign masks, where ONE flipped element of a delta tensor moves that tensor by 1.6e-3 (scripts/diag_fnet.py)
-    assert errs["F"] < 2e-2 and errs["GP"] < 5e-3, errs
+    # (seen over the round's runs: F 5.5e-3, 5.9e-3, 1.0e-2; GP 6.6e-4, 9.4e-4)
+    assert errs["F"] < 5e-2 and errs["GP"] < 5e-3, errs
